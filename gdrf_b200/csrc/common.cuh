@@ -1,0 +1,150 @@
+// Shared device/host helpers for the gdrf_b200 CUDA path (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gdrf {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// "Tiled plane" operand format.
+//
+// Every matrix that feeds the tensor pipe is stored as P bf16 planes (x ~= p0 + p1 [+ p2], an
+// error-compensated split of the fp32 value) and each plane is cut into 128-row x 64-column
+// blocks of 16 KB.  Inside a block the bytes are laid out exactly as a SWIZZLE_128B UMMA
+// shared-memory tile expects them (rows of 128 B, 8-row groups of 1 KB, 16-byte chunk index
+// XORed with row%8), so a block -- or its upper / lower 64-row half -- goes HBM -> SMEM with one
+// cp.async.bulk and no tensor map.  The same block serves as a K-major operand (contraction
+// along its 64 columns) and as an MN-major operand (contraction along its rows).
+// Blocks are ordered [row_tile][col_block].
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_R = 128;
+constexpr int TILE_C = 64;
+constexpr int TILE_ELEMS = TILE_R * TILE_C;   // 8192 bf16 = 16 KB
+
+__host__ __device__ __forceinline__ int tile_off(int r, int c) {
+  return ((r >> 3) << 9) + ((r & 7) << 6) + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7));
+}
+
+struct PlaneMat {
+  bf16* base;            // plane 0
+  long long plane_stride;  // elements between planes
+  int row_tiles;         // rows / 128
+  int col_blocks;        // cols / 64
+  __host__ __device__ __forceinline__ long long block_off(int rt, int cb) const {
+    return ((long long)rt * col_blocks + cb) * TILE_ELEMS;
+  }
+  __device__ __forceinline__ bf16* elem(int plane, int r, int c) const {
+    return base + plane * plane_stride + block_off(r >> 7, c >> 6) + tile_off(r & 127, c & 63);
+  }
+  __host__ __device__ long long plane_elems() const { return (long long)row_tiles * col_blocks * TILE_ELEMS; }
+};
+
+// error-compensated split of an fp32 value into up to three bf16 planes
+template <int P>
+__device__ __forceinline__ void split_bf16(float x, bf16 (&out)[P]) {
+  float r = x;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    out[p] = __float2bfloat16_rn(r);
+    r -= __bfloat162float(out[p]);
+  }
+}
+
+// 8 consecutive fp32 values -> one 16-byte packet per plane
+template <int P>
+__device__ __forceinline__ void split8(const float* v, uint4 (&pk)[P]) {
+  unsigned short h[P][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float r = v[i];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      bf16 b = __float2bfloat16_rn(r);
+      r -= __bfloat162float(b);
+      h[p][i] = __bfloat16_as_ushort(b);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    pk[p].x = h[p][0] | ((uint32_t)h[p][1] << 16);
+    pk[p].y = h[p][2] | ((uint32_t)h[p][3] << 16);
+    pk[p].z = h[p][4] | ((uint32_t)h[p][5] << 16);
+    pk[p].w = h[p][6] | ((uint32_t)h[p][7] << 16);
+  }
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short h) {
+  return __uint_as_float(((uint32_t)h) << 16);
+}
+
+// sum of P planes for 8 consecutive elements (16-byte packets)
+template <int P>
+__device__ __forceinline__ void join8(const uint4 (&pk)[P], float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int p = P - 1; p >= 0; --p) {   // small planes first
+    uint32_t w[4] = {pk[p].x, pk[p].y, pk[p].z, pk[p].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] += bf16_bits_to_float((unsigned short)(w[i] & 0xffff));
+      v[2 * i + 1] += bf16_bits_to_float((unsigned short)(w[i] >> 16));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  `scratch` holds >= 32 T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+  if (warp == 0) r = warp_sum(r);
+  return r;
+}
+
+__host__ __device__ __forceinline__ long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// kernel ids shared with the host API (include/gdrf_b200.h)
+enum { KERNEL_RBF = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2 };
+constexpr int MAX_D = 8;
+
+// k(r2)/variance and d k / d r2 / variance for the three isotropic kernels
+// (pyro.contrib.gp.kernels.{RBF,Matern32,Matern52}; r = sqrt(r2 + 1e-12) as in Isotropy._scaled_dist)
+template <typename T>
+__host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_dr2) {
+  if (kid == KERNEL_RBF) {
+    k = exp(T(-0.5) * r2);
+    dk_dr2 = T(-0.5) * k;
+  } else if (kid == KERNEL_MATERN32) {
+    T s = sqrt(T(3) * (r2 + T(1e-12)));
+    T e = exp(-s);
+    k = (T(1) + s) * e;
+    dk_dr2 = T(-1.5) * e;
+  } else {
+    T s = sqrt(T(5) * (r2 + T(1e-12)));
+    T e = exp(-s);
+    k = (T(1) + s + (T(5) / T(3)) * r2) * e;
+    dk_dr2 = -(T(5) / T(6)) * (T(1) + s) * e;
+  }
+}
+
+}  // namespace gdrf

@@ -1,0 +1,534 @@
+// C ABI of gdrf_b200 (include/gdrf_b200.h): workspace planning and the per-step kernel schedule.
+#include "../../include/gdrf_b200.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "linalg.cuh"
+#include "policies.cuh"
+#include "stages.cuh"
+
+using namespace gdrf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+#define CU(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) return fail(2, "CUDA error: %s (line %lld)", cudaGetErrorString(e_), __LINE__); \
+  } while (0)
+#define LAUNCH_CHECK() CU(cudaGetLastError())
+
+constexpr int DEFAULT_SMS = 148;
+
+struct Plan {
+  // dims
+  int D, M, Mp, MB, JT, MT, K, V, RTmax;
+  long long ncp;          // padded rows per chunk (stride of the [K][ncp] arrays)
+  int chunk_rows;
+  // persistent
+  size_t acc, ck, du, dphi, dz, c5, phisum, status_pad;
+  size_t L64, Linv64, tmpA, tmpB;
+  size_t linv_pl, st_pl;
+  // per chunk
+  size_t kxz_pl, w_pl, r_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
+  size_t wsq, srow, arow, cnt, gv0, floc, q, mu, fvar, theta, g_loc, g2, g1;
+  size_t total;
+  long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
+};
+
+size_t bump(size_t& off, size_t bytes) {
+  size_t o = off;
+  off += (bytes + 255) & ~(size_t)255;
+  return o;
+}
+
+int make_plan(const gdrf_shape* s, Plan& p) {
+  if (!s) return fail(1, "null shape%s");
+  if (s->d < 1 || s->d > MAX_D) return fail(1, "d must be in [1, 8]%s");
+  if (s->m < 1 || s->m > 4096) return fail(1, "m must be in [1, 4096]%s");
+  if (s->k < 1 || s->k > 128) return fail(1, "k must be in [1, 128]%s");
+  if (s->v < 1) return fail(1, "v must be positive%s");
+  if (s->n_local < 0) return fail(1, "n_local must be non-negative%s");
+  if (s->ls_dim != 1 && s->ls_dim != s->d) return fail(1, "ls_dim must be 1 or d%s");
+  if (s->kernel_id < 0 || s->kernel_id > 2) return fail(1, "unknown kernel_id%s");
+  if (s->chunk_rows < 0 || (s->chunk_rows % 128) != 0) return fail(1, "chunk_rows must be a multiple of 128%s");
+  p.D = s->d; p.M = s->m; p.K = s->k; p.V = s->v;
+  p.Mp = (int)round_up_ll(s->m, 256);
+  p.MB = p.Mp / 64; p.JT = p.Mp / 256; p.MT = p.Mp / 128;
+  long long chunk = s->chunk_rows ? s->chunk_rows : (long long)DEFAULT_SMS * 128;
+  const long long nneed = round_up_ll(s->n_local > 0 ? s->n_local : 1, 128);
+  if (chunk > nneed) chunk = nneed;
+  p.chunk_rows = (int)chunk;
+  p.ncp = chunk;
+  p.RTmax = (int)(chunk / 128);
+  const size_t Mp2 = (size_t)p.Mp * p.Mp;
+  size_t off = 0;
+  p.acc = bump(off, sizeof(double) * ACC_HEAD);
+  p.ck = bump(off, sizeof(double) * p.K);
+  p.du = bump(off, sizeof(double) * (size_t)p.K * p.M);
+  p.dphi = bump(off, sizeof(double) * (size_t)p.K * p.V);
+  p.dz = bump(off, sizeof(double) * (size_t)p.M * p.D);
+  p.c5 = bump(off, sizeof(double) * Mp2);
+  p.zero_bytes = (long long)off;
+  p.phisum = bump(off, sizeof(float) * p.K);
+  p.status_pad = bump(off, 256);
+  p.L64 = bump(off, sizeof(double) * Mp2);
+  p.Linv64 = bump(off, sizeof(double) * Mp2);
+  p.tmpA = bump(off, sizeof(double) * Mp2);
+  p.tmpB = bump(off, sizeof(double) * Mp2);
+  p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
+  p.st_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
+  const size_t nm = (size_t)p.ncp * p.Mp;
+  p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
+  p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
+  p.r_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
+  p.dwf = bump(off, sizeof(float) * nm);
+  p.wsq = bump(off, sizeof(float) * p.ncp);
+  p.srow = bump(off, sizeof(float) * p.ncp);
+  p.arow = bump(off, sizeof(float) * p.ncp);
+  p.cnt = bump(off, sizeof(float) * p.ncp);
+  p.gv0 = bump(off, sizeof(float) * p.ncp);
+  const size_t kn = (size_t)p.K * p.ncp;
+  p.floc = bump(off, sizeof(float) * kn);
+  p.q = bump(off, sizeof(float) * kn);
+  p.mu = bump(off, sizeof(float) * kn);
+  p.fvar = bump(off, sizeof(float) * kn);
+  p.theta = bump(off, sizeof(float) * kn);
+  p.g_loc = bump(off, sizeof(float) * kn);
+  p.g2 = bump(off, sizeof(float) * kn);
+  p.g1 = bump(off, sizeof(float) * kn);
+  p.total = off;
+  return 0;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
+
+PlaneMat plane_mat(void* ws, size_t off, long long rows, long long cols) {
+  PlaneMat m;
+  m.base = at<bf16>(ws, off);
+  m.row_tiles = (int)(rows / 128);
+  m.col_blocks = (int)(cols / 64);
+  m.plane_stride = rows * cols;
+  return m;
+}
+
+Hyper make_hyper(const gdrf_shape* s, const gdrf_inputs* in) {
+  Hyper hp;
+  hp.variance = in->variance; hp.lengthscale = in->lengthscale; hp.noise = in->noise;
+  hp.ls_dim = s->ls_dim; hp.kid = s->kernel_id; hp.D = s->d;
+  return hp;
+}
+
+int num_sms() {
+  int dev = 0, n = DEFAULT_SMS;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : DEFAULT_SMS;
+}
+
+int check_device() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(3, "no CUDA device: gdrf_b200 has no CPU path%s");
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(3, "gdrf_b200 is built for sm_100a only%s");
+  return 0;
+}
+
+template <int KPW, int VJ>
+int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st) {
+  const int VC = VJ * 32;
+  const size_t smem = sizeof(float) * ((size_t)p.K * (VC + 1) + (size_t)LK_TN * VC + (size_t)LK_TN * (p.K + 1) + LK_TN);
+  CU(cudaFuncSetAttribute(k_likelihood<KPW, VJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ntiles = (nc + LK_TN - 1) / LK_TN;
+  const int grid = ntiles < sms ? ntiles : sms;
+  k_likelihood<KPW, VJ><<<grid, LK_THREADS, smem, st>>>(
+      nc, (int)p.ncp, p.K, p.V, in->ws + n0 * p.V, at<float>(ws, p.theta), at<float>(ws, p.srow), in->phi,
+      at<float>(ws, p.g1), at<float>(ws, p.arow), at<float>(ws, p.cnt), at<double>(ws, p.dphi), at<double>(ws, p.acc));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dispatch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st) {
+  const int kpw = (p.K + 15) / 16;
+  const int vj_need = (p.V + 31) / 32;
+#define LK(KPW, VJ) return launch_likelihood<KPW, VJ>(p, nc, in, n0, ws, sms, st)
+  if (kpw <= 1) { if (vj_need <= 4) LK(1, 4); if (vj_need <= 8) LK(1, 8); LK(1, 16); }
+  if (kpw <= 2) { if (vj_need <= 4) LK(2, 4); if (vj_need <= 8) LK(2, 8); LK(2, 16); }
+  if (kpw <= 4) { if (vj_need <= 4) LK(4, 4); if (vj_need <= 8) LK(4, 8); LK(4, 16); }
+  if (vj_need <= 4) LK(8, 4);
+  LK(8, 8);
+#undef LK
+}
+
+int launch_du(const Plan& p, PlaneMat w, int RT, void* ws, int sms, cudaStream_t st) {
+  int tiles_per_cta = (RT * p.MB + 2 * sms - 1) / (2 * sms);
+  if (tiles_per_cta < 1) tiles_per_cta = 1;
+  const dim3 grid(p.MB, (RT + tiles_per_cta - 1) / tiles_per_cta);
+  const float* g = at<float>(ws, p.g_loc);
+  double* du = at<double>(ws, p.du);
+  if (p.K <= 16) k_du<4><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
+  else if (p.K <= 32) k_du<8><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
+  else if (p.K <= 64) k_du<16><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
+  else k_du<32><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
+int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
+                  bool with_var, int sms, cudaStream_t st) {
+  const Hyper hp = make_hyper(s, in);
+  PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, p.Mp);
+  PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
+  PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
+  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp);
+  k_kxz_planes<<<dim3(p.MB, RT), 256, 0, st>>>(in->xs + n0 * p.D, nc, in->z, p.M, hp, kxz);
+  LAUNCH_CHECK();
+  {
+    G1::Params g{};
+    g.kxz = kxz; g.linv = linv; g.w = w; g.wsq = at<float>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
+    CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st));
+  }
+  k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<float>(ws, p.floc), (int)p.ncp);
+  LAUNCH_CHECK();
+  if (with_var) {
+    G2<false>::Params g{};
+    g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
+    g.q = at<float>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.JT = p.JT; g.ncp = (int)p.ncp;
+    CU(launch_gemm<G2<false>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st));
+  }
+  return 0;
+}
+
+__global__ void k_scale(const float* __restrict__ g, long long n, const float* __restrict__ sdev, float shost,
+                        float* __restrict__ dst) {
+  const float s = (sdev ? sdev[0] : 1.f) * shost;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = s * g[i];
+}
+
+__global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms) {
+  if (threadIdx.x == 0) {
+    terms[0] = acc[ACC_LP_MU];
+    terms[1] = acc[ACC_LQ];
+    terms[2] = acc[ACC_LL];
+    terms[3] = acc[ACC_LP_PHI];
+  }
+}
+
+// sum_n sum_v w log(softmax_k(f_loc)[n] . phi[:, v])   (abstract_gdrf.py:113-139); warp per observation
+__global__ void __launch_bounds__(256) k_perplexity(int N, int K, int V, const float* __restrict__ floc,
+                                                    const int* __restrict__ ws, const float* __restrict__ phi,
+                                                    double* __restrict__ out) {
+  extern __shared__ float pp_smem[];   // [8 warps][K]
+  __shared__ double scratch[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* th = pp_smem + warp * K;
+  double num = 0.0, den = 0.0;
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < N; n += (long long)gridDim.x * 8) {
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, floc[(long long)k * N + n]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float e = __expf(floc[(long long)k * N + n] - mx);
+      th[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    float a = 0.f, c = 0.f;
+    for (int v = lane; v < V; v += 32) {
+      const int w = ws[n * V + v];
+      if (w != 0) {
+        float pv = 0.f;
+        for (int k = 0; k < K; ++k) pv = fmaf(th[k], phi[(long long)k * V + v], pv);
+        a += (float)w * __logf(pv * inv);
+        c += (float)w;
+      }
+    }
+    num += (double)warp_sum(a);
+    den += (double)warp_sum(c);
+    __syncwarp();
+  }
+  if (lane != 0) num = den = 0.0;
+  num = block_sum(num, scratch);
+  den = block_sum(den, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&out[0], num);
+    atomicAdd(&out[1], den);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gdrf_last_error(void) { return g_err; }
+
+const char* gdrf_build_info(void) {
+  return "gdrf_b200 sm_100a: tcgen05 split-bf16 contractions (TMEM accumulators, cp.async.bulk operand ring)";
+}
+
+int gdrf_workspace_bytes(const gdrf_shape* shape, size_t* out_bytes) {
+  Plan p;
+  if (int e = make_plan(shape, p)) return e;
+  if (!out_bytes) return fail(1, "null out pointer%s");
+  *out_bytes = p.total;
+  return 0;
+}
+
+int gdrf_grad_elems(const gdrf_shape* s, int64_t* out_elems) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (!out_elems) return fail(1, "null out pointer%s");
+  *out_elems = (int64_t)s->k * s->m * s->m + (int64_t)s->k * s->m + (int64_t)s->k * s->v + (int64_t)s->m * s->d + 2 +
+               s->ls_dim;
+  return 0;
+}
+
+int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int njitter, void* ws, size_t ws_bytes,
+                  gdrf_stream_t stream, int* dev_status) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !ws || !dev_status) return fail(1, "null pointer argument%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  if (njitter < 0) return fail(1, "njitter must be >= 0%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Hyper hp = make_hyper(s, in);
+  CU(cudaMemsetAsync(dev_status, 0, sizeof(int), st));
+  const dim3 g2d(ceil_div(p.Mp, 256), p.Mp);
+  if (s->flags & GDRF_FLAG_CHOL_FP32_STATUS) {
+    float* k32 = at<float>(ws, p.tmpA);
+    k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
+    LAUNCH_CHECK();
+    cholesky_inplace<float>(k32, p.Mp, dev_status, st);
+    LAUNCH_CHECK();
+  }
+  double* L = at<double>(ws, p.L64);
+  k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, L);
+  LAUNCH_CHECK();
+  cholesky_inplace<double>(L, p.Mp, dev_status, st);
+  LAUNCH_CHECK();
+  double* Linv = at<double>(ws, p.Linv64);
+  tri_inverse(L, Linv, p.Mp, st);
+  LAUNCH_CHECK();
+  PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
+  k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_outputs* out, void* ws, size_t ws_bytes,
+                   gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !out || !ws || !out->terms) return fail(1, "null pointer argument%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  const bool want_grad = (s->flags & GDRF_FLAG_WANT_GRAD) != 0;
+  if (want_grad && !out->grad) return fail(1, "GDRF_FLAG_WANT_GRAD needs out->grad%s");
+  if (s->n_offset < 0 || s->n_offset + s->n_local > s->n_eps) return fail(1, "eps window out of range%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = num_sms();
+  const Hyper hp = make_hyper(s, in);
+  const int K = p.K, M = p.M, Mp = p.Mp;
+
+  CU(cudaMemsetAsync(at<char>(ws, p.acc), 0, (size_t)p.zero_bytes, st));
+  if (want_grad) CU(cudaMemsetAsync(out->grad, 0, sizeof(float) * (size_t)K * M * M, st));
+
+  PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
+  PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
+  PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
+  PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
+  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)K * Mp, Mp);
+  PlaneMat rm = plane_mat(ws, p.r_pl, p.ncp, (long long)K * Mp);
+  float* dwf = at<float>(ws, p.dwf);
+  double* acc = at<double>(ws, p.acc);
+
+  k_pack_st<<<dim3(p.MB, p.MB, K), 256, 0, st>>>(in->u_scale_tril, K, M, Mp, stm);
+  LAUNCH_CHECK();
+  k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
+  LAUNCH_CHECK();
+
+  // tiles of dS on / below the diagonal (i tile of 128 rows, j tile of 256 columns)
+  G6::Params g6{};
+  if (want_grad) {
+    int nt = 0;
+    for (int b = 0; b < p.JT; ++b)
+      for (int a = 0; a < p.MT; ++a)
+        if (128 * a + 127 >= 256 * b && 128 * a < M && 256 * b < M) {
+          if (nt >= G6::MAX_TILES) return fail(1, "too many dS tiles%s");
+          g6.ta[nt] = (unsigned char)a;
+          g6.tb[nt] = (unsigned char)b;
+          ++nt;
+        }
+    g6.ntile = nt;
+  }
+
+  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
+    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
+    const int RT = (nc + 127) / 128;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, sms, st)) return e;
+    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.floc),
+                                      at<float>(ws, p.q), at<float>(ws, p.wsq), in->eps, hp,
+                                      at<float>(ws, p.phisum), at<float>(ws, p.mu), at<float>(ws, p.fvar),
+                                      at<float>(ws, p.theta), at<float>(ws, p.srow), acc);
+    LAUNCH_CHECK();
+    if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
+    k_obs_finalize<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta),
+                                       at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),
+                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<float>(ws, p.wsq), in->eps, hp,
+                                       at<float>(ws, p.phisum), at<float>(ws, p.g_loc), at<float>(ws, p.g2),
+                                       at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
+    LAUNCH_CHECK();
+    if (!want_grad) continue;
+    {
+      G2<true>::Params g{};
+      g.w = w; g.st = stm; g.r = rm; g.q = nullptr; g.g2 = at<float>(ws, p.g2);
+      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.ncp = (int)p.ncp;
+      CU(launch_gemm<G2<true>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st));
+    }
+    {
+      G3::Params g{};
+      g.r = rm; g.st = stm; g.dw = dwf; g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp;
+      CU(launch_gemm<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, st));
+    }
+    {
+      const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
+      CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
+                                                       in->u_loc, K, M, (int)p.ncp, dwt);
+      LAUNCH_CHECK();
+    }
+    if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
+    {
+      g6.w = w; g6.r = rm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
+      const int base = K * g6.ntile;
+      int splits = base >= sms ? 1 : (sms + base - 1) / base;
+      const int NBt = 2 * RT;
+      if (splits > NBt) splits = NBt;
+      int per = (NBt + splits - 1) / splits;
+      splits = (NBt + per - 1) / per;
+      g6.splits = splits; g6.nb_per_split = per;
+      CU(launch_gemm<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, st));
+    }
+    {
+      G4::Params g{};
+      g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+      CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st));
+    }
+    {
+      int rows_per_cta = (int)round_up_ll(((long long)nc * p.MT + 2 * sms - 1) / (2 * sms), 128);
+      if (rows_per_cta < 128) rows_per_cta = 128;
+      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
+          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
+      LAUNCH_CHECK();
+    }
+    {
+      G5::Params g{};
+      g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+      const int base = p.MT * p.MT;
+      int splits = base >= 2 * sms ? 1 : (2 * sms + base - 1) / base;
+      const int NBt = 2 * RT;
+      if (splits > NBt) splits = NBt;
+      int per = (NBt + splits - 1) / splits;
+      splits = (NBt + per - 1) / per;
+      g.splits = splits; g.nb_per_split = per;
+      CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
+    }
+  }
+
+  if (want_grad && s->n_local > 0) {
+    // Cholesky adjoint (Murray 2016; torch cholesky_backward):  G_L = -tril(L^-T C5),
+    // Phi = tril(L^T G_L) with halved diagonal, G_K = L^-T Phi L^-1, symmetrised inside k_kuu_backward.
+    double* L = at<double>(ws, p.L64);
+    double* Linv = at<double>(ws, p.Linv64);
+    double* tA = at<double>(ws, p.tmpA);
+    double* tB = at<double>(ws, p.tmpB);
+    const dim3 g2d(ceil_div(Mp, 256), Mp);
+    dgemm<true, false>(Linv, at<double>(ws, p.c5), tA, Mp, st);
+    k_tril_op<<<g2d, 256, 0, st>>>(tA, Mp, 0);
+    dgemm<true, false>(L, tA, tB, Mp, st);
+    k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
+    dgemm<true, false>(Linv, tB, tA, Mp, st);
+    dgemm<false, false>(tA, Linv, tB, Mp, st);
+    LAUNCH_CHECK();
+    k_kuu_backward<<<ceil_div(M, 128), 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
+    LAUNCH_CHECK();
+  }
+  const int include_prior = (s->flags & GDRF_FLAG_INCLUDE_PRIOR) ? 1 : 0;
+  if (include_prior) {
+    k_prior<<<K, 128, 0, st>>>(in->phi, in->beta, K, p.V, acc);
+    LAUNCH_CHECK();
+  }
+  if (want_grad) {
+    const long long small = (long long)K * M + (long long)K * p.V + (long long)M * p.D + 2 + s->ls_dim;
+    k_assemble<<<(int)((small + 255) / 256), 256, 0, st>>>(K, M, p.V, p.D, s->ls_dim, include_prior, in->phi, in->beta,
+                                                           acc, at<double>(ws, p.ck), at<double>(ws, p.du),
+                                                           at<double>(ws, p.dphi), at<double>(ws, p.dz), out->grad);
+    LAUNCH_CHECK();
+  }
+  k_copy_terms<<<1, 32, 0, st>>>(acc, out->terms);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int gdrf_elbo_backward(const float* grad, int64_t elems, const float* scale_dev, float scale_host, float* dst,
+                       gdrf_stream_t stream) {
+  if (!grad || !dst || elems < 0) return fail(1, "bad argument%s");
+  if (elems == 0) return 0;
+  long long blocks = (elems + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_scale<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(grad, elems, scale_dev, scale_host, dst);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int gdrf_marginal_mean(const gdrf_shape* s, const gdrf_inputs* in, float* out_floc, void* ws, size_t ws_bytes,
+                       gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !ws || !out_floc) return fail(1, "null pointer argument%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = num_sms();
+  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
+    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
+    const int RT = (nc + 127) / 128;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, false, sms, st)) return e;
+    CU(cudaMemcpy2DAsync(out_floc + n0, sizeof(float) * (size_t)s->n_local, at<float>(ws, p.floc),
+                         sizeof(float) * (size_t)p.ncp, sizeof(float) * (size_t)nc, p.K, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int gdrf_perplexity_terms(const gdrf_shape* s, const gdrf_inputs* in, const float* floc, double* out,
+                          gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !floc || !out) return fail(1, "null pointer argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(out, 0, 2 * sizeof(double), st));
+  if (s->n_local == 0) return 0;
+  long long blocks = (s->n_local + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_perplexity<<<(int)blocks, 256, sizeof(float) * 8 * p.K, st>>>((int)s->n_local, p.K, p.V, floc, in->ws, in->phi, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// Split-bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), fed by
+// cp.async.bulk (TMA bulk copies) of pre-swizzled 16 KB operand blocks, warp-specialised:
+//
+//   warp 0      one elected lane issues the bulk copies into an NSTAGES-deep SMEM ring
+//   warp 1      allocates TMEM; one elected lane issues tcgen05.mma for every (plane_a, plane_b)
+//               product of the error-compensated split and commits to the ring / accumulator barriers
+//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM) and run
+//               the policy's fused epilogue (row norms, rescale + re-split, fp32 store, accumulate)
+//
+// A "policy" describes one of the contractions of the ELBO (see policies.cuh): where the operand
+// blocks live, which k-blocks a triangular operand lets us skip, and what the epilogue does.  The
+// same policy drives `gemm_ref_kernel`, a plain-FMA CUDA kernel used by the tests to check the tensor
+// path element for element (it is a device-side checker, not a fallback: the product never selects it).
+#pragma once
+#include "common.cuh"
+
+namespace gdrf {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (reported as a CUDA error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("gdrf gemm: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, one CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// descriptors  (bit layouts: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
+// ------------------------------------------------------------------------------------------
+// SWIZZLE_128B shared-memory matrix descriptor.
+//   K-major  operand: rows of 64 bf16 (128 B); 8-row groups 1024 B apart (SBO); LBO unused (1).
+//   MN-major operand: 64 MN-elements contiguous (128 B) per k-row; 8-k-row groups 1024 B apart (SBO);
+//                     successive 64-wide MN groups LBO bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);              // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;      // [16,30) leading byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;      // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                                // [46,48) descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                // [61,64) layout type SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4)                     // [4,6)   accumulator format F32
+         | (1u << 7)                   // [7,10)  A format BF16
+         | (1u << 10)                  // [10,13) B format BF16
+         | ((a_mn ? 1u : 0u) << 15)    // [15]    A major (0 = K, 1 = MN)
+         | ((b_mn ? 1u : 0u) << 16)    // [16]    B major
+         | ((uint32_t)(N >> 3) << 17)  // [17,23) N >> 3
+         | ((uint32_t)(M >> 4) << 24); // [24,29) M >> 4
+}
+
+// number of (plane_a, plane_b) products kept: all pairs with pa + pb <= max(PA,PB)-1
+__host__ __device__ constexpr int num_products(int PA, int PB) {
+  int n = 0;
+  const int ord = (PA > PB ? PA : PB) - 1;
+  for (int a = 0; a < PA; ++a)
+    for (int b = 0; b < PB; ++b)
+      if (a + b <= ord) ++n;
+  return n;
+}
+
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 216 * 1024;
+
+template <class P>
+struct GemmCfg {
+  static constexpr int A_BYTES = 16384;                       // one plane of a 128 x 64 A stage
+  static constexpr int B_BYTES = (P::BN / 128) * 16384;       // one plane of a BN x 64 B stage
+  static constexpr int STAGE_BYTES = P::PA * A_BYTES + P::PB * B_BYTES;
+  static constexpr int NSTAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) < 4 ? (GEMM_SMEM_BUDGET / STAGE_BYTES) : 4;
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * P::BN <= 256) ? 256 : 512;
+  static_assert(NSTAGES >= 2, "need at least a double-buffered ring");
+  static_assert(P::BN == 128 || P::BN == 256, "BN");
+};
+
+// ------------------------------------------------------------------------------------------
+// the tensor-core kernel
+// ------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ typename P::Params prm) {
+  using Cfg = GemmCfg<P>;
+  constexpr int NST = Cfg::NSTAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + NST * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [NST]
+  uint64_t* empty_bar = bars + NST;          // [NST]
+  uint64_t* tfull_bar = bars + 2 * NST;      // [2]
+  uint64_t* tempty_bar = bars + 2 * NST + 2; // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NST + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = P::num_items(prm);
+
+  if (warp == 0) {
+    // ------------------------------ bulk-copy producer ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nsub = P::num_subs(prm, item);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int kn = P::k_iters(prm, item, sub);
+          for (int kit = 0; kit < kn; ++kit, ++it) {
+            const int s = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < P::PA; ++pl) {
+              uint8_t* dst = st + pl * Cfg::A_BYTES;
+              if (!P::A_MN) {
+                bulk_g2s(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s]);
+              } else {
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc)
+                  bulk_g2s(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+              }
+            }
+#pragma unroll
+            for (int pl = 0; pl < P::PB; ++pl) {
+              uint8_t* dst = st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+              if (!P::B_MN) {
+#pragma unroll
+                for (int pc = 0; pc < P::BN / 128; ++pc)
+                  bulk_g2s(dst + pc * 16384, P::b_src(prm, item, sub, kit, pl, pc), 16384, &full_bar[s]);
+              } else {
+#pragma unroll
+                for (int pc = 0; pc < P::BN / 64; ++pc)
+                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, P::BN, P::A_MN, P::B_MN);
+      constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
+      uint32_t it = 0, unit = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nsub = P::num_subs(prm, item);
+        for (int sub = 0; sub < nsub; ++sub, ++unit) {
+          const int acc = unit & 1;
+          const uint32_t aph = (unit >> 1) & 1;
+          mbar_wait(&tempty_bar[acc], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * P::BN;
+          const int kn = P::k_iters(prm, item, sub);
+          for (int kit = 0; kit < kn; ++kit, ++it) {
+            const int s = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
+            bool first = (kit == 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+              for (int pa = 0; pa < P::PA; ++pa) {
+#pragma unroll
+                for (int pb = 0; pb < P::PB; ++pb) {
+                  if (pa + pb > ORD) continue;
+                  const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                  const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                  const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                  const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                  umma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                  first = false;
+                }
+              }
+            }
+            umma_commit(&empty_bar[s]);        // frees the ring slot when these MMAs retire
+          }
+          umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;       // accumulator row owned by this thread
+    typename P::Epi epi;
+    uint32_t unit = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int nsub = P::num_subs(prm, item);
+      epi.item_begin(prm, item, row);
+      for (int sub = 0; sub < nsub; ++sub, ++unit) {
+        const int acc = unit & 1;
+        const uint32_t aph = (unit >> 1) & 1;
+        epi.sub_begin(prm, item, sub, row);
+        mbar_wait(&tfull_bar[acc], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * P::BN;
+#pragma unroll 1
+        for (int c = 0; c < P::BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if (c == P::BN / 32 - 1) {           // accumulator fully read: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          epi.chunk(prm, item, sub, row, c * 32, v);
+        }
+        epi.sub_end(prm, item, sub, row);
+      }
+      epi.item_end(prm, item, row);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plain-FMA checker with the same policy interface (tests only; 128 threads, thread = row)
+// ------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(128) gemm_ref_kernel(const typename P::Params prm) {
+  const int row = threadIdx.x;
+  const int n_items = P::num_items(prm);
+  typename P::Epi epi;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int nsub = P::num_subs(prm, item);
+    epi.item_begin(prm, item, row);
+    for (int sub = 0; sub < nsub; ++sub) {
+      epi.sub_begin(prm, item, sub, row);
+      const int kn = P::k_iters(prm, item, sub);
+      for (int c = 0; c < P::BN / 32; ++c) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int kit = 0; kit < kn; ++kit) {
+          for (int kk = 0; kk < 64; ++kk) {
+            float a = 0.f;
+            for (int pl = P::PA - 1; pl >= 0; --pl) {
+              const bf16* src = P::A_MN ? P::a_src(prm, item, sub, kit, pl, row >> 6) + tile_off(kk, row & 63)
+                                        : P::a_src(prm, item, sub, kit, pl, 0) + tile_off(row, kk);
+              a += __bfloat162float(*src);
+            }
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 32 + j;
+              float b = 0.f;
+              for (int pl = P::PB - 1; pl >= 0; --pl) {
+                const bf16* src = P::B_MN ? P::b_src(prm, item, sub, kit, pl, col >> 6) + tile_off(kk, col & 63)
+                                          : P::b_src(prm, item, sub, kit, pl, col >> 7) + tile_off(col & 127, kk);
+                b += __bfloat162float(*src);
+              }
+              v[j] = fmaf(a, b, v[j]);
+            }
+          }
+        }
+        epi.chunk(prm, item, sub, row, c * 32, v);
+      }
+      epi.sub_end(prm, item, sub, row);
+    }
+    epi.item_end(prm, item, row);
+  }
+}
+
+template <class P>
+inline cudaError_t launch_gemm(const typename P::Params& prm, int n_items, int num_sms, bool use_ref,
+                               cudaStream_t stream) {
+  if (n_items <= 0) return cudaSuccess;
+  if (use_ref) {
+    gemm_ref_kernel<P><<<n_items < 4096 ? n_items : 4096, 128, 0, stream>>>(prm);
+    return cudaGetLastError();
+  }
+  using Cfg = GemmCfg<P>;
+  static bool configured = false;   // attribute is per (function, device context); cheap to repeat
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  configured = true;
+  (void)configured;
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  gemm_tc_kernel<P><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+}  // namespace gdrf

@@ -1,0 +1,292 @@
+// The six contractions of the ELBO + gradient, expressed as policies for gemm_tc_kernel.
+//
+// Notation: n observation, i/j/m inducing index, k topic.
+//   Kxz = k(xs, Z)              W   = Kxz Linv^T            (Linv = chol(Kuu + jI)^-1, lower)
+//   T_k = W S_k                 q_kn = sum_j T_k[n,j]^2     (S_k lower triangular)
+//   R_k = diag(2 g_var[k,:]) T_k
+//   dW  = sum_k R_k S_k^T (+ mean / var0 terms added by k_dw_finalize)
+//   dS_k = tril(W^T R_k)        dKxz = dWtot Linv           C5 = dWtot^T W   (feeds the Cholesky adjoint)
+//
+// Operand storage (all "tiled planes", common.cuh), per chunk of RT*128 observation rows, Mp = M
+// rounded up to 256, MB = Mp/64, JT = Mp/256:
+//   KXZ, W, DWT : [rows n][cols inducing]            3 planes
+//   LINV        : [rows m][cols i]                   3 planes   (zero above the diagonal / in padding)
+//   ST          : [rows (k, j)][cols i] = S_k[i, j]  2 planes   (zero for i < j)
+//   R           : [rows n][cols (k, j)]              2 planes
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace gdrf {
+
+__device__ __forceinline__ void store8(bf16* dst, const uint4& pk) { *reinterpret_cast<uint4*>(dst) = pk; }
+
+// ---------------------------------------------------------------------------------------------
+// G1:  W[n, m] = sum_{i <= m} Kxz[n, i] Linv[m, i]      epilogue: W planes + wsq[n] = sum_m W^2
+// ---------------------------------------------------------------------------------------------
+struct G1 {
+  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr bool A_MN = false, B_MN = false;
+  struct Params {
+    PlaneMat kxz, linv, w;
+    float* wsq;
+    int RT, MB;
+  };
+  __device__ static int num_items(const Params& p) { return p.RT; }
+  __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return min(p.MB, 2 * (sub + 1)); }
+  __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int) {
+    return p.kxz.base + pl * p.kxz.plane_stride + p.kxz.block_off(item, kit);
+  }
+  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int) {
+    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(sub, kit);
+  }
+  struct Epi {
+    float acc;
+    __device__ void item_begin(const Params&, int, int) { acc = 0.f; }
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
+      const int r = item * 128 + row;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 pk[3];
+        split8<3>(&v[g * 8], pk);
+        const int col = sub * 128 + c0 + g * 8;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) store8(p.w.elem(pl, r, col), pk[pl]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params& p, int item, int row) { p.wsq[item * 128 + row] = acc; }
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
+// G2:  T[n, (k, j)] = sum_{i >= j} W[n, i] S_k[i, j]
+//   FWD epilogue: q[k, n] = sum_j T^2          BWD epilogue: R = 2 g_var[k, n] * T  (2 planes)
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+struct G2 {
+  static constexpr int PA = 2, PB = 2, BN = 256;
+  static constexpr bool A_MN = false, B_MN = false;
+  struct Params {
+    PlaneMat w, st, r;
+    float* q;          // [K][ncp]   (FWD out)
+    const float* g2;   // [K][ncp]   (BWD in: 2 * dELBO/df_var)
+    int RT, MB, K, JT, ncp;
+  };
+  __device__ static int num_items(const Params& p) { return p.RT; }
+  __device__ static int num_subs(const Params& p, int) { return p.K * p.JT; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - 4 * (sub % p.JT); }
+  __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
+    const int jt = sub % p.JT;
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(item, 4 * jt + kit);
+  }
+  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
+    const int jt = sub % p.JT;
+    return p.st.base + pl * p.st.plane_stride + p.st.block_off(sub * 2 + pc, 4 * jt + kit);
+  }
+  struct Epi {
+    float acc;
+    __device__ void item_begin(const Params&, int, int) { acc = 0.f; }
+    __device__ void sub_begin(const Params& p, int item, int sub, int row) {
+      if (BWD) {
+        acc = p.g2[(long long)(sub / p.JT) * p.ncp + item * 128 + row];
+      } else if (sub % p.JT == 0) {
+        acc = 0.f;
+      }
+    }
+    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
+      if (BWD) {
+        const int r = item * 128 + row;
+        const int col0 = sub * 256 + c0;     // (k * JT + jt) * 256 == k * Mp + jt * 256
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float s[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] = acc * v[g * 8 + j];
+          uint4 pk[2];
+          split8<2>(s, pk);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) store8(p.r.elem(pl, r, col0 + g * 8), pk[pl]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);
+      }
+    }
+    __device__ void sub_end(const Params& p, int item, int sub, int row) {
+      if (!BWD && (sub % p.JT) == p.JT - 1) p.q[(long long)(sub / p.JT) * p.ncp + item * 128 + row] = acc;
+    }
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
+// G3:  dW[n, i] = sum_k sum_{j <= i} R[n, (k, j)] S_k[i, j]      (B = ST read MN-major)
+// ---------------------------------------------------------------------------------------------
+struct G3 {
+  static constexpr int PA = 2, PB = 2, BN = 256;
+  static constexpr bool A_MN = false, B_MN = true;
+  struct Params {
+    PlaneMat r, st;
+    float* dw;   // [ncp][Mp] fp32
+    int RT, MB, K, JT, Mp;
+  };
+  __device__ static int num_items(const Params& p) { return p.RT; }
+  __device__ static int num_subs(const Params& p, int) { return p.JT; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return p.K * 4 * (sub + 1); }
+  __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
+    const int seg = 4 * (sub + 1);
+    const int k = kit / seg, jb = kit - k * seg;
+    return p.r.base + pl * p.r.plane_stride + p.r.block_off(item, k * p.MB + jb);
+  }
+  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
+    const int seg = 4 * (sub + 1);
+    const int k = kit / seg, jb = kit - k * seg;
+    return p.st.base + pl * p.st.plane_stride + p.st.block_off(k * 2 * p.JT + (jb >> 1), sub * 4 + pc) +
+           (jb & 1) * 4096;
+  }
+  struct Epi {
+    __device__ void item_begin(const Params&, int, int) {}
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
+      float4* dst = reinterpret_cast<float4*>(p.dw + (long long)(item * 128 + row) * p.Mp + sub * 256 + c0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
+// G4:  dKxz[n, i] = sum_{m >= i} dWtot[n, m] Linv[m, i]          (B = LINV read MN-major)
+// ---------------------------------------------------------------------------------------------
+struct G4 {
+  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr bool A_MN = false, B_MN = true;
+  struct Params {
+    PlaneMat dwt, linv;
+    float* dkxz;   // [ncp][Mp] fp32
+    int RT, MB, Mp;
+  };
+  __device__ static int num_items(const Params& p) { return p.RT; }
+  __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - 2 * sub; }
+  __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
+    return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(item, 2 * sub + kit);
+  }
+  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
+    const int mb = 2 * sub + kit;
+    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(mb >> 1, sub * 2 + pc) + (mb & 1) * 4096;
+  }
+  struct Epi {
+    __device__ void item_begin(const Params&, int, int) {}
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
+      float4* dst = reinterpret_cast<float4*>(p.dkxz + (long long)(item * 128 + row) * p.Mp + sub * 128 + c0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
+// G5:  C5[a, b] += sum_n dWtot[n, a] W[n, b]        (both operands MN-major; split over n; fp64 atomics)
+// ---------------------------------------------------------------------------------------------
+struct G5 {
+  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr bool A_MN = true, B_MN = true;
+  struct Params {
+    PlaneMat dwt, w;
+    double* c5;   // [Mp][Mp]
+    int RT, MB, Mp, MT, splits, nb_per_split;
+  };
+  __device__ static int num_items(const Params& p) { return p.MT * p.MT * p.splits; }
+  __device__ static int num_subs(const Params&, int) { return 1; }
+  __device__ static int k_iters(const Params& p, int item, int) {
+    const int s = item / (p.MT * p.MT);
+    return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
+  }
+  __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
+    const int s = item / (p.MT * p.MT), t = item - s * p.MT * p.MT, at = t / p.MT;
+    const int nb = s * p.nb_per_split + kit;
+    return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(nb >> 1, at * 2 + pc) + (nb & 1) * 4096;
+  }
+  __device__ static const bf16* b_src(const Params& p, int item, int, int kit, int pl, int pc) {
+    const int s = item / (p.MT * p.MT), t = item - s * p.MT * p.MT, bt = t % p.MT;
+    const int nb = s * p.nb_per_split + kit;
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, bt * 2 + pc) + (nb & 1) * 4096;
+  }
+  struct Epi {
+    __device__ void item_begin(const Params&, int, int) {}
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
+      const int t = item % (p.MT * p.MT), at = t / p.MT, bt = t % p.MT;
+      double* dst = p.c5 + (long long)(at * 128 + row) * p.Mp + bt * 128 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, (double)v[j]);
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
+// G6:  dS_k[i, j] += sum_n W[n, i] R[n, (k, j)]   for j <= i   (both MN-major; tiles on/below the diagonal)
+// ---------------------------------------------------------------------------------------------
+struct G6 {
+  static constexpr int PA = 2, PB = 2, BN = 256;
+  static constexpr bool A_MN = true, B_MN = true;
+  static constexpr int MAX_TILES = 512;
+  struct Params {
+    PlaneMat w, r;
+    float* ds;   // [K][M][M] fp32, unpadded gradient accumulator
+    int RT, MB, K, M, ntile, splits, nb_per_split;
+    unsigned char ta[MAX_TILES], tb[MAX_TILES];
+  };
+  __device__ static int num_items(const Params& p) { return p.K * p.ntile * p.splits; }
+  __device__ static int num_subs(const Params&, int) { return 1; }
+  __device__ static int k_iters(const Params& p, int item, int) {
+    const int s = item / (p.K * p.ntile);
+    return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
+  }
+  __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
+    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, t = rem % p.ntile;
+    const int nb = s * p.nb_per_split + kit;
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, p.ta[t] * 2 + pc) + (nb & 1) * 4096;
+  }
+  __device__ static const bf16* b_src(const Params& p, int item, int, int kit, int pl, int pc) {
+    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
+    const int nb = s * p.nb_per_split + kit;
+    return p.r.base + pl * p.r.plane_stride + p.r.block_off(nb >> 1, k * p.MB + p.tb[t] * 4 + pc) + (nb & 1) * 4096;
+  }
+  struct Epi {
+    __device__ void item_begin(const Params&, int, int) {}
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
+      const int rem = item % (p.K * p.ntile), k = rem / p.ntile, t = rem % p.ntile;
+      const int i = p.ta[t] * 128 + row;
+      const int j0 = p.tb[t] * 256 + c0;
+      if (i >= p.M) return;
+      float* dst = p.ds + ((long long)k * p.M + i) * p.M;
+      if (p.splits == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j0 + j <= i) dst[j0 + j] += v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j0 + j <= i) atomicAdd(dst + j0 + j, v[j]);
+      }
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+}  // namespace gdrf

@@ -1,0 +1,667 @@
+// Per-observation (HBM-bound) stages of the ELBO and its gradient, and the operand packers.
+// Reference semantics restated in SURVEY.md section 8(c); citations are to /root/reference files.
+#pragma once
+#include "common.cuh"
+
+namespace gdrf {
+
+struct Hyper {
+  const float* variance;     // [1]
+  const float* lengthscale;  // [ls_dim]
+  const float* noise;        // [1]
+  int ls_dim, kid, D;
+};
+
+// slots of the fp64 accumulator block (zeroed at the start of every step)
+enum { ACC_LP_MU = 0, ACC_LQ = 1, ACC_LL = 2, ACC_LP_PHI = 3, ACC_DNOISE = 4, ACC_DVAR = 5, ACC_DLS = 6,
+       ACC_HEAD = ACC_DLS + MAX_D + 2 };
+
+// ---------------------------------------------------------------------------------------------
+// K_xz = k(xs, Z) for one 128 x 64 block per CTA, written as three bf16 planes.
+// Direct differences (more accurate than the reference's |x|^2 - 2xz + |z|^2 expansion,
+// pyro Isotropy._square_scaled_dist); padding rows / columns are written as zeros.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs, int nc, const float* __restrict__ Z,
+                                                    int M, Hyper hp, PlaneMat kxz) {
+  __shared__ float zs[64][MAX_D];
+  __shared__ float inv_ls[MAX_D];
+  const int cb = blockIdx.x, rt = blockIdx.y, D = hp.D;
+  for (int t = threadIdx.x; t < 64 * D; t += blockDim.x) {
+    const int c = t / D, d = t - c * D;
+    const int col = cb * 64 + c;
+    zs[c][d] = (col < M) ? Z[col * D + d] : 0.f;
+  }
+  if (threadIdx.x < D) inv_ls[threadIdx.x] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : threadIdx.x];
+  __syncthreads();
+  const float var = hp.variance[0];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int idx = threadIdx.x + 256 * w;
+    const int r = idx & 127, g = idx >> 7;
+    const int n = rt * 128 + r;
+    float x[MAX_D];
+    if (n < nc)
+      for (int d = 0; d < D; ++d) x[d] = xs[(long long)n * D + d];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float val = 0.f;
+      if (n < nc && cb * 64 + c < M) {
+        float r2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float t = (x[d] - zs[c][d]) * inv_ls[d];
+          r2 = fmaf(t, t, r2);
+        }
+        float k, dk;
+        kernel_eval<float>(hp.kid, r2, k, dk);
+        val = var * k;
+      }
+      v[j] = val;
+    }
+    uint4 pk[3];
+    split8<3>(v, pk);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+      *reinterpret_cast<uint4*>(kxz.elem(pl, n, cb * 64 + g * 8)) = pk[pl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110), 2 planes; zero elsewhere.
+// grid (Mp/64 [j tile], Mp/64 [i tile], K), 256 threads; transposes through shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, int K, int M, int Mp, PlaneMat st) {
+  __shared__ float tile[64][65];
+  const int jt = blockIdx.x, it = blockIdx.y, k = blockIdx.z;
+  for (int t = threadIdx.x; t < 64 * 64; t += 256) {
+    const int ii = t >> 6, jj = t & 63;
+    const int i = it * 64 + ii, j = jt * 64 + jj;
+    tile[ii][jj] = (i < M && j < M && i >= j) ? S[((long long)k * M + i) * M + j] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 64 * 8; t += 256) {
+    const int jj = t >> 3, g = t & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tile[g * 8 + e][jj];
+    uint4 pk[2];
+    split8<2>(v, pk);
+    const int row = k * Mp + jt * 64 + jj;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
+  }
+}
+
+// LINV planes (3) from the fp64 inverse Cholesky factor [Mp][Mp]; identity padding is dropped.
+__global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Linv, int M, int Mp, PlaneMat linv) {
+  const int cb = blockIdx.x, rt = blockIdx.y;
+  for (int t = threadIdx.x; t < 128 * 8; t += 256) {
+    const int r = t >> 3, g = t & 7;
+    const int m = rt * 128 + r;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = cb * 64 + g * 8 + e;
+      v[e] = (m < M && i <= m) ? (float)Linv[(long long)m * Mp + i] : 0.f;
+    }
+    uint4 pk[3];
+    split8<3>(v, pk);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(linv.elem(pl, m, cb * 64 + g * 8)) = pk[pl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// f_loc[k, n] = sum_m W[n, m] u_loc[k, m]   (pyro conditional: loc = W @ v_2D; mean function is zero,
+// abstract_gdrf.py:17-18).  grid (RT, ceil(K/16)), 128 threads = rows; W rebuilt from its 3 planes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restrict__ u, int K, int M, int MB,
+                                              float* __restrict__ floc, int ncp) {
+  __shared__ float us[16][64];
+  const int rt = blockIdx.x, kg = blockIdx.y;
+  const int n = rt * 128 + threadIdx.x;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int mb = 0; mb < MB; ++mb) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 16 * 64; t += 128) {
+      const int kk = t >> 6, c = t & 63;
+      const int k = kg * 16 + kk, m = mb * 64 + c;
+      us[kk][c] = (k < K && m < M) ? u[(long long)k * M + m] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      uint4 pk[3];
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, n, mb * 64 + g * 8));
+      float wv[8];
+      join8<3>(pk, wv);
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float a = acc[kk];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(wv[j], us[kk][g * 8 + j], a);
+        acc[kk] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = kg * 16 + kk;
+    if (k < K) floc[(long long)k * ncp + n] = acc[kk];
+  }
+}
+
+__global__ void k_phisum(const float* __restrict__ phi, int K, int V, float* __restrict__ phisum) {
+  __shared__ float scratch[32];
+  const int k = blockIdx.x;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += phi[(long long)k * V + v];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) phisum[k] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per observation: marginal variance, reparameterised draw, the two Normal terms, topic softmax.
+//   var0 = clamp(variance - |W_n|^2, 0); f_var = var0 + q            (pyro conditional)
+//   mu = f_loc + f_var * eps   (guide Normal(f_loc, f_var): the variance is used as the scale,
+//                               sparse_gdrf.py:403-405)
+//   lq    += -log f_var - .5 log 2pi - .5 eps^2                                 (guide, :403-405)
+//   lp_mu += -log(f_var+noise) - .5 log 2pi - (f_var eps)^2 / (2 (f_var+noise)^2) (model, :354-357)
+//   theta = softmax_k(mu)  (abstract_gdrf.py:21-22);  s = sum_k theta_k * rowsum(phi)_k
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_obs_prepare(int nc, int ncp, int K, long long n0, long long n_stride,
+                                                     const float* __restrict__ floc, const float* __restrict__ q,
+                                                     const float* __restrict__ wsq, const float* __restrict__ eps,
+                                                     Hyper hp, const float* __restrict__ phisum,
+                                                     float* __restrict__ mu, float* __restrict__ fvar,
+                                                     float* __restrict__ theta, float* __restrict__ srow,
+                                                     double* __restrict__ acc) {
+  __shared__ double scratch[32];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double lq = 0.0, lp = 0.0;
+  if (n < nc) {
+    const float var = hp.variance[0], noise = hp.noise[0];
+    const float var0 = fmaxf(var - wsq[n], 0.f);
+    const float HALF_LOG_2PI = 0.91893853320467274178f;
+    float mx = -INFINITY;
+    float lqf = 0.f, lpf = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const long long o = (long long)k * ncp + n;
+      const float fv = var0 + q[o];
+      const float e = eps[(long long)k * n_stride + n0 + n];
+      const float d = fv * e;
+      const float m = floc[o] + d;
+      const float sp = fv + noise;
+      lqf += -logf(fv) - HALF_LOG_2PI - 0.5f * e * e;
+      const float z = d / sp;
+      lpf += -logf(sp) - HALF_LOG_2PI - 0.5f * z * z;
+      mu[o] = m;
+      fvar[o] = fv;
+      mx = fmaxf(mx, m);
+    }
+    float den = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const long long o = (long long)k * ncp + n;
+      const float ex = __expf(mu[o] - mx);
+      theta[o] = ex;
+      den += ex;
+    }
+    const float inv = 1.f / den;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const long long o = (long long)k * ncp + n;
+      const float t = theta[o] * inv;
+      theta[o] = t;
+      s = fmaf(t, phisum[k], s);
+    }
+    srow[n] = s;
+    lq = lqf;
+    lp = lpf;
+  }
+  lq = block_sum(lq, scratch);
+  lp = block_sum(lp, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&acc[ACC_LQ], lq);
+    atomicAdd(&acc[ACC_LP_MU], lp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused mixture + multinomial log-likelihood, forward and backward in one pass over ws
+// (sparse_gdrf.py:361-372 -> torch.distributions.Multinomial.log_prob):
+//   p = theta phi;  phat = p / sum_v p;  logit = log(clamp(phat, eps32, 1 - eps32))
+//   ll_n = lgamma(n_n + 1) - sum_v lgamma(w + 1) + sum_v w logit
+// The N x V probability matrix never leaves the SM.  Backward, with a_v = [eps32 <= phat <= 1-eps32],
+// r_v = w_v a_v / p_v and A_n = sum_v w_v a_v:
+//   d ll / d theta_k = sum_v phi_kv r_v - (A_n / s_n) rowsum(phi)_k          (G1 accumulates the first term)
+//   d ll / d phi_kv  = sum_n theta_nk r_nv - sum_n theta_nk A_n / s_n        (second term: k_obs_finalize)
+// 512 threads; observation tiles of 32; V processed in chunks of VJ*32 columns so that phi's chunk,
+// the r tile and the d-phi register accumulators fit on chip.
+// ---------------------------------------------------------------------------------------------
+constexpr int LK_THREADS = 512;
+constexpr int LK_TN = 32;
+
+template <int KPW, int VJ>
+__global__ void __launch_bounds__(LK_THREADS, 1)
+    k_likelihood(int nc, int ncp, int K, int V, const int* __restrict__ ws, const float* __restrict__ theta,
+                 const float* __restrict__ srow, const float* __restrict__ phi, float* __restrict__ g1 /*[ncp][K]*/,
+                 float* __restrict__ arow, float* __restrict__ cnt, double* __restrict__ dphi_acc /*[K][V]*/,
+                 double* __restrict__ acc) {
+  constexpr int VC = VJ * 32;
+  extern __shared__ float lk_smem[];
+  float* phis = lk_smem;                     // [K][VC + 1]
+  float* rt = phis + K * (VC + 1);           // [TN][VC]
+  float* th = rt + LK_TN * VC;               // [TN][K + 1]
+  float* sinv = th + LK_TN * (K + 1);        // [TN]
+  __shared__ double scratch[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (nc + LK_TN - 1) / LK_TN;
+  const float EPS32 = 1.1920928955078125e-07f;
+  double ll_local = 0.0;
+
+  for (int v0 = 0; v0 < V; v0 += VC) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < K * VC; t += LK_THREADS) {
+      const int k = t / VC, v = t - k * VC;
+      phis[k * (VC + 1) + v] = (v0 + v < V) ? phi[(long long)k * V + v0 + v] : 0.f;
+    }
+    float dacc[KPW][VJ];
+#pragma unroll
+    for (int a = 0; a < KPW; ++a)
+#pragma unroll
+      for (int j = 0; j < VJ; ++j) dacc[a][j] = 0.f;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nb = tile * LK_TN;
+      __syncthreads();
+      for (int t = threadIdx.x; t < LK_TN * K; t += LK_THREADS) {
+        const int k = t / LK_TN, i = t - k * LK_TN;
+        th[i * (K + 1) + k] = (nb + i < nc) ? theta[(long long)k * ncp + nb + i] : 0.f;
+      }
+      if (threadIdx.x < LK_TN) sinv[threadIdx.x] = (nb + threadIdx.x < nc) ? 1.f / srow[nb + threadIdx.x] : 0.f;
+      __syncthreads();
+      // ---- (b) p, log-likelihood, r ----
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int i = warp * 2 + h;
+        const int n = nb + i;
+        float llp = 0.f, ap = 0.f, cp = 0.f;
+        const float* thi = th + i * (K + 1);
+        const float si = sinv[i];
+#pragma unroll 1
+        for (int j = 0; j < VJ; ++j) {
+          const int v = lane + 32 * j;
+          float r = 0.f;
+          if (n < nc && v0 + v < V) {
+            const int c = ws[(long long)n * V + v0 + v];
+            if (c != 0) {
+              float p = 0.f;
+              for (int k = 0; k < K; ++k) p = fmaf(thi[k], phis[k * (VC + 1) + v], p);
+              const float ph = p * si;
+              const float pc = fminf(fmaxf(ph, EPS32), 1.f - EPS32);
+              const float cf = (float)c;
+              llp += cf * __logf(pc) - (c > 1 ? lgammaf(cf + 1.f) : 0.f);
+              cp += cf;
+              if (ph >= EPS32 && ph <= 1.f - EPS32) {
+                ap += cf;
+                r = cf / p;
+              }
+            }
+          }
+          rt[i * VC + v] = r;
+        }
+        llp = warp_sum(llp);
+        ap = warp_sum(ap);
+        cp = warp_sum(cp);
+        if (lane == 0 && n < nc) {
+          ll_local += (double)llp;
+          if (v0 == 0) {
+            arow[n] = ap;
+            cnt[n] = cp;
+          } else {
+            arow[n] += ap;
+            cnt[n] += cp;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- (c) G1[n][k] = sum_v phi[k][v] r[n][v] : lanes = k, warps = observation pairs ----
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int i = warp * 2 + h;
+        const int n = nb + i;
+        for (int k = lane; k < K; k += 32) {
+          float a = 0.f;
+          const float* pk = phis + k * (VC + 1);
+          const float* ri = rt + i * VC;
+#pragma unroll 8
+          for (int v = 0; v < VC; ++v) a = fmaf(pk[v], ri[v], a);
+          if (n < nc) {
+            if (v0 == 0) g1[(long long)n * K + k] = a;
+            else g1[(long long)n * K + k] += a;
+          }
+        }
+      }
+      // ---- (d) dphi[k][v] += sum_n theta[n][k] r[n][v] : warps = k groups, lanes = v ----
+      {
+        const int kbase = warp * KPW;
+#pragma unroll 4
+        for (int i = 0; i < LK_TN; ++i) {
+          float rv[VJ];
+#pragma unroll
+          for (int j = 0; j < VJ; ++j) rv[j] = rt[i * VC + lane + 32 * j];
+#pragma unroll
+          for (int a = 0; a < KPW; ++a) {
+            const float t = (kbase + a < K) ? th[i * (K + 1) + kbase + a] : 0.f;
+#pragma unroll
+            for (int j = 0; j < VJ; ++j) dacc[a][j] = fmaf(t, rv[j], dacc[a][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < KPW; ++a) {
+      const int k = warp * KPW + a;
+      if (k < K) {
+#pragma unroll
+        for (int j = 0; j < VJ; ++j) {
+          const int v = v0 + lane + 32 * j;
+          if (v < V && dacc[a][j] != 0.f) atomicAdd(&dphi_acc[(long long)k * V + v], (double)dacc[a][j]);
+        }
+      }
+    }
+  }
+  ll_local = block_sum(ll_local, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[ACC_LL], ll_local);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per observation, after the likelihood pass: softmax backward and the gradients w.r.t. the
+// marginal mean / variance, noise and (directly) the kernel variance.
+//   g_theta_k = G1[n][k] - (A_n / s_n) rowsum(phi)_k ;  g_mu_k = theta_k (g_theta_k - sum_j theta_j g_theta_j)
+//   dELBO/df_var = -1/sp - eps^2 f_var noise / sp^3 + 1/f_var + g_mu eps      (sp = f_var + noise)
+//   dELBO/dnoise = -1/sp + eps^2 f_var^2 / sp^3
+//   gv0_n = sum_k dELBO/df_var  where the clamp var0 = max(variance - |W_n|^2, 0) is inactive
+// Outputs: g_loc = g_mu, g2 = 2 dELBO/df_var (row scale of R), gv0; padding rows are zeroed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, long long n0, long long n_stride,
+                                                      const float* __restrict__ theta, const float* __restrict__ srow,
+                                                      const float* __restrict__ g1, const float* __restrict__ arow,
+                                                      const float* __restrict__ cnt, const float* __restrict__ fvar,
+                                                      const float* __restrict__ wsq, const float* __restrict__ eps,
+                                                      Hyper hp, const float* __restrict__ phisum,
+                                                      float* __restrict__ g_loc, float* __restrict__ g2,
+                                                      float* __restrict__ gv0, double* __restrict__ ck,
+                                                      double* __restrict__ acc, int npad) {
+  __shared__ double scratch[32];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double dnoise = 0.0, dvar = 0.0, llc = 0.0;
+  const bool live = n < nc;
+  float ratio = 0.f;
+  if (live) {
+    const float noise = hp.noise[0], var = hp.variance[0];
+    ratio = arow[n] / srow[n];
+    float dot = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float gt = g1[(long long)n * K + k] - ratio * phisum[k];
+      dot = fmaf(theta[(long long)k * ncp + n], gt, dot);
+    }
+    float gsum = 0.f, dn = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const long long o = (long long)k * ncp + n;
+      const float gt = g1[(long long)n * K + k] - ratio * phisum[k];
+      const float gm = theta[o] * (gt - dot);
+      const float fv = fvar[o];
+      const float e = eps[(long long)k * n_stride + n0 + n];
+      const float sp = fv + noise;
+      const float isp = 1.f / sp;
+      const float e2 = e * e;
+      const float gv = -isp - e2 * fv * noise * isp * isp * isp + 1.f / fv + gm * e;
+      dn += -isp + e2 * fv * fv * isp * isp * isp;
+      g_loc[o] = gm;
+      g2[o] = 2.f * gv;
+      gsum += gv;
+    }
+    const bool clamp_open = (var - wsq[n]) >= 0.f;
+    const float g0 = clamp_open ? gsum : 0.f;
+    gv0[n] = g0;
+    dnoise = dn;
+    dvar = g0;
+    llc = lgamma((double)cnt[n] + 1.0);
+  } else if (n < npad) {
+    for (int k = 0; k < K; ++k) {
+      const long long o = (long long)k * ncp + n;
+      g_loc[o] = 0.f;
+      g2[o] = 0.f;
+    }
+    gv0[n] = 0.f;
+  }
+  // c_k = sum_n theta[n][k] A_n / s_n  (the renormalisation term of d ll / d phi)
+  for (int k = 0; k < K; ++k) {
+    float c = live ? theta[(long long)k * ncp + n] * ratio : 0.f;
+    c = warp_sum(c);
+    if (lane == 0 && c != 0.f) atomicAdd(&ck[k], (double)c);
+  }
+  dnoise = block_sum(dnoise, scratch);
+  dvar = block_sum(dvar, scratch);
+  llc = block_sum(llc, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&acc[ACC_DNOISE], dnoise);
+    atomicAdd(&acc[ACC_DVAR], dvar);
+    atomicAdd(&acc[ACC_LL], llc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// du_loc[k, m] += sum_n g_loc[k, n] W[n, m]          grid (MB, row splits), 256 threads
+// ---------------------------------------------------------------------------------------------
+template <int KQ>   // topics per thread = KQ (K <= 4 * KQ)
+__global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict__ g_loc, int K, int M, int RT, int ncp,
+                                            int tiles_per_cta, double* __restrict__ du_acc) {
+  const int cb = blockIdx.x;
+  const int c = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const int m = cb * 64 + c;
+  float a[KQ];
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) a[i] = 0.f;
+  const int rt0 = blockIdx.y * tiles_per_cta;
+  const int rt1 = min(RT, rt0 + tiles_per_cta);
+  for (int rt = rt0; rt < rt1; ++rt) {
+#pragma unroll 2
+    for (int r = 0; r < 128; ++r) {
+      const int n = rt * 128 + r;
+      float wv = 0.f;
+#pragma unroll
+      for (int pl = 2; pl >= 0; --pl) wv += __bfloat162float(*w.elem(pl, n, m));
+#pragma unroll
+      for (int i = 0; i < KQ; ++i) {
+        const int k = kq + 4 * i;
+        if (k < K) a[i] = fmaf(g_loc[(long long)k * ncp + n], wv, a[i]);
+      }
+    }
+  }
+  if (m < M) {
+#pragma unroll
+    for (int i = 0; i < KQ; ++i) {
+      const int k = kq + 4 * i;
+      if (k < K) atomicAdd(&du_acc[(long long)k * M + m], (double)a[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 3 planes
+// grid (MB, RT), 256 threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __restrict__ dw, int Mp,
+                                                     const float* __restrict__ g_loc, const float* __restrict__ gv0,
+                                                     const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt) {
+  extern __shared__ float dwf_smem[];
+  float* us = dwf_smem;            // [K][64]
+  float* gs = us + K * 64;         // [K][128]
+  const int cb = blockIdx.x, rt = blockIdx.y;
+  for (int t = threadIdx.x; t < K * 64; t += 256) {
+    const int k = t >> 6, c = t & 63;
+    const int m = cb * 64 + c;
+    us[t] = (m < M) ? u[(long long)k * M + m] : 0.f;
+  }
+  for (int t = threadIdx.x; t < K * 128; t += 256) {
+    const int k = t >> 7, r = t & 127;
+    gs[t] = g_loc[(long long)k * ncp + rt * 128 + r];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int wv = 0; wv < 4; ++wv) {
+    const int idx = threadIdx.x + 256 * wv;
+    const int r = idx & 127, g = idx >> 7;
+    const int n = rt * 128 + r;
+    const int col = cb * 64 + g * 8;
+    uint4 pk[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, n, col));
+    float wj[8];
+    join8<3>(pk, wj);
+    const float4* src = reinterpret_cast<const float4*>(dw + (long long)n * Mp + col);
+    const float4 d0 = src[0], d1 = src[1];
+    float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float m2g = -2.f * gv0[n];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(m2g, wj[j], v[j]);
+    for (int k = 0; k < K; ++k) {
+      const float gk = gs[k * 128 + r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(gk, us[k * 64 + g * 8 + j], v[j]);
+    }
+    uint4 out[3];
+    split8<3>(v, out);
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, n, col)) = out[pl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain dKxz into the kernel hyper-parameters and the inducing points:
+//   K_xz[n,i] = variance * f(r2),  r2 = sum_d ((x_nd - z_id) / l_d)^2
+//   dvariance += dKxz f ;  dl_d += dKxz variance f' (-2 (x-z)^2 / l_d^3) ;  dZ[i,d] += dKxz variance f' (-2 (x-z)/l_d^2)
+// grid (Mp/128, row splits), 128 threads = columns i.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ dkxz, int Mp, const float* __restrict__ xs,
+                                                      int nc, const float* __restrict__ Z, int M, Hyper hp,
+                                                      int rows_per_cta, double* __restrict__ dz_acc,
+                                                      double* __restrict__ acc) {
+  __shared__ double scratch[32];
+  __shared__ float xsh[128][MAX_D];
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int D = hp.D;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(nc, r0 + rows_per_cta);
+  float z[MAX_D], il[MAX_D];
+  for (int d = 0; d < D; ++d) {
+    z[d] = (i < M) ? Z[i * D + d] : 0.f;
+    il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+  }
+  const float var = hp.variance[0];
+  float dz[MAX_D], dl[MAX_D];
+  for (int d = 0; d < D; ++d) dz[d] = dl[d] = 0.f;
+  float dv = 0.f;
+  for (int rb = r0; rb < r1; rb += 128) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 128 * D; t += 128) {
+      const int r = t / D, d = t - r * D;
+      xsh[r][d] = (rb + r < r1) ? xs[(long long)(rb + r) * D + d] : 0.f;
+    }
+    __syncthreads();
+    const int rn = min(128, r1 - rb);
+    if (i < M) {
+      for (int r = 0; r < rn; ++r) {
+        const float g = dkxz[(long long)(rb + r) * Mp + i];
+        float diff[MAX_D];
+        float r2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          diff[d] = (xsh[r][d] - z[d]) * il[d];
+          r2 = fmaf(diff[d], diff[d], r2);
+        }
+        float k, dk;
+        kernel_eval<float>(hp.kid, r2, k, dk);
+        dv = fmaf(g, k, dv);
+        const float h = g * var * dk;
+        for (int d = 0; d < D; ++d) {
+          dz[d] = fmaf(h, -2.f * diff[d] * il[d], dz[d]);
+          dl[d] = fmaf(h, -2.f * diff[d] * diff[d] * il[d], dl[d]);
+        }
+      }
+    }
+  }
+  if (i < M)
+    for (int d = 0; d < D; ++d) atomicAdd(&dz_acc[i * D + d], (double)dz[d]);
+  double dvs = block_sum((double)dv, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dvs);
+  if (hp.ls_dim == 1) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += dl[d];
+    double t = block_sum((double)s, scratch);
+    if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS], t);
+  } else {
+    for (int d = 0; d < D; ++d) {
+      double t = block_sum((double)dl[d], scratch);
+      if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS + d], t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dirichlet prior on phi (sparse_gdrf.py:358-360) and the final gradient assembly into the flat
+// fp32 buffer  [dS K*M*M | du K*M | dphi K*V | dZ M*D | dvariance | dlengthscale ls_dim | dnoise].
+// dS is accumulated in place by G6; everything else comes from the fp64 accumulators.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prior(const float* __restrict__ phi, const float* __restrict__ beta, int K, int V,
+                        double* __restrict__ acc) {
+  __shared__ double scratch[32];
+  const int k = blockIdx.x;
+  double sb = 0.0, t = 0.0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const double b = beta[(long long)k * V + v];
+    sb += b;
+    t += (b - 1.0) * log((double)phi[(long long)k * V + v]) - lgamma(b);
+  }
+  sb = block_sum(sb, scratch);
+  t = block_sum(t, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[ACC_LP_PHI], lgamma(sb) + t);
+}
+
+__global__ void k_assemble(int K, int M, int V, int D, int ls_dim, int include_prior, const float* __restrict__ phi,
+                           const float* __restrict__ beta, const double* __restrict__ acc,
+                           const double* __restrict__ ck, const double* __restrict__ du_acc,
+                           const double* __restrict__ dphi_acc, const double* __restrict__ dz_acc,
+                           float* __restrict__ grad) {
+  const long long oS = 0, oU = oS + (long long)K * M * M, oP = oU + (long long)K * M, oZ = oP + (long long)K * V,
+                  oV = oZ + (long long)M * D, oL = oV + 1, oN = oL + ls_dim;
+  const long long total = (long long)K * M + (long long)K * V + (long long)M * D + 2 + ls_dim;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long idx = t;
+    if (idx < (long long)K * M) { grad[oU + idx] = (float)du_acc[idx]; continue; }
+    idx -= (long long)K * M;
+    if (idx < (long long)K * V) {
+      const int k = (int)(idx / V);
+      double g = dphi_acc[idx] - ck[k];
+      if (include_prior) g += ((double)beta[idx] - 1.0) / (double)phi[idx];
+      grad[oP + idx] = (float)g;
+      continue;
+    }
+    idx -= (long long)K * V;
+    if (idx < (long long)M * D) { grad[oZ + idx] = (float)dz_acc[idx]; continue; }
+    idx -= (long long)M * D;
+    if (idx == 0) { grad[oV] = (float)acc[ACC_DVAR]; continue; }
+    idx -= 1;
+    if (idx < ls_dim) { grad[oL + idx] = (float)acc[ACC_DLS + idx]; continue; }
+    grad[oN] = (float)acc[ACC_DNOISE];
+  }
+}
+
+}  // namespace gdrf

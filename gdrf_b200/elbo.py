@@ -1,0 +1,228 @@
+"""The ELBO of the sparse multinomial GDRF as one custom autograd op over the C ABI.
+
+``GDRFElbo.apply`` replaces everything ``pyro.infer.SVI.step`` evaluates for
+``SparseMultinomialGDRF.model`` / ``.guide`` (reference ``gdrf/models/sparse_gdrf.py:322-409``): kernel
+matrices, the jitter-escalating Cholesky (``gdrf/models/utils.py:27-40``), the whitened sparse-GP
+conditional, the reparameterised draw of ``mu``, both Normal terms, the Dirichlet prior on ``phi``, the
+topic softmax, the theta-phi mixture and the multinomial log-likelihood -- and their gradients.
+
+Inputs are the *constrained* parameter values; autograd chains through the constraint transforms
+outside the op.  The value returned is ELBO / n_global for the observations handed in (this rank's
+shard); the reference's loss (``poutine.scale(1/N)``, ``train_script.py:365``) is its negative.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index or 0, 0)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _WORKSPACES.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _WORKSPACES.clear()
+
+
+def _f32(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def effective_jitter(jitter: float, njitter: int) -> float:
+    """Diagonal loading after ``njitter`` failed attempts: the reference adds jitter*10^i cumulatively
+    and in place (``gdrf/models/utils.py:33``)."""
+    return float(sum(jitter * (10 ** i) for i in range(njitter + 1)))
+
+
+class _Call:
+    """Validated shapes + ctypes structs for one evaluation."""
+
+    def __init__(self, xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
+                 kernel_id, n_offset, flags, chunk_rows):
+        if not xs.is_cuda:
+            raise RuntimeError("gdrf_b200 runs on an sm_100a CUDA device only; there is no CPU path")
+        dev = xs.device
+        self.device = dev
+        N, D = xs.shape
+        M = Z.shape[0]
+        K = u_loc.shape[0]
+        V = ws.shape[1]
+        if ws.shape[0] != N:
+            raise ValueError(f"xs has {N} rows but ws has {ws.shape[0]}")
+        if Z.shape[1] != D:
+            raise ValueError("Inducing points and data should have the same number of dimensions, "
+                             f"but got {Z.shape[1]} and {D}.")
+        if u_loc.shape != (K, M) or (u_scale_tril is not None and u_scale_tril.shape != (K, M, M)):
+            raise ValueError("u_loc must be [K, M] and u_scale_tril [K, M, M]")
+        if phi.shape != (K, V) or beta.shape != (K, V):
+            raise ValueError("phi and beta must be [K, V]")
+        if eps.dim() != 2 or eps.shape[0] != K or eps.shape[1] < n_offset + N:
+            raise ValueError("eps must be [K, >= n_offset + N]")
+        ls = lengthscale.reshape(-1)
+        if ls.numel() not in (1, D):
+            raise ValueError("lengthscale must have 1 or D entries")
+        self.t = dict(
+            xs=_f32(xs, "xs", dev), ws=ws.detach().to(torch.int32).contiguous(), eps=_f32(eps, "eps", dev),
+            z=_f32(Z, "Z", dev), variance=_f32(variance.reshape(1), "variance", dev),
+            lengthscale=_f32(ls, "lengthscale", dev), u_loc=_f32(u_loc, "u_loc", dev),
+            u_scale_tril=None if u_scale_tril is None else _f32(u_scale_tril, "u_scale_tril", dev), noise=_f32(noise.reshape(1), "noise", dev),
+            phi=_f32(phi, "phi", dev), beta=_f32(beta, "beta", dev))
+        if self.t["ws"].device != dev:
+            raise ValueError("ws must live on the same device as xs")
+        self.shape = _lib.Shape(n_local=N, n_offset=int(n_offset), n_eps=int(eps.shape[1]), d=D, m=M, k=K, v=V,
+                                kernel_id=int(kernel_id), ls_dim=int(ls.numel()), chunk_rows=int(chunk_rows),
+                                flags=int(flags))
+        self.inputs = _lib.Inputs(**{k: (None if v is None else v.data_ptr()) for k, v in self.t.items()})
+        self.ws_bytes = _lib.workspace_bytes(self.shape)
+        self.workspace = _workspace(dev, self.ws_bytes)
+        self.stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def prologue(self, jitter: float, maxjitter: int) -> int:
+        """jittercholesky (utils.py:27-40): escalate until the factorisation succeeds."""
+        lib = _lib.load()
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for nj in range(int(maxjitter)):
+            _lib.check(lib.gdrf_prologue(ctypes.byref(self.shape), ctypes.byref(self.inputs), float(jitter), nj,
+                                         self.workspace.data_ptr(), self.ws_bytes, self.stream, status.data_ptr()))
+            if int(status.item()) == 0:      # the one host read-back of the step (mirrors try/except)
+                return nj
+        raise RuntimeError("reached max jitter, covariance is unstable")
+
+    def step(self, want_grad: bool):
+        lib = _lib.load()
+        terms = torch.empty(4, dtype=torch.float64, device=self.device)
+        grad = None
+        flags = self.shape.flags & ~_lib.FLAG_WANT_GRAD
+        if want_grad:
+            flags |= _lib.FLAG_WANT_GRAD
+            grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
+        self.shape.flags = flags
+        out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None)
+        _lib.check(lib.gdrf_elbo_step(ctypes.byref(self.shape), ctypes.byref(self.inputs), ctypes.byref(out),
+                                      self.workspace.data_ptr(), self.ws_bytes, self.stream))
+        return terms, grad
+
+
+def split_grad(flat: torch.Tensor, K: int, M: int, V: int, D: int, ls_dim: int):
+    """Views into the flat gradient of include/gdrf_b200.h:gdrf_outputs."""
+    o = 0
+    out = {}
+    for name, shape in (("u_scale_tril", (K, M, M)), ("u_loc", (K, M)), ("phi", (K, V)), ("Z", (M, D)),
+                        ("variance", ()), ("lengthscale", (ls_dim,)), ("noise", ())):
+        n = 1
+        for s in shape:
+            n *= s
+        out[name] = flat[o:o + n].view(shape)
+        o += n
+    return out
+
+
+class GDRFElbo(torch.autograd.Function):
+    """elbo_over_n = GDRFElbo.apply(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta,
+    eps, kernel_id, jitter, maxjitter, n_global, n_offset, include_prior, flags, chunk_rows)"""
+
+    last_terms: Optional[torch.Tensor] = None   # [lp_mu, lq, ll, lp_phi] of the most recent call (device, fp64)
+    last_njitter: int = 0
+
+    @staticmethod
+    def forward(ctx, xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
+                kernel_id: int, jitter: float, maxjitter: int, n_global: int, n_offset: int = 0,
+                include_prior: bool = True, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+        fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
+        call = _Call(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
+                     kernel_id, n_offset, fl, chunk_rows)
+        want_grad = any(ctx.needs_input_grad[i] for i in (2, 3, 4, 5, 6, 7, 8))
+        GDRFElbo.last_njitter = call.prologue(jitter, maxjitter)
+        terms, grad = call.step(want_grad)
+        GDRFElbo.last_terms = terms
+        ctx.n_global = int(n_global)
+        ctx.dims = (u_loc.shape[0], Z.shape[0], ws.shape[1], xs.shape[1], call.shape.ls_dim)
+        ctx.ls_shape = lengthscale.shape
+        ctx.var_shape = variance.shape
+        ctx.noise_shape = noise.shape
+        ctx.dtypes = tuple(t.dtype for t in (Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi))
+        ctx.stream = call.stream
+        if grad is not None:
+            ctx.save_for_backward(grad)
+        elbo = (terms[0] + terms[3] + terms[2] - terms[1]) / float(n_global)
+        return elbo.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (flat,) = ctx.saved_tensors
+        lib = _lib.load()
+        dst = torch.empty_like(flat)
+        go = grad_out.detach().to(torch.float32).contiguous()
+        _lib.check(lib.gdrf_elbo_backward(flat.data_ptr(), flat.numel(), go.data_ptr(), 1.0 / ctx.n_global,
+                                          dst.data_ptr(), torch.cuda.current_stream(flat.device).cuda_stream))
+        K, M, V, D, ls_dim = ctx.dims
+        g = split_grad(dst, K, M, V, D, ls_dim)
+        dZ, dvar, dls, du, dS, dnoise, dphi = (g["Z"], g["variance"].reshape(ctx.var_shape),
+                                               g["lengthscale"].reshape(ctx.ls_shape), g["u_loc"],
+                                               g["u_scale_tril"], g["noise"].reshape(ctx.noise_shape), g["phi"])
+        outs = [dZ, dvar, dls, du, dS, dnoise, dphi]
+        outs = [o.to(dt) if ctx.needs_input_grad[i + 2] else None for i, (o, dt) in enumerate(zip(outs, ctx.dtypes))]
+        return (None, None, *outs, None, None, None, None, None, None, None, None, None, None)
+
+
+def elbo_value_and_grads(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
+                         kernel: str = "rbf", jitter: float = 1e-8, maxjitter: int = 5, n_global=None,
+                         n_offset: int = 0, include_prior: bool = True,
+                         flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+    """Direct (no autograd graph) evaluation: returns (terms fp64[4] = lp_mu, lq, ll, lp_phi;
+    dict of d ELBO_sum / d constrained parameter; njitter)."""
+    fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
+    call = _Call(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
+                 _lib.KERNEL_IDS[kernel], n_offset, fl, chunk_rows)
+    nj = call.prologue(jitter, maxjitter)
+    terms, grad = call.step(True)
+    g = split_grad(grad, u_loc.shape[0], Z.shape[0], ws.shape[1], xs.shape[1], call.shape.ls_dim)
+    return terms, g, nj
+
+
+def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitter: float = 1e-8,
+                  maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0) -> torch.Tensor:
+    """f_loc [K, N] of ``log_topic_probs`` (sparse_gdrf.py:161-186)."""
+    K, M = u_loc.shape
+    N = xs.shape[0]
+    dev = xs.device
+    dummy_ws = torch.zeros(N, 1, dtype=torch.int32, device=dev)
+    call = _Call(xs, dummy_ws, Z, variance, lengthscale, u_loc,
+                 None, torch.ones((), device=dev), torch.ones(K, 1, device=dev),
+                 torch.ones(K, 1, device=dev), torch.zeros(K, N, device=dev), _lib.KERNEL_IDS[kernel], 0, flags,
+                 chunk_rows)
+    call.prologue(jitter, maxjitter)
+    out = torch.empty(K, N, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().gdrf_marginal_mean(ctypes.byref(call.shape), ctypes.byref(call.inputs), out.data_ptr(),
+                                              call.workspace.data_ptr(), call.ws_bytes, call.stream))
+    return out
+
+
+def perplexity_from_mean(floc: torch.Tensor, ws: torch.Tensor, phi: torch.Tensor) -> torch.Tensor:
+    """exp(-sum w log(word_probs) / sum w)  (abstract_gdrf.py:137-139) without the N x V matrix."""
+    K, N = floc.shape
+    V = ws.shape[1]
+    dev = floc.device
+    shape = _lib.Shape(n_local=N, n_offset=0, n_eps=N, d=1, m=1, k=K, v=V, kernel_id=0, ls_dim=1, chunk_rows=0, flags=0)
+    wsc = ws.detach().to(torch.int32).contiguous()
+    phic = phi.detach().to(torch.float32).contiguous()
+    inputs = _lib.Inputs(ws=wsc.data_ptr(), phi=phic.data_ptr())
+    out = torch.zeros(2, dtype=torch.float64, device=dev)
+    fl = floc.detach().to(torch.float32).contiguous()
+    _lib.check(_lib.load().gdrf_perplexity_terms(ctypes.byref(shape), ctypes.byref(inputs), fl.data_ptr(),
+                                                 out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return torch.exp(-out[0] / out[1]).to(torch.float32)

@@ -1,0 +1,266 @@
+"""Drop-in for ``gdrf.models.SparseMultinomialGDRF`` (reference ``gdrf/models/sparse_gdrf.py:16-129,
+322-409`` and its bases ``abstract_gdrf.py`` / ``topic_model.py``) with the ELBO evaluated by the fused
+sm_100a op in :mod:`gdrf_b200.elbo`.
+
+Same constructor keywords, parameter names (``u_loc``, ``u_scale_tril``, ``noise``, ``_inducing_points``,
+``_word_topic_matrix_map``, ``_kernel.variance``, ``_kernel.lengthscale`` -- each stored
+``<name>_unconstrained`` the way ``pyro.nn.PyroParam`` stores them), methods (``model``, ``guide``,
+``log_topic_probs``, ``topic_probs``, ``word_probs``, ``perplexity``, ``ml_topics``, ``ml_words``,
+``scale``, ``artifacts``) and error behaviour.  Only ``whiten=True`` with the default zero mean and
+softmax link is accelerated; anything else raises ``NotImplementedError`` (there is no fallback path).
+
+When Pyro is importable, ``model`` contributes the whole ELBO as one ``pyro.factor`` and ``guide``
+registers nothing to sample, so ``pyro.infer.SVI(model=scale(m.model), guide=scale(m.guide), ...)``
+(``train_script.py:365-371``) sees the identical loss and gradients.  Without Pyro,
+:class:`gdrf_b200.svi.SVI` provides the same ``step(xs=, ws=, subsample=)`` call.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _lib
+from .elbo import GDRFElbo, marginal_mean, perplexity_from_mean
+from .kernels import kernel_kind
+
+try:  # optional: the reference's inference driver
+    import pyro  # type: ignore
+    _HAVE_PYRO = True
+except Exception:  # pragma: no cover - pyro is absent in the build image
+    pyro = None
+    _HAVE_PYRO = False
+
+
+def validate_dirichlet_param(b: torch.Tensor, K: int, V: int, device="cuda") -> torch.Tensor:
+    """gdrf/models/utils.py:6-24."""
+    assert (b <= 0).sum().item() == 0, "b must be positive"
+    if b.dim() == 0:
+        return torch.ones(K, V, device=device) * b.to(device)
+    if b.dim() == 1:
+        if b.shape[0] == K:
+            return b.repeat(V, 1).T.to(device)
+        if b.shape[0] == V:
+            return b.repeat(K, 1).to(device)
+        raise ValueError("parameter b must have length K or V if 1D")
+    if b.dim() == 2:
+        assert b.shape == torch.Size((K, V)), "b should be KxV if 2D"
+        return b.to(device)
+    raise ValueError("invalid b parameter- you passed %s" % (b,))
+
+
+def host_jittercholesky(Kff: torch.Tensor, N: int, jitter: float, maxjitter: int) -> torch.Tensor:
+    """gdrf/models/utils.py:27-40, used once by the constructor to initialise u_scale_tril."""
+    Kff = Kff.clone()
+    njitter = 0
+    while njitter < maxjitter:
+        try:
+            Kff.view(-1)[:: N + 1] += jitter * (10 ** njitter)
+            return torch.linalg.cholesky(Kff)
+        except RuntimeError:
+            njitter += 1
+    raise RuntimeError("reached max jitter, covariance is unstable")
+
+
+class SparseMultinomialGDRF(nn.Module):
+    def __init__(self, num_observation_categories: int, num_topic_categories: int,
+                 world: List[Tuple[float, float]], kernel, dirichlet_param: Union[float, torch.Tensor],
+                 n_points: Union[int, List[int]], fixed_inducing_points: bool = False,
+                 inducing_init: str = "random", mean_function: Callable = None, link_function: Callable = None,
+                 noise: Optional[float] = None, device: str = "cpu", whiten: bool = True, jitter: float = 1e-8,
+                 maxjitter: int = 5, randomize_wt_matrix: bool = False, randomize_metric=None,
+                 randomize_iters: int = 100, **kwargs):
+        super().__init__()
+        if mean_function is not None or link_function is not None:
+            raise NotImplementedError("only the default zero mean and softmax link are accelerated")
+        if not whiten:
+            raise NotImplementedError("only whiten=True is accelerated")
+        self._V = int(num_observation_categories)
+        self._K = int(num_topic_categories)
+        self.device = torch.device(device)
+        self._world = world
+        self._lower_bounds = torch.tensor([b[0] for b in world], dtype=torch.float32, device=self.device)
+        self._upper_bounds = torch.tensor([b[1] for b in world], dtype=torch.float32, device=self.device)
+        self._delta_bounds = self._upper_bounds - self._lower_bounds
+        self._n_dims = len(world)
+        self._kernel = kernel.to(self.device)
+        self._kernel_kind = kernel_kind(kernel)
+        if isinstance(dirichlet_param, float):
+            dirichlet_param = torch.tensor(dirichlet_param)
+        self._dirichlet_param = validate_dirichlet_param(torch.as_tensor(dirichlet_param, dtype=torch.float32),
+                                                         self._K, self._V, device=self.device)
+        self._n_points = [n_points for _ in world] if isinstance(n_points, int) else list(n_points)
+        self._fixed_inducing_points = fixed_inducing_points
+        if inducing_init == "random":
+            points = [torch.sort(torch.rand(self._n_points[i]))[0].to(self.device) * self._delta_bounds[i]
+                      + self._lower_bounds[i] for i in range(self.dims)]
+        elif inducing_init == "grid":
+            points = [torch.arange(b[0], b[1] + (b[1] - b[0]) / (n - 1) - 1e-10, (b[1] - b[0]) / (n - 1))
+                      for b, n in zip(world, self._n_points)]
+        else:
+            raise ValueError(f"inducing_init argument {inducing_init} not valid. Only 'random' and 'grid' "
+                             "are currently supported")
+        inducing = torch.stack([x.flatten() for x in torch.meshgrid(*points, indexing="ij")]).T.to(self.device)
+        scaled = self.scale(inducing.float())
+        if fixed_inducing_points:
+            self.register_buffer("_inducing_points_fixed", scaled)
+        else:   # interval(0, 1) per dimension -> sigmoid
+            sc = scaled.clamp(1e-6, 1 - 1e-6)
+            self._inducing_points_unconstrained = nn.Parameter(torch.log(sc) - torch.log1p(-sc))
+        self._jitter = float(jitter)
+        self._maxjitter = int(maxjitter)
+        self._whiten = whiten
+        self.M = scaled.size(-2)
+        self.D = scaled.size(-1)
+        self.u_loc_unconstrained = nn.Parameter(torch.zeros(self._K, self.M, device=self.device))
+        with torch.no_grad():
+            L = host_jittercholesky(self._kernel(scaled).contiguous(), self.M, self._jitter, self._maxjitter)
+        S0 = L.float().repeat(self._K, 1, 1)
+        # lower_cholesky: strictly-lower entries free, diagonal through exp
+        unc = S0.tril(-1) + S0.diagonal(dim1=-2, dim2=-1).log().diag_embed()
+        self.u_scale_tril_unconstrained = nn.Parameter(unc)
+        noise = torch.tensor(1.0) if noise is None else torch.as_tensor(noise, dtype=torch.float32)
+        self.noise_unconstrained = nn.Parameter(noise.to(self.device).log())
+        # make_wt_matrix (abstract_gdrf.py:57-84): softmax over the *topic* axis of beta, then stored through
+        # the stacked-simplex constraint (unconstrained = log p, constrained = row softmax)
+        wt = torch.softmax(self._dirichlet_param, dim=-2)
+        if randomize_wt_matrix:
+            wt = torch.softmax(torch.randn_like(wt), dim=-2)
+        self._word_topic_matrix_map_unconstrained = nn.Parameter(wt.log())
+        self._eps_generator: Optional[torch.Generator] = None
+        self.num_particles = 1
+        if "xs" in kwargs and "ws" in kwargs and self.device.type == "cuda":
+            with torch.no_grad():       # the reference runs self.model once at the end of __init__ (:123)
+                self.elbo(kwargs["xs"].to(self.device), kwargs["ws"].to(self.device))
+
+    # ------------------------------------------------------------------ constrained views
+    @property
+    def K(self): return self._K
+
+    @property
+    def V(self): return self._V
+
+    @property
+    def dims(self): return self._n_dims
+
+    @property
+    def u_loc(self): return self.u_loc_unconstrained
+
+    @property
+    def u_scale_tril(self):
+        u = self.u_scale_tril_unconstrained
+        return u.tril(-1) + u.diagonal(dim1=-2, dim2=-1).exp().diag_embed()
+
+    @property
+    def noise(self): return self.noise_unconstrained.exp()
+
+    @property
+    def _inducing_points(self):
+        if self._fixed_inducing_points:
+            return self._inducing_points_fixed
+        return torch.sigmoid(self._inducing_points_unconstrained)
+
+    @property
+    def _word_topic_matrix_map(self):
+        return torch.softmax(self._word_topic_matrix_map_unconstrained, dim=-1)
+
+    @property
+    def word_topic_matrix(self): return self._word_topic_matrix_map
+
+    @property
+    def kernel_lengthscale(self): return self._kernel.lengthscale.detach().cpu().numpy()
+
+    @property
+    def kernel_variance(self): return self._kernel.variance.detach().cpu().numpy()
+
+    # ------------------------------------------------------------------ input scaling (topic_model.py:168-198)
+    def scale(self, input: torch.Tensor) -> torch.Tensor:
+        return (input - self._lower_bounds) / self._delta_bounds
+
+    def _check_bounds(self, input: torch.Tensor, epsilon: float = 1e-8) -> bool:
+        inp = input.to(self.device)
+        return bool(input.shape[-1] == self._n_dims and ((inp - self._lower_bounds > -epsilon)
+                                                         & (inp - self._upper_bounds < epsilon)).all())
+
+    def _scaled(self, xs: torch.Tensor) -> torch.Tensor:
+        assert self._check_bounds(xs)
+        return self.scale(xs.to(self.device).float())
+
+    def _check_Xnew_shape(self, Xnew: torch.Tensor):
+        Z = self._inducing_points
+        if Xnew.dim() != Z.dim():
+            raise ValueError("Inducing points and test data should have the same number of dimensions, "
+                             "but got {} and {}.".format(Z.dim(), Xnew.dim()))
+        if Z.shape[1:] != Xnew.shape[1:]:
+            raise ValueError("Inducing points and test data should have the same shape of features, "
+                             "but got {} and {}.".format(Z.shape[1:], Xnew.shape[1:]))
+
+    # ------------------------------------------------------------------ the hot path
+    def seed_eps(self, seed: int) -> None:
+        self._eps_generator = torch.Generator(device=self.device).manual_seed(int(seed))
+
+    def elbo(self, xs: torch.Tensor, ws: torch.Tensor, eps: Optional[torch.Tensor] = None,
+             n_global: Optional[int] = None, n_offset: int = 0, include_prior: bool = True,
+             flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0, scaled: bool = False) -> torch.Tensor:
+        """ELBO / N of model+guide for (xs, ws) -- differentiable w.r.t. every parameter.  ``eps`` are the
+        guide's standard-normal draws for the ``mu`` site ([K, N]); drawn on the device when omitted."""
+        xs = xs.to(self.device)
+        self._check_Xnew_shape(xs)
+        x = xs.float() if scaled else self._scaled(xs)
+        N = x.shape[0]
+        if eps is None:
+            eps = torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
+        n_global = N if n_global is None else int(n_global)
+        return GDRFElbo.apply(x, ws.to(self.device), self._inducing_points, self._kernel.variance,
+                              self._kernel.lengthscale, self.u_loc, self.u_scale_tril, self.noise,
+                              self._word_topic_matrix_map, self._dirichlet_param, eps,
+                              _lib.KERNEL_IDS[self._kernel_kind], self._jitter, self._maxjitter, n_global,
+                              n_offset, include_prior, flags, chunk_rows)
+
+    def model(self, xs, ws, subsample=False):
+        """sparse_gdrf.py:322-373.  Under Pyro: one factor carrying N * (ELBO / N); the enclosing
+        ``poutine.scale(1/N)`` (train_script.py:365) restores the reference's loss."""
+        if _HAVE_PYRO:
+            e = self.elbo(xs, ws)
+            pyro.factor("gdrf_elbo", e * xs.shape[0])
+            return ws
+        self._last_elbo = self.elbo(xs, ws)
+        return ws
+
+    def guide(self, xs, ws, subsample=False):
+        """sparse_gdrf.py:375-409.  Every guide site is reparameterised and folded into ``model``'s factor."""
+        return None
+
+    # ------------------------------------------------------------------ evaluation path (abstract_gdrf.py:113-139)
+    def log_topic_probs(self, xs):
+        xs = xs.to(self.device)
+        self._check_Xnew_shape(xs)
+        return marginal_mean(self._scaled(xs), self._inducing_points, self._kernel.variance,
+                             self._kernel.lengthscale, self.u_loc, self._kernel_kind, self._jitter, self._maxjitter)
+
+    def topic_probs(self, xs):
+        return torch.softmax(self.log_topic_probs(xs), -2).T
+
+    def word_probs(self, xs):
+        return self.topic_probs(xs) @ self.word_topic_matrix
+
+    def ml_topics(self, xs):
+        return torch.argmax(self.log_topic_probs(xs), dim=-2)
+
+    def ml_words(self, xs):
+        return torch.argmax(self.word_probs(xs), dim=-2)
+
+    def perplexity(self, x, w):
+        return perplexity_from_mean(self.log_topic_probs(x), w.to(self.device), self.word_topic_matrix)
+
+    def forward(self, Xnew, full_cov=False):
+        if full_cov:
+            raise NotImplementedError("full_cov=True is not accelerated")
+        raise NotImplementedError("forward(): use log_topic_probs for the marginal mean")
+
+    def artifacts(self, xs, ws, all: bool = False):
+        ret = {"kernel variance": self.kernel_variance, "kernel lengthscale": self.kernel_lengthscale}
+        if not self._fixed_inducing_points:
+            ret["inducing_points"] = self._inducing_points.detach().cpu().numpy()
+        return ret

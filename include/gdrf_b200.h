@@ -1,0 +1,118 @@
+/* gdrf_b200 -- C ABI of the B200-native sparse multinomial GDRF ELBO + gradient.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, no C++ or torch types.  It replaces, for
+ * the reference san-soucie/gdrf, everything that `pyro.infer.SVI.step` evaluates through
+ *   gdrf/models/sparse_gdrf.py:322-373   SparseMultinomialGDRF.model
+ *   gdrf/models/sparse_gdrf.py:375-409   SparseMultinomialGDRF.guide
+ *   gdrf/models/utils.py:27-40           jittercholesky
+ *   gdrf/models/sparse_gdrf.py:161-186   log_topic_probs (evaluation path)
+ * (and the pyro.contrib.gp kernels / `conditional` / torch.distributions code those call).
+ *
+ * Ownership: the caller owns every buffer (inputs, outputs, workspace); the library allocates nothing and
+ * keeps no global state besides a thread-local error string.  All pointers are DEVICE pointers unless
+ * stated otherwise.  All work is enqueued on `stream`; no call synchronises the device.  The only value
+ * the host has to read back between calls is the 4-byte Cholesky status (to reproduce the try/except
+ * escalation of jittercholesky).  Every entry point returns 0 on success and a non-zero code otherwise
+ * (gdrf_last_error() then describes it).  The library needs an sm_100a device; there is no CPU path.
+ */
+#ifndef GDRF_B200_H
+#define GDRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gdrf_stream_t; /* == cudaStream_t */
+
+enum { GDRF_KERNEL_RBF = 0, GDRF_KERNEL_MATERN32 = 1, GDRF_KERNEL_MATERN52 = 2 };
+
+enum {
+  GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
+  GDRF_FLAG_INCLUDE_PRIOR = 2,    /* add the Dirichlet log-density of phi and its gradient (one rank only)   */
+  GDRF_FLAG_CHOL_FP32_STATUS = 4, /* decide not-PD with an fp32 factorisation of the reference's fp32 Kuu    */
+  /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
+  GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
+  GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,
+  GDRF_FLAG_REF_ALL = 0x3f << 8
+};
+
+typedef struct gdrf_shape {
+  int64_t n_local;    /* observations in xs / ws / eps handed to this call (this rank's shard)               */
+  int64_t n_offset;   /* column of eps holding this shard's first observation                                */
+  int64_t n_eps;      /* row stride of eps (= total observations when eps is the global [K, N] tensor)        */
+  int32_t d;          /* input dimensions (<= 8)                                                              */
+  int32_t m;          /* inducing points (<= 4096)                                                            */
+  int32_t k;          /* topics (<= 128)                                                                      */
+  int32_t v;          /* observation categories                                                               */
+  int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT rbf / matern32 / matern52)        */
+  int32_t ls_dim;     /* 1 (isotropic lengthscale) or d                                                       */
+  int32_t chunk_rows; /* observations streamed per pass, multiple of 128; 0 = library default                 */
+  int32_t flags;      /* GDRF_FLAG_*                                                                          */
+} gdrf_shape;
+
+/* Constrained parameter values and data, row-major, fp32 unless noted. */
+typedef struct gdrf_inputs {
+  const float* xs;           /* [n_local, d]   observation locations, already scaled to the unit cube         */
+  const int32_t* ws;         /* [n_local, v]   category counts (train_script.py:268: int32)                   */
+  const float* eps;          /* [k, n_eps]     fixed standard-normal draws of the guide's mu site             */
+  const float* z;            /* [m, d]         inducing points                                                */
+  const float* variance;     /* [1]            kernel variance                                                */
+  const float* lengthscale;  /* [ls_dim]       kernel lengthscale                                             */
+  const float* u_loc;        /* [k, m]                                                                        */
+  const float* u_scale_tril; /* [k, m, m]      lower triangular (entries above the diagonal are ignored)      */
+  const float* noise;        /* [1]                                                                           */
+  const float* phi;          /* [k, v]         word-topic matrix, rows on the simplex                         */
+  const float* beta;         /* [k, v]         Dirichlet concentration                                        */
+} gdrf_inputs;
+
+/* terms[0..3] = { log p(mu), log q(mu), log p(w | mu, phi), log p(phi) } summed over this shard (fp64);
+ *   ELBO = terms[0] + terms[3] + terms[2] - terms[1];  the reference's loss is -ELBO / N (train_script.py:365).
+ * grad  = d ELBO / d (constrained parameter), fp32, laid out
+ *   [ u_scale_tril k*m*m | u_loc k*m | phi k*v | z m*d | variance 1 | lengthscale ls_dim | noise 1 ]
+ *   (gdrf_grad_elems() floats); u_scale_tril's entries above the diagonal are 0.                            */
+typedef struct gdrf_outputs {
+  double* terms; /* [4]                      */
+  float* grad;   /* [gdrf_grad_elems(shape)] or NULL when GDRF_FLAG_WANT_GRAD is clear                        */
+} gdrf_outputs;
+
+/* Sizes.  HOST out-pointers. */
+int gdrf_workspace_bytes(const gdrf_shape* shape, size_t* out_bytes);
+int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
+
+/* Kuu = k(Z,Z) + (sum_{i<=njitter} jitter*10^i) I, its Cholesky factor and inverse, packed for the tensor
+ * pipe; *dev_status (DEVICE int) = 0 when the factorisation succeeded, else 1 + the failing column.
+ * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39).          */
+int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
+                  size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
+
+/* One evaluation of the ELBO terms (and, with GDRF_FLAG_WANT_GRAD, of the full gradient) over this shard,
+ * streamed in chunks of chunk_rows observations.  Requires a successful gdrf_prologue on the same
+ * workspace with the same z / variance / lengthscale.                                                       */
+int gdrf_elbo_step(const gdrf_shape* shape, const gdrf_inputs* in, const gdrf_outputs* out, void* workspace,
+                   size_t workspace_bytes, gdrf_stream_t stream);
+
+/* Backward of the scalar op: dst[i] = scale_dev[0] * scale_host * grad[i] (autograd chain with the
+ * upstream gradient kept on the device).                                                                    */
+int gdrf_elbo_backward(const float* grad, int64_t elems, const float* scale_dev, float scale_host, float* dst,
+                       gdrf_stream_t stream);
+
+/* Evaluation path: marginal mean f_loc[k, n] = (W u_loc^T)^T (log_topic_probs, sparse_gdrf.py:161-186).
+ * out_floc is [k, n_local] fp32.  Requires gdrf_prologue.                                                   */
+int gdrf_marginal_mean(const gdrf_shape* shape, const gdrf_inputs* in, float* out_floc, void* workspace,
+                       size_t workspace_bytes, gdrf_stream_t stream);
+
+/* perplexity pieces (abstract_gdrf.py:137-139): out[0] = sum w log(word_probs), out[1] = sum w  (fp64),
+ * from f_loc [k, n_local]; the N x V word-probability matrix is never materialised.                        */
+int gdrf_perplexity_terms(const gdrf_shape* shape, const gdrf_inputs* in, const float* floc, double* out,
+                          gdrf_stream_t stream);
+
+const char* gdrf_last_error(void);
+const char* gdrf_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDRF_B200_H */
