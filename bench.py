@@ -1,0 +1,385 @@
+"""bench.py -- ELBO + gradient throughput of the sparse multinomial GDRF (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C4|C3|...]
+
+One "step" = one evaluation of the ELBO and its full gradient over the whole synthetic data set
+(SURVEY.md 8(d) inputs at BASELINE.json configs[3]: N=1M, D=3, K=32, V=512, M=1024=16x8x8, RBF), including
+the M x M prologue and, for N > 1 ranks, the all-reduce of the parameter gradients.  Observations are
+sharded by index across ranks (strong scaling: the data set is fixed, no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: N, D, K, V, grid, kernel      
+    "C1": dict(N=4800, D=2, K=5, V=100, grid=[25, 25], kernel="rbf"),
+    "C2": dict(N=100_000, D=1, K=8, V=174, grid=[1000], kernel="matern32"),
+    "C3": dict(N=100_000, D=2, K=16, V=128, grid=[16, 16], kernel="rbf"),
+    "C4": dict(N=1_000_000, D=3, K=32, V=512, grid=[16, 8, 8], kernel="rbf"),
+    "C5": dict(N=8_000_000, D=3, K=64, V=1024, grid=[16, 16, 8], kernel="matern52"),
+}
+METRIC = "ELBO+grad observations/sec (N=1M,K=32,V=512,M=1024) at 1/2/4/8 B200 vs CPU"
+GEN_CHUNK = 15_625          # data generated in seeded chunks so that any sharding sees identical observations
+
+
+def algorithmic_flops_per_obs(M, K, V):
+    """each logical fp32 multiply-add counted once, S_k triangular, no credit for
+    split-precision emulation or recompute."""
+    return 3 * M * M * K + 3 * M * M + 6 * M * K + 6 * K * V
+
+
+def params_for(cfg, device, dtype=None):
+    """Deterministic parameters of SURVEY.md 8(d) (variance 25, lengthscale 0.75 x grid spacing, noise 1,
+    u_loc ~ 0.5 N(0,1), S_k = chol(Kuu + jI) + 0.05 tril(N(0,1)), phi = row softmax(N(0,1)), beta 0.01)."""
+    import torch
+    from gdrf_b200.kernels import KERNEL_DICT
+    grid, D, K, V = cfg["grid"], cfg["D"], cfg["K"], cfg["V"]
+    axes = [torch.linspace(0.0, 1.0, n) if n > 1 else torch.tensor([0.5]) for n in grid]
+    Z = torch.stack([m.flatten() for m in torch.meshgrid(*axes, indexing="ij")]).T.contiguous().float()
+    M = Z.shape[0]
+    spacing = min(1.0 / (n - 1) for n in grid if n > 1)
+    ls = torch.tensor([0.75 * spacing])
+    var = torch.tensor(25.0)
+    jitter = 1e-4
+    kern = KERNEL_DICT[cfg["kernel"]](D, variance=var.double(), lengthscale=ls.double()).double()
+    with torch.no_grad():
+        Kuu = kern(Z.double())
+    L0 = torch.linalg.cholesky(Kuu + jitter * torch.eye(M, dtype=torch.float64)).float()
+    S = L0.expand(K, M, M) + 0.05 * torch.randn(K, M, M, generator=torch.Generator().manual_seed(8)).tril()
+    S = S.tril().contiguous()
+    dg = S.diagonal(dim1=-2, dim2=-1)
+    dg.copy_(dg.abs().clamp(min=1e-3))
+    p = dict(Z=Z, variance=var, lengthscale=ls, noise=torch.tensor(1.0),
+             u_loc=0.5 * torch.randn(K, M, generator=torch.Generator().manual_seed(7)),
+             u_scale_tril=S,
+             phi=torch.softmax(torch.randn(K, V, generator=torch.Generator().manual_seed(9)), -1),
+             beta=torch.full((K, V), 0.01))
+    return {k: v.to(device) for k, v in p.items()}, jitter, 15
+
+
+def gen_chunk(cfg, chunk_id, rows, device):
+    """xs ~ U[0,1)^D, counts ~ Multinomial(n_n, theta* phi*), n_n ~ U{V..10V-1}, eps ~ N(0,1); seeded by the
+    global chunk index."""
+    import torch
+    D, K, V = cfg["D"], cfg["K"], cfg["V"]
+    g = torch.Generator(device=device).manual_seed(1234 + 7919 * chunk_id)
+    xs = torch.rand(rows, D, generator=g, device=device)
+    gp = torch.Generator(device=device).manual_seed(4321)
+    phi_star = torch._sample_dirichlet(torch.full((K, V), 0.1, device=device), generator=gp)
+    theta_star = torch._sample_dirichlet(torch.full((rows, K), 0.3, device=device), generator=g)
+    probs = theta_star @ phi_star
+    counts = torch.randint(V, 10 * V, (rows,), generator=g, device=device)
+    ws = torch.zeros(rows, V, dtype=torch.int32, device=device)
+    sub = 4096
+    for r0 in range(0, rows, sub):
+        r1 = min(rows, r0 + sub)
+        idx = torch.multinomial(probs[r0:r1], 10 * V, replacement=True, generator=g)
+        mask = (torch.arange(10 * V, device=device)[None, :] < counts[r0:r1, None]).to(torch.int32)
+        ws[r0:r1].scatter_add_(1, idx, mask)
+    eps = torch.randn(K, rows, generator=g, device=device)
+    return xs, ws, eps
+
+
+def gen_shard(cfg, lo, hi, device):
+    import torch
+    assert lo % GEN_CHUNK == 0 or cfg["N"] < GEN_CHUNK
+    xs_l, ws_l, eps_l = [], [], []
+    n = lo
+    while n < hi:
+        rows = min(GEN_CHUNK, hi - n)
+        x, w, e = gen_chunk(cfg, n // GEN_CHUNK, rows, device)
+        xs_l.append(x); ws_l.append(w); eps_l.append(e)
+        n += rows
+    return torch.cat(xs_l), torch.cat(ws_l), torch.cat(eps_l, dim=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(cfg, sample_rows, steps, warmup):
+    """The reference's CPU path: the fp32 oracle executed op for op as the reference does (two conditionals,
+    unfused ops, N x V probabilities materialised, torch autograd backward), all host threads, on a bounded
+    sample of the workload (observations are independent given the parameters, so obs/s does not depend on N
+    beyond the M x M prologue, which is included)."""
+    import torch
+    from oracle import gdrf_oracle as O     # the one place bench.py executes oracle/: the reported baseline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dev = torch.device("cpu")
+    p, jitter, maxjitter = params_for(cfg, dev)
+    xs, ws, eps = gen_chunk(cfg, 0, sample_rows, dev)
+    inp = O.OracleInputs(xs=xs, ws=ws, Z=p["Z"], variance=p["variance"], lengthscale=p["lengthscale"],
+                         u_loc=p["u_loc"], u_scale_tril=p["u_scale_tril"], noise=p["noise"], phi=p["phi"],
+                         beta=p["beta"], eps=eps, kernel=cfg["kernel"], jitter=jitter, maxjitter=maxjitter,
+                         n_global=cfg["N"])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(inp, twice=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": sample_rows / best, "unit": "observations/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_rows} observations of the workload, fp32 oracle as the reference executes it "
+                      f"(2 conditionals + autograd), best of {steps} after {warmup} warm-up",
+            "ms_per_step": 1e3 * statistics.mean(times)}
+
+
+def run_reference(args, cfg_name, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 2000 if cfg["K"] * cfg["grid"][0] > 200 else 8000
+    rows = min(rows, cfg["N"])
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    r = cpu_reference_rate(cfg, rows, steps, warmup)
+    line = {"metric": METRIC, "value": r["value"], "unit": "observations/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{cfg_name}: N={cfg['N']} D={cfg['D']} K={cfg['K']} V={cfg['V']} "
+                                   f"M={_prod(cfg['grid'])} {cfg['kernel']}; bounded sample of {rows} observations/step"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def _prod(xs):
+    p = 1
+    for x in xs:
+        p *= x
+    return p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=int, default=0, help="override the number of observations (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.n:
+        cfg["N"] = args.n
+    if args.impl == "reference":
+        run_reference(args, args.config, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gdrf_b200 import _lib
+    from gdrf_b200.elbo import _Call
+    from gdrf_b200.svi import shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a B200: gdrf_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    N, D, K, V = cfg["N"], cfg["D"], cfg["K"], cfg["V"]
+    M = _prod(cfg["grid"])
+    lo, hi = shard_bounds(N, rank, world)
+    if N >= GEN_CHUNK:      # keep shards on generation-chunk boundaries
+        per = (N // GEN_CHUNK) // world * GEN_CHUNK
+        lo, hi = rank * per, (N if rank == world - 1 else (rank + 1) * per)
+    xs, ws, eps = gen_shard(cfg, lo, hi, dev)
+    n_local = hi - lo
+    prm, jitter, maxjitter = params_for(cfg, dev)
+    lib = _lib.load()
+    flags = _lib.FLAG_CHOL_FP32_STATUS | (_lib.FLAG_INCLUDE_PRIOR if rank == 0 else 0)
+
+    def one_step(x, w, e):
+        call = _Call(x, w, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],
+                     prm["noise"], prm["phi"], prm["beta"], e, _lib.KERNEL_IDS[cfg["kernel"]], 0, flags, 0)
+        call.prologue(jitter, maxjitter)
+        terms, grad = call.step(True)
+        if world > 1:                      # the one collective of the step: small parameter gradients + ELBO terms
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+            dist.all_reduce(terms, op=dist.ReduceOp.SUM)
+        return terms, grad
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for _ in range(warmup):
+        terms, grad = one_step(xs, ws, eps)
+    barrier()
+    lib.gdrf_profile_enable(1)
+    _lib.profile_read()
+    launches0 = lib.gdrf_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for a, b in ev:
+        a.record()
+        terms, grad = one_step(xs, ws, eps)
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = lib.gdrf_launch_count() - launches0
+    prof = _lib.profile_read()
+    lib.gdrf_profile_enable(0)
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = tmax.item() / steps
+    value = N / (ms_per_step * 1e-3)
+    t = terms.cpu()
+    loss = -float(t[0] + t[3] + t[2] - t[1]) / N
+
+    # ---------------- end-to-end through the C ABI with host buffers ("e2e") ----------------
+    e2e = None
+    if not args.no_e2e:
+        hx, hw, he = (t_.cpu().pin_memory() for t_ in (xs, ws, eps))
+        dx, dw, de = torch.empty_like(xs), torch.empty_like(ws), torch.empty_like(eps)
+        h_terms = torch.empty(4, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True); dw.copy_(hw, non_blocking=True); de.copy_(he, non_blocking=True)
+            tm, _ = one_step(dx, dw, de)
+            h_terms.copy_(tm, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_terms
+
+        e2e_step()
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev2:
+            a.record()
+            e2e_step()
+            b.record()
+        barrier()
+        ms2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        h2d = hx.numel() * 4 + hw.numel() * 4 + he.numel() * 4
+        e2e = {"value": N / (ms2.item() / steps * 1e-3), "unit": "observations/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32, "ms_per_step": ms2.item() / steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        peak_tf, peak_src = float(peaks.get("bf16_tflops_sustained", 1384.6)), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    else:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    tri = 2.0 * (M * M / 2.0) * K                 # triangular-aware flops per observation of one W*S_k contraction
+    alg = {"G1": 2.0 * M * M / 2, "G2_fwd": tri, "G2_bwd": tri, "G3": tri, "G4": 2.0 * M * M / 2, "G5": 2.0 * M * M,
+           "G6": tri}
+    kernel_ms = {k: v[0] for k, v in prof.items()}
+    dom = max(kernel_ms, key=kernel_ms.get)
+    dom_ms, dom_n = prof[dom]
+    roofline = None
+    if dom_n > 0 and dom_ms > 0:
+        per_launch_ms = dom_ms / dom_n
+        obs_per_launch = n_local * steps / dom_n
+        achieved = alg[dom] * obs_per_launch / (per_launch_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": per_launch_ms, "launches": dom_n,
+                    "share_of_step": dom_ms / (ms_dev if ms_dev > 0 else 1.0),
+                    "note": "algorithmic flops: triangular-aware, each fp32 multiply-add counted once; the kernel "
+                            "issues 3 (bwd) or 6 (fwd) bf16 MMAs per logical product (error-compensated split)",
+                    "all_contractions_ms_per_step": {k: v / steps for k, v in kernel_ms.items()}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        rows = 2000 if K * M > 8192 else 8000
+        cpu_baseline = cpu_reference_rate(cfg, min(rows, N), 2, 1)
+        cpu_baseline.pop("ms_per_step", None)
+
+    line = {"metric": METRIC, "value": value, "unit": "observations/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (bf16x3/bf16x6 error-compensated tcgen05 products, f32 accumulate, f64 MxM prologue)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: N={N} D={D} K={K} V={V} M={M} {cfg['kernel']}, sharded by "
+                                   f"observation over {world} GPU(s)", "l2": "inputs (ws) exceed L2 every step",
+                       "parallelism": f"obs-shard x{world}", "jitter": jitter},
+            "loss": loss, "wall_s_timed": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "alg_tflops_step": algorithmic_flops_per_obs(M, K, V) * N / (ms_per_step * 1e-3) / 1e12}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ class Outputs(ctypes.Structure):
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
            "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_perplexity_terms", "gdrf_last_error",
-           "gdrf_build_info")
+           "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
 _lib = None
 
@@ -62,6 +62,11 @@ def load() -> ctypes.CDLL:
     lib.gdrf_perplexity_terms.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p]
     for n in EXPORTS[:7]:
         getattr(lib, n).restype = c_int
+    lib.gdrf_launch_count.restype = ctypes.c_longlong
+    lib.gdrf_profile_enable.argtypes = [c_int]
+    lib.gdrf_profile_enable.restype = c_int
+    lib.gdrf_profile_read.argtypes = [P(c_double), P(ctypes.c_longlong)]
+    lib.gdrf_profile_read.restype = c_int
     lib.gdrf_last_error.restype = c_char_p
     lib.gdrf_build_info.restype = c_char_p
     _lib = lib
@@ -83,3 +88,13 @@ def grad_elems(shape: Shape) -> int:
     out = c_int64(0)
     check(load().gdrf_grad_elems(ctypes.byref(shape), ctypes.byref(out)))
     return int(out.value)
+
+
+PROFILE_KINDS = ("G1", "G2_fwd", "G2_bwd", "G3", "G4", "G5", "G6")
+
+
+def profile_read():
+    ms = (c_double * 7)()
+    n = (ctypes.c_longlong * 7)()
+    check(load().gdrf_profile_read(ms, n))
+    return {k: (ms[i], int(n[i])) for i, k in enumerate(PROFILE_KINDS)}

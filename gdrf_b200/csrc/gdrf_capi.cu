@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -25,9 +26,35 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
     cudaError_t e_ = (x);                                                             \
     if (e_ != cudaSuccess) return fail(2, "CUDA error: %s (line %lld)", cudaGetErrorString(e_), __LINE__); \
   } while (0)
-#define LAUNCH_CHECK() CU(cudaGetLastError())
+#define LAUNCH_CHECK() do { ++g_launches; CU(cudaGetLastError()); } while (0)
 
 constexpr int DEFAULT_SMS = 148;
+
+// ---- optional instrumentation (bench.py): kernel-launch counter and CUDA-event timing of the contractions ----
+long long g_launches = 0;
+bool g_profile = false;
+enum { PK_G1 = 0, PK_G2F, PK_G2B, PK_G3, PK_G4, PK_G5, PK_G6, PK_COUNT };
+struct ProfRec { int kind; cudaEvent_t a, b; };
+constexpr int PROF_MAX = 4096;
+ProfRec g_prof[PROF_MAX];
+int g_prof_n = 0;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  int idx = -1; cudaStream_t st;
+  ProfScope(int kind, cudaStream_t s) : st(s) {
+    if (g_profile && g_prof_n < PROF_MAX) {
+      idx = g_prof_n++;
+      g_prof[idx].kind = kind; g_prof[idx].a = prof_event(); g_prof[idx].b = prof_event();
+      cudaEventRecord(g_prof[idx].a, st);
+    }
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+};
 
 struct Plan {
   // dims
@@ -86,7 +113,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tmpA = bump(off, sizeof(double) * Mp2);
   p.tmpB = bump(off, sizeof(double) * Mp2);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
-  p.st_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
+  p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
@@ -196,15 +223,15 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   {
     G1::Params g{};
     g.kxz = kxz; g.linv = linv; g.w = w; g.wsq = at<float>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
-    CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st));
+    { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
   }
   k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<float>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
     G2<false>::Params g{};
     g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
-    g.q = at<float>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.JT = p.JT; g.ncp = (int)p.ncp;
-    CU(launch_gemm<G2<false>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st));
+    g.q = at<float>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<false>::BN; g.ncp = (int)p.ncp;
+    { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<false>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
   }
   return 0;
 }
@@ -276,6 +303,32 @@ extern "C" {
 
 const char* gdrf_last_error(void) { return g_err; }
 
+long long gdrf_launch_count(void) { return g_launches; }
+
+int gdrf_profile_enable(int on) {
+  g_profile = on != 0;
+  return 0;
+}
+
+// ms[7], launches[7]: summed CUDA-event time and launch count of G1, G2-forward, G2-backward, G3, G4, G5, G6
+// since the last read.  Synchronises the device.
+int gdrf_profile_read(double* ms, long long* launches) {
+  if (!ms || !launches) return fail(1, "null pointer argument%s");
+  for (int i = 0; i < PK_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < g_prof_n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) == cudaSuccess) {
+      ms[g_prof[i].kind] += t;
+      launches[g_prof[i].kind] += 1;
+    }
+    g_event_pool.push_back(g_prof[i].a);
+    g_event_pool.push_back(g_prof[i].b);
+  }
+  g_prof_n = 0;
+  return 0;
+}
+
 const char* gdrf_build_info(void) {
   return "gdrf_b200 sm_100a: tcgen05 split-bf16 contractions (TMEM accumulators, cp.async.bulk operand ring)";
 }
@@ -314,15 +367,18 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
     k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
     LAUNCH_CHECK();
     cholesky_inplace<float>(k32, p.Mp, dev_status, st);
+    g_launches += 3 * (p.Mp / NB);
     LAUNCH_CHECK();
   }
   double* L = at<double>(ws, p.L64);
   k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, L);
   LAUNCH_CHECK();
   cholesky_inplace<double>(L, p.Mp, dev_status, st);
+  g_launches += 3 * (p.Mp / NB);
   LAUNCH_CHECK();
   double* Linv = at<double>(ws, p.Linv64);
   tri_inverse(L, Linv, p.Mp, st);
+  g_launches += p.Mp / NB;
   LAUNCH_CHECK();
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
   k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv);
@@ -397,13 +453,13 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     {
       G2<true>::Params g{};
       g.w = w; g.st = stm; g.r = rm; g.q = nullptr; g.g2 = at<float>(ws, p.g2);
-      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.ncp = (int)p.ncp;
-      CU(launch_gemm<G2<true>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st));
+      g.RT = RT; g.MB = p.MB; g.K = K; g.NT = Mp / G2<true>::BN; g.ncp = (int)p.ncp;
+      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_gemm<G2<true>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
     }
     {
       G3::Params g{};
       g.r = rm; g.st = stm; g.dw = dwf; g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp;
-      CU(launch_gemm<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, st));
+      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_gemm<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, st)); }
     }
     {
       const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
@@ -422,12 +478,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       int per = (NBt + splits - 1) / splits;
       splits = (NBt + per - 1) / per;
       g6.splits = splits; g6.nb_per_split = per;
-      CU(launch_gemm<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, st));
+      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_gemm<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, st)); }
     }
     {
       G4::Params g{};
       g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
-      CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st));
+      { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
     }
     {
       int rows_per_cta = (int)round_up_ll(((long long)nc * p.MT + 2 * sms - 1) / (2 * sms), 128);
@@ -446,7 +502,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       int per = (NBt + splits - 1) / splits;
       splits = (NBt + per - 1) / per;
       g.splits = splits; g.nb_per_split = per;
-      CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
+      { ProfScope ps(PK_G5, st); ++g_launches; CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st)); }
     }
   }
 
@@ -464,6 +520,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
     dgemm<true, false>(Linv, tB, tA, Mp, st);
     dgemm<false, false>(tA, Linv, tB, Mp, st);
+    g_launches += 5;
     LAUNCH_CHECK();
     k_kuu_backward<<<ceil_div(M, 128), 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
     LAUNCH_CHECK();

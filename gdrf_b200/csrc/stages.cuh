@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
 }
 
 // ---------------------------------------------------------------------------------------------
-// ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110), 2 planes; zero elsewhere.
+// ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110), 3 planes; zero elsewhere.
 // grid (Mp/64 [j tile], Mp/64 [i tile], K), 256 threads; transposes through shared memory.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, int K, int M, int Mp, PlaneMat st) {
@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, in
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = tile[g * 8 + e][jj];
-    uint4 pk[2];
-    split8<2>(v, pk);
+    uint4 pk[3];
+    split8<3>(v, pk);
     const int row = k * Mp + jt * 64 + jj;
 #pragma unroll
-    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
+    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
   }
 }
 

@@ -1,0 +1,165 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gdrf_b200.h declares, its
+host-only entry points validate arguments, the Python boundary mirrors the reference surface, and the
+observation-sharded data-parallel logic is exact (gloo, world_size 2).  No GPU needed."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import gdrf_b200
+from gdrf_b200 import _lib
+from gdrf_b200.svi import shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gdrf_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "gdrf_b200.h")).read()
+    declared = set(re.findall(r"\b(gdrf_[a-z_]+)\s*\(", header))
+    assert {"gdrf_workspace_bytes", "gdrf_prologue", "gdrf_elbo_step", "gdrf_elbo_backward",
+            "gdrf_marginal_mean", "gdrf_last_error"} <= declared
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_lib.EXPORTS) == declared
+    assert b"tcgen05" in lib.gdrf_build_info()
+
+
+def _shape(**kw):
+    base = dict(n_local=1000, n_offset=0, n_eps=1000, d=2, m=64, k=4, v=50, kernel_id=0, ls_dim=1,
+                chunk_rows=0, flags=0)
+    base.update(kw)
+    return _lib.Shape(**base)
+
+
+def test_sizes_and_argument_validation():
+    s = _shape()
+    assert _lib.grad_elems(s) == 4 * 64 * 64 + 4 * 64 + 4 * 50 + 64 * 2 + 1 + 1 + 1
+    b1 = _lib.workspace_bytes(s)
+    b2 = _lib.workspace_bytes(_shape(n_local=100000, n_eps=100000))
+    assert 0 < b1 < b2
+    # workspace is O(chunk), independent of N beyond one chunk
+    assert _lib.workspace_bytes(_shape(n_local=10 ** 7, n_eps=10 ** 7)) == b2
+    for bad in (dict(d=0), dict(d=9), dict(m=5000), dict(k=0), dict(k=129), dict(ls_dim=3), dict(kernel_id=7),
+                dict(chunk_rows=100)):
+        with pytest.raises(RuntimeError):
+            _lib.workspace_bytes(_shape(**bad))
+    assert _lib.load().gdrf_last_error() != b""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    s = _shape()
+    inp = _lib.Inputs()
+    status = ctypes.c_int(0)
+    buf = ctypes.create_string_buffer(16)
+    rc = _lib.load().gdrf_prologue(ctypes.byref(s), ctypes.byref(inp), 1e-6, 0, buf, 10 ** 12, None,
+                                   ctypes.byref(status))
+    assert rc != 0
+    msg = _lib.load().gdrf_last_error().decode()
+    assert "no CPU path" in msg or "sm_100a" in msg or "CUDA" in msg
+    m = _cpu_model()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.elbo(torch.rand(10, 2), torch.ones(10, 7, dtype=torch.int32))
+
+
+def _cpu_model(**kw):
+    from gdrf_b200 import RBF, SparseMultinomialGDRF
+    args = dict(num_observation_categories=7, num_topic_categories=3, world=[(0.0, 2.0), (0.0, 1.0)],
+                kernel=RBF(2, variance=torch.tensor(4.0), lengthscale=torch.tensor(0.3)), dirichlet_param=0.01,
+                n_points=4, inducing_init="grid", jitter=1e-6, maxjitter=8)
+    args.update(kw)
+    return SparseMultinomialGDRF(**args)
+
+
+def test_model_surface_matches_reference_names_and_init():
+    m = _cpu_model()
+    keys = set(m.state_dict().keys())
+    # PyroParam storage names of gdrf/models/sparse_gdrf.py:79-122 (+ the kernel's, train_script.py:290-298)
+    assert {"u_loc_unconstrained", "u_scale_tril_unconstrained", "noise_unconstrained",
+            "_inducing_points_unconstrained", "_word_topic_matrix_map_unconstrained",
+            "_kernel.variance_unconstrained", "_kernel.lengthscale_unconstrained"} <= keys
+    assert m.K == 3 and m.V == 7 and m.dims == 2 and m.M == 16 and m.D == 2
+    assert torch.allclose(m.u_loc, torch.zeros(3, 16))
+    assert float(m.noise.detach()) == pytest.approx(1.0)
+    # inducing grid scaled into the unit cube (sparse_gdrf.py:61-77)
+    Z = m._inducing_points
+    assert Z.min() >= 0 and Z.max() <= 1 and Z.shape == (16, 2)
+    # u_scale_tril init = chol(Kuu + jitter I) repeated K times (sparse_gdrf.py:100-110)
+    S = m.u_scale_tril
+    Kuu = m._kernel(Z) + 1e-6 * torch.eye(16)
+    assert torch.allclose(S[1] @ S[1].T, Kuu, atol=1e-4)
+    # word-topic matrix: uniform rows (abstract_gdrf.py:57-84 with scalar beta)
+    assert torch.allclose(m.word_topic_matrix, torch.full((3, 7), 1 / 7.0), atol=1e-6)
+    # scale(): affine map to the unit cube; bounds are asserted (topic_model.py:168-198)
+    assert torch.allclose(m.scale(torch.tensor([[1.0, 0.5]])), torch.tensor([[0.5, 0.5]]))
+    with pytest.raises(AssertionError):
+        m._scaled(torch.tensor([[3.0, 0.5]]))
+    with pytest.raises(ValueError, match="same number of dimensions"):
+        m._check_Xnew_shape(torch.rand(5))
+    fixed = _cpu_model(fixed_inducing_points=True)
+    assert "_inducing_points_unconstrained" not in fixed.state_dict()
+    with pytest.raises(NotImplementedError):
+        _cpu_model(whiten=False)
+    with pytest.raises(ValueError, match="inducing_init"):
+        _cpu_model(inducing_init="sobol")
+
+
+def test_shard_bounds_cover_without_overlap():
+    for n, w in ((10, 3), (1_000_000, 8), (7, 8), (0, 2)):
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import gdrf_oracle as O
+from gdrf_b200.svi import SVI, shard_bounds
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[4])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+inp = O.make_problem(N=101, D=2, K=3, V=8, grid=[3, 3]).to(torch.float64)
+
+class OracleBacked(torch.nn.Module):            # stands in for the CUDA op: same elbo() contract, CPU arithmetic
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.ParameterDict({k: torch.nn.Parameter(getattr(inp, k).clone()) for k in O.GRAD_NAMES})
+    def elbo(self, xs, ws, eps=None, n_global=None, n_offset=0, include_prior=True):
+        sh = O.OracleInputs(xs, ws, inp.Z, inp.variance, inp.lengthscale, inp.u_loc, inp.u_scale_tril, inp.noise,
+                            inp.phi, inp.beta, eps[:, n_offset:n_offset + xs.shape[0]], inp.kernel, inp.jitter,
+                            inp.maxjitter, n_global=n_global)
+        out = O.elbo_terms(sh, {k: self.p[k] for k in O.GRAD_NAMES})
+        e = out["elbo"] if include_prior else out["elbo"] - out["lp_phi"]
+        return e / n_global
+
+m = OracleBacked()
+lo, hi = shard_bounds(101, rank, world)
+loss = SVI(m).loss_and_grads(inp.xs[lo:hi], inp.ws[lo:hi], eps=inp.eps, n_global=101, n_offset=lo)
+full, g = O.loss_and_grads(inp)
+assert abs(loss.item() - full["loss"].item()) < 1e-10 * abs(full["loss"].item()), (loss.item(), full["loss"].item())
+for k in O.GRAD_NAMES:
+    gk = m.p[k].grad if k != "u_scale_tril" else m.p[k].grad.tril()
+    assert O.rel_err(gk, g[k]) < 1e-9, k
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_sharded_step_equals_single_rank(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
