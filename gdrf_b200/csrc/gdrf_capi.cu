@@ -67,7 +67,7 @@ struct Plan {
   size_t linv_pl, st_pl;
   // per chunk
   size_t kxz_pl, w_pl, r_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
-  size_t wsq, srow, arow, cnt, gv0, floc, q, mu, fvar, theta, g_loc, g2, g1;
+  size_t wsq, srow, arow, cnt, gv0, floc, q, fvar, theta, g_loc, g2, g1;
   size_t total;
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
 };
@@ -119,15 +119,14 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.r_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.dwf = bump(off, sizeof(float) * nm);
-  p.wsq = bump(off, sizeof(float) * p.ncp);
+  p.wsq = bump(off, sizeof(double) * p.ncp);
   p.srow = bump(off, sizeof(float) * p.ncp);
   p.arow = bump(off, sizeof(float) * p.ncp);
   p.cnt = bump(off, sizeof(float) * p.ncp);
   p.gv0 = bump(off, sizeof(float) * p.ncp);
   const size_t kn = (size_t)p.K * p.ncp;
-  p.floc = bump(off, sizeof(float) * kn);
-  p.q = bump(off, sizeof(float) * kn);
-  p.mu = bump(off, sizeof(float) * kn);
+  p.floc = bump(off, sizeof(double) * kn);
+  p.q = bump(off, sizeof(double) * kn);
   p.fvar = bump(off, sizeof(float) * kn);
   p.theta = bump(off, sizeof(float) * kn);
   p.g_loc = bump(off, sizeof(float) * kn);
@@ -202,10 +201,17 @@ int launch_du(const Plan& p, PlaneMat w, int RT, void* ws, int sms, cudaStream_t
   const dim3 grid(p.MB, (RT + tiles_per_cta - 1) / tiles_per_cta);
   const float* g = at<float>(ws, p.g_loc);
   double* du = at<double>(ws, p.du);
-  if (p.K <= 16) k_du<4><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
-  else if (p.K <= 32) k_du<8><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
-  else if (p.K <= 64) k_du<16><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
-  else k_du<32><<<grid, 256, 0, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);
+#define DU(KQ)                                                                                              \
+  do {                                                                                                      \
+    const size_t smem = sizeof(float) * (128 * 65 + 4 * KQ * 128);                                          \
+    CU(cudaFuncSetAttribute(k_du<KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    k_du<KQ><<<grid, 256, smem, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);                   \
+  } while (0)
+  if (p.K <= 16) DU(4);
+  else if (p.K <= 32) DU(8);
+  else if (p.K <= 64) DU(16);
+  else DU(32);
+#undef DU
   LAUNCH_CHECK();
   return 0;
 }
@@ -222,15 +228,15 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   LAUNCH_CHECK();
   {
     G1::Params g{};
-    g.kxz = kxz; g.linv = linv; g.w = w; g.wsq = at<float>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
+    g.kxz = kxz; g.linv = linv; g.w = w; g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
     { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
   }
-  k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<float>(ws, p.floc), (int)p.ncp);
+  k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
     G2<false>::Params g{};
     g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
-    g.q = at<float>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<false>::BN; g.ncp = (int)p.ncp;
+    g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<false>::BN; g.ncp = (int)p.ncp;
     { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<false>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
   }
   return 0;
@@ -241,6 +247,12 @@ __global__ void k_scale(const float* __restrict__ g, long long n, const float* _
   const float s = (sdev ? sdev[0] : 1.f) * shost;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = s * g[i];
+}
+
+__global__ void k_export_floc(const double* __restrict__ floc, int ncp, int nc, float* __restrict__ out,
+                              long long n_stride) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (n < nc) out[(long long)k * n_stride + n] = (float)floc[(long long)k * ncp + n];
 }
 
 __global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms) {
@@ -437,15 +449,15 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
     if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, sms, st)) return e;
-    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.floc),
-                                      at<float>(ws, p.q), at<float>(ws, p.wsq), in->eps, hp,
-                                      at<float>(ws, p.phisum), at<float>(ws, p.mu), at<float>(ws, p.fvar),
+    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
+                                      at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
+                                      at<float>(ws, p.phisum), at<float>(ws, p.fvar),
                                       at<float>(ws, p.theta), at<float>(ws, p.srow), acc);
     LAUNCH_CHECK();
     if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
     k_obs_finalize<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta),
                                        at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),
-                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<float>(ws, p.wsq), in->eps, hp,
+                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq), in->eps, hp,
                                        at<float>(ws, p.phisum), at<float>(ws, p.g_loc), at<float>(ws, p.g2),
                                        at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
     LAUNCH_CHECK();
@@ -566,8 +578,9 @@ int gdrf_marginal_mean(const gdrf_shape* s, const gdrf_inputs* in, float* out_fl
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
     if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, false, sms, st)) return e;
-    CU(cudaMemcpy2DAsync(out_floc + n0, sizeof(float) * (size_t)s->n_local, at<float>(ws, p.floc),
-                         sizeof(float) * (size_t)p.ncp, sizeof(float) * (size_t)nc, p.K, cudaMemcpyDeviceToDevice, st));
+    k_export_floc<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
+                                                             out_floc + n0, (long long)s->n_local);
+    LAUNCH_CHECK();
   }
   return 0;
 }

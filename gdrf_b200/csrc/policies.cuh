@@ -20,6 +20,19 @@ namespace gdrf {
 
 __device__ __forceinline__ void store8(bf16* dst, const uint4& pk) { *reinterpret_cast<uint4*>(dst) = pk; }
 
+// sum of 32 squares: four independent fp32 partial sums of 8 terms, combined in fp64
+__device__ __forceinline__ double sumsq32(const float (&v)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s0 = fmaf(v[j], v[j], s0);
+    s1 = fmaf(v[8 + j], v[8 + j], s1);
+    s2 = fmaf(v[16 + j], v[16 + j], s2);
+    s3 = fmaf(v[24 + j], v[24 + j], s3);
+  }
+  return ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // G1:  W[n, m] = sum_{i <= m} Kxz[n, i] Linv[m, i]      epilogue: W planes + wsq[n] = sum_m W^2
 // ---------------------------------------------------------------------------------------------
@@ -28,7 +41,7 @@ struct G1 {
   static constexpr bool A_MN = false, B_MN = false;
   struct Params {
     PlaneMat kxz, linv, w;
-    float* wsq;
+    double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients)
     int RT, MB;
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
@@ -41,8 +54,8 @@ struct G1 {
     return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(sub, kit);
   }
   struct Epi {
-    float acc;
-    __device__ void item_begin(const Params&, int, int) { acc = 0.f; }
+    double acc;
+    __device__ void item_begin(const Params&, int, int) { acc = 0.0; }
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
       const int r = item * 128 + row;
@@ -54,8 +67,7 @@ struct G1 {
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) store8(p.w.elem(pl, r, col), pk[pl]);
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);
+      acc += sumsq32(v);
     }
     __device__ void sub_end(const Params&, int, int, int) {}
     __device__ void item_end(const Params& p, int item, int row) { p.wsq[item * 128 + row] = acc; }
@@ -78,7 +90,7 @@ struct G2 {
   static constexpr int PCS = BN / 128;    // 128-row pieces of ST per tile
   struct Params {
     PlaneMat w, st, r;
-    float* q;          // [K][ncp]   (FWD out)
+    double* q;         // [K][ncp]   (FWD out, fp64: q feeds mu = f_loc + f_var * eps)
     const float* g2;   // [K][ncp]   (BWD in: 2 * dELBO/df_var)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
   };
@@ -94,13 +106,14 @@ struct G2 {
     return p.st.base + pl * p.st.plane_stride + p.st.block_off(sub * PCS + pc, CB * jt + kit);
   }
   struct Epi {
-    float acc;
-    __device__ void item_begin(const Params&, int, int) { acc = 0.f; }
+    float acc;     // BWD: row scale 2 g_var
+    double qacc;   // FWD: running sum of squares
+    __device__ void item_begin(const Params&, int, int) { acc = 0.f; qacc = 0.0; }
     __device__ void sub_begin(const Params& p, int item, int sub, int row) {
       if (BWD) {
         acc = p.g2[(long long)(sub / p.NT) * p.ncp + item * 128 + row];
       } else if (sub % p.NT == 0) {
-        acc = 0.f;
+        qacc = 0.0;
       }
     }
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
@@ -118,12 +131,11 @@ struct G2 {
           for (int pl = 0; pl < 2; ++pl) store8(p.r.elem(pl, r, col0 + g * 8), pk[pl]);
         }
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);
+        qacc += sumsq32(v);
       }
     }
     __device__ void sub_end(const Params& p, int item, int sub, int row) {
-      if (!BWD && (sub % p.NT) == p.NT - 1) p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row] = acc;
+      if (!BWD && (sub % p.NT) == p.NT - 1) p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row] = qacc;
     }
     __device__ void item_end(const Params&, int, int) {}
   };

@@ -117,13 +117,13 @@ __global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Li
 // abstract_gdrf.py:17-18).  grid (RT, ceil(K/16)), 128 threads = rows; W rebuilt from its 3 planes.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restrict__ u, int K, int M, int MB,
-                                              float* __restrict__ floc, int ncp) {
+                                              double* __restrict__ floc, int ncp) {
   __shared__ float us[16][64];
   const int rt = blockIdx.x, kg = blockIdx.y;
   const int n = rt * 128 + threadIdx.x;
-  float acc[16];
+  double acc[16];     // fp32 dot products over 64 columns, summed across blocks in fp64
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
   for (int mb = 0; mb < MB; ++mb) {
     __syncthreads();
     for (int t = threadIdx.x; t < 16 * 64; t += 128) {
@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restric
       us[kk][c] = (k < K && m < M) ? u[(long long)k * M + m] : 0.f;
     }
     __syncthreads();
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part[i] = 0.f;
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       uint4 pk[3];
@@ -141,12 +144,14 @@ __global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restric
       join8<3>(pk, wv);
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) {
-        float a = acc[kk];
+        float a = part[kk];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a = fmaf(wv[j], us[kk][g * 8 + j], a);
-        acc[kk] = a;
+        part[kk] = a;
       }
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += (double)part[i];
   }
 #pragma unroll
   for (int kk = 0; kk < 16; ++kk) {
@@ -174,53 +179,52 @@ __global__ void k_phisum(const float* __restrict__ phi, int K, int V, float* __r
 //   theta = softmax_k(mu)  (abstract_gdrf.py:21-22);  s = sum_k theta_k * rowsum(phi)_k
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_obs_prepare(int nc, int ncp, int K, long long n0, long long n_stride,
-                                                     const float* __restrict__ floc, const float* __restrict__ q,
-                                                     const float* __restrict__ wsq, const float* __restrict__ eps,
+                                                     const double* __restrict__ floc, const double* __restrict__ q,
+                                                     const double* __restrict__ wsq, const float* __restrict__ eps,
                                                      Hyper hp, const float* __restrict__ phisum,
-                                                     float* __restrict__ mu, float* __restrict__ fvar,
-                                                     float* __restrict__ theta, float* __restrict__ srow,
-                                                     double* __restrict__ acc) {
+                                                     float* __restrict__ fvar, float* __restrict__ theta,
+                                                     float* __restrict__ srow, double* __restrict__ acc) {
+  // fp64 throughout: mu carries f_var * eps with f_var = O(variance), and d ll / d mu = O(counts), so fp32
+  // rounding of mu (1e-5 absolute) alone would cost 1e-4 ... 1e-3 relative in the gradients.
   __shared__ double scratch[32];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double lq = 0.0, lp = 0.0;
   if (n < nc) {
-    const float var = hp.variance[0], noise = hp.noise[0];
-    const float var0 = fmaxf(var - wsq[n], 0.f);
-    const float HALF_LOG_2PI = 0.91893853320467274178f;
-    float mx = -INFINITY;
-    float lqf = 0.f, lpf = 0.f;
+    const double var = hp.variance[0], noise = hp.noise[0];
+    const double var0 = fmax(var - wsq[n], 0.0);
+    const double HALF_LOG_2PI = 0.91893853320467274178;
+    double mx = -INFINITY;
     for (int k = 0; k < K; ++k) {
       const long long o = (long long)k * ncp + n;
-      const float fv = var0 + q[o];
-      const float e = eps[(long long)k * n_stride + n0 + n];
-      const float d = fv * e;
-      const float m = floc[o] + d;
-      const float sp = fv + noise;
-      lqf += -logf(fv) - HALF_LOG_2PI - 0.5f * e * e;
-      const float z = d / sp;
-      lpf += -logf(sp) - HALF_LOG_2PI - 0.5f * z * z;
-      mu[o] = m;
-      fvar[o] = fv;
-      mx = fmaxf(mx, m);
+      const double fv = var0 + q[o];
+      const double e = eps[(long long)k * n_stride + n0 + n];
+      const double d = fv * e;
+      const double m = floc[o] + d;
+      const double sp = fv + noise;
+      lq += -log(fv) - HALF_LOG_2PI - 0.5 * e * e;
+      const double z = d / sp;
+      lp += -log(sp) - HALF_LOG_2PI - 0.5 * z * z;
+      fvar[o] = (float)fv;
+      mx = fmax(mx, m);
     }
-    float den = 0.f;
+    double den = 0.0;
     for (int k = 0; k < K; ++k) {
       const long long o = (long long)k * ncp + n;
-      const float ex = __expf(mu[o] - mx);
-      theta[o] = ex;
-      den += ex;
+      const double fv = var0 + q[o];
+      const double m = floc[o] + fv * (double)eps[(long long)k * n_stride + n0 + n];
+      den += exp(m - mx);
     }
-    const float inv = 1.f / den;
-    float s = 0.f;
+    const double inv = 1.0 / den;
+    double s = 0.0;
     for (int k = 0; k < K; ++k) {
       const long long o = (long long)k * ncp + n;
-      const float t = theta[o] * inv;
-      theta[o] = t;
-      s = fmaf(t, phisum[k], s);
+      const double fv = var0 + q[o];
+      const double m = floc[o] + fv * (double)eps[(long long)k * n_stride + n0 + n];
+      const double t = exp(m - mx) * inv;
+      theta[o] = (float)t;
+      s += t * (double)phisum[k];
     }
-    srow[n] = s;
-    lq = lqf;
-    lp = lpf;
+    srow[n] = (float)s;
   }
   lq = block_sum(lq, scratch);
   lp = block_sum(lp, scratch);
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, lo
                                                       const float* __restrict__ theta, const float* __restrict__ srow,
                                                       const float* __restrict__ g1, const float* __restrict__ arow,
                                                       const float* __restrict__ cnt, const float* __restrict__ fvar,
-                                                      const float* __restrict__ wsq, const float* __restrict__ eps,
+                                                      const double* __restrict__ wsq, const float* __restrict__ eps,
                                                       Hyper hp, const float* __restrict__ phisum,
                                                       float* __restrict__ g_loc, float* __restrict__ g2,
                                                       float* __restrict__ gv0, double* __restrict__ ck,
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, lo
       g2[o] = 2.f * gv;
       gsum += gv;
     }
-    const bool clamp_open = (var - wsq[n]) >= 0.f;
+    const bool clamp_open = ((double)var - wsq[n]) >= 0.0;
     const float g0 = clamp_open ? gsum : 0.f;
     gv0[n] = g0;
     dnoise = dn;
@@ -458,11 +462,16 @@ __global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// du_loc[k, m] += sum_n g_loc[k, n] W[n, m]          grid (MB, row splits), 256 threads
+// du_loc[k, m] += sum_n g_loc[k, n] W[n, m]          grid (MB, row splits), 256 threads.
+// Each 128 x 64 block of W is rebuilt from its planes into shared memory once; g_loc's [K][128] slab sits
+// beside it; thread (m, kq) owns topics kq, kq + 4, ...
 // ---------------------------------------------------------------------------------------------
 template <int KQ>   // topics per thread = KQ (K <= 4 * KQ)
 __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict__ g_loc, int K, int M, int RT, int ncp,
                                             int tiles_per_cta, double* __restrict__ du_acc) {
+  extern __shared__ float du_smem[];
+  float* wsm = du_smem;                 // [128][65]
+  float* gsm = du_smem + 128 * 65;      // [4 * KQ][128]
   const int cb = blockIdx.x;
   const int c = threadIdx.x & 63, kq = threadIdx.x >> 6;
   const int m = cb * 64 + c;
@@ -472,17 +481,27 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
   const int rt0 = blockIdx.y * tiles_per_cta;
   const int rt1 = min(RT, rt0 + tiles_per_cta);
   for (int rt = rt0; rt < rt1; ++rt) {
-#pragma unroll 2
+    __syncthreads();
+    for (int t = threadIdx.x; t < 128 * 8; t += 256) {
+      const int r = t >> 3, g = t & 7;
+      uint4 pk[3];
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, rt * 128 + r, cb * 64 + g * 8));
+      float v[8];
+      join8<3>(pk, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wsm[r * 65 + g * 8 + j] = v[j];
+    }
+    for (int t = threadIdx.x; t < 4 * KQ * 128; t += 256) {
+      const int k = t >> 7, r = t & 127;
+      gsm[t] = (k < K) ? g_loc[(long long)k * ncp + rt * 128 + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
     for (int r = 0; r < 128; ++r) {
-      const int n = rt * 128 + r;
-      float wv = 0.f;
+      const float wv = wsm[r * 65 + c];
 #pragma unroll
-      for (int pl = 2; pl >= 0; --pl) wv += __bfloat162float(*w.elem(pl, n, m));
-#pragma unroll
-      for (int i = 0; i < KQ; ++i) {
-        const int k = kq + 4 * i;
-        if (k < K) a[i] = fmaf(g_loc[(long long)k * ncp + n], wv, a[i]);
-      }
+      for (int i = 0; i < KQ; ++i) a[i] = fmaf(gsm[(kq + 4 * i) * 128 + r], wv, a[i]);
     }
   }
   if (m < M) {

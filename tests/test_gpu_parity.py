@@ -106,8 +106,8 @@ def test_tensor_path_matches_plain_fma_checker():
     t_tc, g_tc, _ = _run(inp)
     t_rf, g_rf, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_REF_ALL)
     assert torch.allclose(t_tc, t_rf, rtol=1e-6, atol=1e-3)
-    for k in g_tc:
-        assert O.rel_err(g_tc[k], g_rf[k]) < 2e-3, k     # both carry the same split; only summation order differs
+    for k in g_tc:   # both carry the same split; only summation order differs
+        assert O.rel_err(g_tc[k], g_rf[k]) < (2 * HYPER_TOL if k in HYPER else 1e-3), k
 
 
 def test_chunk_streaming_and_sharding_are_exact_properties():
