@@ -1,6 +1,7 @@
 // Shared device/host helpers for the gdrf_b200 CUDA path (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -74,6 +75,36 @@ __device__ __forceinline__ void split8(const float* v, uint4 (&pk)[P]) {
     pk[p].z = h[p][4] | ((uint32_t)h[p][5] << 16);
     pk[p].w = h[p][6] | ((uint32_t)h[p][7] << 16);
   }
+}
+
+// 8 consecutive fp32 values -> one 16-byte packet per fp16 plane (x ~= h0 + h1, 22 significant bits for
+// |x| in the normal fp16 range; the caller guarantees |x| < 65504)
+template <int P>
+__device__ __forceinline__ void split8h(const float* v, uint4 (&pk)[P]) {
+  unsigned short h[P][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float r = v[i];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      __half b = __float2half_rn(r);
+      r -= __half2float(b);
+      h[p][i] = __half_as_ushort(b);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    pk[p].x = h[p][0] | ((uint32_t)h[p][1] << 16);
+    pk[p].y = h[p][2] | ((uint32_t)h[p][3] << 16);
+    pk[p].z = h[p][4] | ((uint32_t)h[p][5] << 16);
+    pk[p].w = h[p][6] | ((uint32_t)h[p][7] << 16);
+  }
+}
+
+enum { FMT_F16 = 0, FMT_BF16 = 1 };   // tcgen05 kind::f16 operand formats (instruction descriptor encoding)
+
+__device__ __forceinline__ float plane_to_float(const bf16* p, int fmt) {
+  return fmt == FMT_BF16 ? __bfloat162float(*p) : __half2float(*reinterpret_cast<const __half*>(p));
 }
 
 __device__ __forceinline__ float bf16_bits_to_float(unsigned short h) {

@@ -64,7 +64,7 @@ struct Plan {
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, status_pad;
   size_t L64, Linv64, tmpA, tmpB;
-  size_t linv_pl, st_pl;
+  size_t linv_pl, st_pl, st16_pl, w16_pl;
   // per chunk
   size_t kxz_pl, w_pl, r_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
   size_t wsq, srow, arow, cnt, gv0, floc, q, fvar, theta, g_loc, g2, g1;
@@ -114,9 +114,11 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tmpB = bump(off, sizeof(double) * Mp2);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
+  p.st16_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
+  p.w16_pl = bump(off, sizeof(bf16) * 2 * nm);
   p.r_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.dwf = bump(off, sizeof(float) * nm);
   p.wsq = bump(off, sizeof(double) * p.ncp);
@@ -228,16 +230,24 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   LAUNCH_CHECK();
   {
     G1::Params g{};
-    g.kxz = kxz; g.linv = linv; g.w = w; g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
+    g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
     { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
   }
   k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
-    G2<false>::Params g{};
-    g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
-    g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<false>::BN; g.ncp = (int)p.ncp;
-    { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<false>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+    if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
+      G2<0>::Params g{};
+      g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
+      g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<0>::BN; g.ncp = (int)p.ncp;
+      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<0>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+    } else {                                 // fp16 2 x 2 planes (22-bit operands), 3 products
+      G2<2>::Params g{};
+      g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp);
+      g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
+      g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
+      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+    }
   }
   return 0;
 }
@@ -253,6 +263,12 @@ __global__ void k_export_floc(const double* __restrict__ floc, int ncp, int nc, 
                               long long n_stride) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (n < nc) out[(long long)k * n_stride + n] = (float)floc[(long long)k * ncp + n];
+}
+
+// status stays >0 on a failed factorisation; otherwise -1 flags an fp16-range overflow of S or W (|W| <= sigma)
+__global__ void k_merge_status(const int* __restrict__ range_flag, const float* __restrict__ variance,
+                               int* __restrict__ status) {
+  if (*status == 0 && (*range_flag != 0 || !(variance[0] < 3.0e9f))) *status = -1;
 }
 
 __global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms) {
@@ -395,6 +411,18 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
   k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv);
   LAUNCH_CHECK();
+  if (in->u_scale_tril) {
+    // operand planes of S for this step; an entry outside the fp16 range turns the status into -1 so the
+    // caller runs the forward row-norm contraction on the 24-bit bf16 path instead (GDRF_FLAG_FWD_BF16)
+    int* range_flag = at<int>(ws, p.status_pad);
+    CU(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
+    k_pack_st<<<dim3(p.MB, p.MB, p.K), 256, 0, st>>>(in->u_scale_tril, p.K, p.M, p.Mp,
+                                                     plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp),
+                                                     plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp), range_flag);
+    LAUNCH_CHECK();
+    k_merge_status<<<1, 1, 0, st>>>(range_flag, in->variance, dev_status);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -425,8 +453,6 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   float* dwf = at<float>(ws, p.dwf);
   double* acc = at<double>(ws, p.acc);
 
-  k_pack_st<<<dim3(p.MB, p.MB, K), 256, 0, st>>>(in->u_scale_tril, K, M, Mp, stm);
-  LAUNCH_CHECK();
   k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
   LAUNCH_CHECK();
 
@@ -463,10 +489,10 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     LAUNCH_CHECK();
     if (!want_grad) continue;
     {
-      G2<true>::Params g{};
+      G2<1>::Params g{};
       g.w = w; g.st = stm; g.r = rm; g.q = nullptr; g.g2 = at<float>(ws, p.g2);
-      g.RT = RT; g.MB = p.MB; g.K = K; g.NT = Mp / G2<true>::BN; g.ncp = (int)p.ncp;
-      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_gemm<G2<true>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+      g.RT = RT; g.MB = p.MB; g.K = K; g.NT = Mp / G2<1>::BN; g.ncp = (int)p.ncp;
+      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_gemm<G2<1>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
     }
     {
       G3::Params g{};

@@ -118,10 +118,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;                                // [61,64) layout type SWIZZLE_128B
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn, int fmt) {
   return (1u << 4)                     // [4,6)   accumulator format F32
-         | (1u << 7)                   // [7,10)  A format BF16
-         | (1u << 10)                  // [10,13) B format BF16
+         | ((uint32_t)fmt << 7)        // [7,10)  A format: 0 = F16, 1 = BF16
+         | ((uint32_t)fmt << 10)       // [10,13) B format
          | ((a_mn ? 1u : 0u) << 15)    // [15]    A major (0 = K, 1 = MN)
          | ((b_mn ? 1u : 0u) << 16)    // [16]    B major
          | ((uint32_t)(N >> 3) << 17)  // [17,23) N >> 3
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, P::BN, P::A_MN, P::B_MN);
+      constexpr uint32_t idesc = make_idesc(128, P::BN, P::A_MN, P::B_MN, P::FMT);
       constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
       uint32_t it = 0, unit = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(const typename P::Params 
             for (int pl = P::PA - 1; pl >= 0; --pl) {
               const bf16* src = P::A_MN ? P::a_src(prm, item, sub, kit, pl, row >> 6) + tile_off(kk, row & 63)
                                         : P::a_src(prm, item, sub, kit, pl, 0) + tile_off(row, kk);
-              a += __bfloat162float(*src);
+              a += plane_to_float(src, P::FMT);
             }
             for (int j = 0; j < 32; ++j) {
               const int col = c * 32 + j;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(const typename P::Params 
               for (int pl = P::PB - 1; pl >= 0; --pl) {
                 const bf16* src = P::B_MN ? P::b_src(prm, item, sub, kit, pl, col >> 6) + tile_off(kk, col & 63)
                                           : P::b_src(prm, item, sub, kit, pl, col >> 7) + tile_off(col & 127, kk);
-                b += __bfloat162float(*src);
+                b += plane_to_float(src, P::FMT);
               }
               v[j] = fmaf(a, b, v[j]);
             }
@@ -374,11 +374,8 @@ inline cudaError_t launch_gemm(const typename P::Params& prm, int n_items, int n
     return cudaGetLastError();
   }
   using Cfg = GemmCfg<P>;
-  static bool configured = false;   // attribute is per (function, device context); cheap to repeat
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  configured = true;
-  (void)configured;
   const int grid = n_items < num_sms ? n_items : num_sms;
   gemm_tc_kernel<P><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm);
   return cudaGetLastError();

@@ -39,8 +39,9 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 struct G1 {
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int FMT = FMT_BF16;
   struct Params {
-    PlaneMat kxz, linv, w;
+    PlaneMat kxz, linv, w, w16;   // w16: fp16 2-plane copy of W for the forward row-norm contraction
     double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients)
     int RT, MB;
   };
@@ -66,6 +67,10 @@ struct G1 {
         const int col = sub * 128 + c0 + g * 8;
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) store8(p.w.elem(pl, r, col), pk[pl]);
+        uint4 hk[2];
+        split8h<2>(&v[g * 8], hk);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) store8(p.w16.elem(pl, r, col), hk[pl]);
       }
       acc += sumsq32(v);
     }
@@ -78,13 +83,19 @@ struct G1 {
 // G2:  T[n, (k, j)] = sum_{i >= j} W[n, i] S_k[i, j]
 //   FWD epilogue: q[k, n] = sum_j T^2          BWD epilogue: R = 2 g_var[k, n] * T  (2 planes)
 // ---------------------------------------------------------------------------------------------
-template <bool BWD>
+// MODE 0: forward, bf16 3x3 planes / 6 products, 128-wide tiles (reference-precision path, also the fallback
+//         when an operand leaves the fp16 range)
+// MODE 1: backward, bf16 2x2 planes / 3 products, 256-wide tiles, R epilogue
+// MODE 2: forward, fp16 2x2 planes / 3 products (22-bit operands), 256-wide tiles -- the default forward
+template <int MODE>
 struct G2 {
+  static constexpr bool BWD = (MODE == 1);
+  static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
   // The forward needs T to fp32 accuracy: f_var enters mu = f_loc + f_var * eps as a *scale* of O(variance),
   // and d ll / d mu is O(counts), so a 2^-17 relative error in q shows up as 1e-3 in the gradients.
   // Forward: 3 planes x 3 planes, 6 products, 128-wide tiles.  Backward (R only feeds averaged sums):
   // 2 x 2 planes, 3 products, 256-wide tiles.
-  static constexpr int PA = BWD ? 2 : 3, PB = BWD ? 2 : 3, BN = BWD ? 256 : 128;
+  static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int CB = BN / 64;      // 64-column blocks per tile
   static constexpr int PCS = BN / 128;    // 128-row pieces of ST per tile
@@ -145,6 +156,7 @@ struct G2 {
 // G3:  dW[n, i] = sum_k sum_{j <= i} R[n, (k, j)] S_k[i, j]      (B = ST read MN-major)
 // ---------------------------------------------------------------------------------------------
 struct G3 {
+  static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = false, B_MN = true;
   struct Params {
@@ -183,6 +195,7 @@ struct G3 {
 // G4:  dKxz[n, i] = sum_{m >= i} dWtot[n, m] Linv[m, i]          (B = LINV read MN-major)
 // ---------------------------------------------------------------------------------------------
 struct G4 {
+  static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = true;
   struct Params {
@@ -217,6 +230,7 @@ struct G4 {
 // G5:  C5[a, b] += sum_n dWtot[n, a] W[n, b]        (both operands MN-major; split over n; fp64 atomics)
 // ---------------------------------------------------------------------------------------------
 struct G5 {
+  static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = true, B_MN = true;
   struct Params {
@@ -258,6 +272,7 @@ struct G5 {
 // G6:  dS_k[i, j] += sum_n W[n, i] R[n, (k, j)]   for j <= i   (both MN-major; tiles on/below the diagonal)
 // ---------------------------------------------------------------------------------------------
 struct G6 {
+  static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = true, B_MN = true;
   static constexpr int MAX_TILES = 512;

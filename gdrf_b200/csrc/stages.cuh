@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
 // ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110), 3 planes; zero elsewhere.
 // grid (Mp/64 [j tile], Mp/64 [i tile], K), 256 threads; transposes through shared memory.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, int K, int M, int Mp, PlaneMat st) {
+__global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, int K, int M, int Mp, PlaneMat st,
+                                                 PlaneMat st16, int* __restrict__ range_flag) {
   __shared__ float tile[64][65];
   const int jt = blockIdx.x, it = blockIdx.y, k = blockIdx.z;
   for (int t = threadIdx.x; t < 64 * 64; t += 256) {
@@ -90,6 +91,14 @@ __global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, in
     const int row = k * Mp + jt * 64 + jj;
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
+    bool over = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) over |= !(fabsf(v[e]) < 60000.f);
+    if (over) atomicExch(range_flag, 1);
+    uint4 hk[2];
+    split8h<2>(v, hk);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st16.elem(pl, row, it * 64 + g * 8)) = hk[pl];
   }
 }
 

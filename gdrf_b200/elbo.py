@@ -98,7 +98,11 @@ class _Call:
         for nj in range(int(maxjitter)):
             _lib.check(lib.gdrf_prologue(ctypes.byref(self.shape), ctypes.byref(self.inputs), float(jitter), nj,
                                          self.workspace.data_ptr(), self.ws_bytes, self.stream, status.data_ptr()))
-            if int(status.item()) == 0:      # the one host read-back of the step (mirrors try/except)
+            st = int(status.item())          # the one host read-back of the step (mirrors try/except)
+            if st == -1:                     # factorised, but an operand leaves the fp16 range: 24-bit bf16 forward
+                self.shape.flags |= _lib.FLAG_FWD_BF16
+                st = 0
+            if st == 0:
                 return nj
         raise RuntimeError("reached max jitter, covariance is unstable")
 

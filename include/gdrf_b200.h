@@ -33,6 +33,9 @@ enum {
   GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
   GDRF_FLAG_INCLUDE_PRIOR = 2,    /* add the Dirichlet log-density of phi and its gradient (one rank only)   */
   GDRF_FLAG_CHOL_FP32_STATUS = 4, /* decide not-PD with an fp32 factorisation of the reference's fp32 Kuu    */
+  GDRF_FLAG_FWD_BF16 = 16,        /* forward row-norm contraction on 3 bf16 planes / 6 products (24-bit operands,
+                                     any fp32 range) instead of 2 fp16 planes / 3 products (22-bit, |x| < 6e4);
+                                     required when gdrf_prologue reported status -1                          */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
   GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
   GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,
@@ -83,7 +86,9 @@ int gdrf_workspace_bytes(const gdrf_shape* shape, size_t* out_bytes);
 int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
 
 /* Kuu = k(Z,Z) + (sum_{i<=njitter} jitter*10^i) I, its Cholesky factor and inverse, packed for the tensor
- * pipe; *dev_status (DEVICE int) = 0 when the factorisation succeeded, else 1 + the failing column.
+ * pipe (also packs u_scale_tril when in->u_scale_tril is non-NULL); *dev_status (DEVICE int) = 0 when the
+ * factorisation succeeded, 1 + the failing column when it did not, -1 when it succeeded but u_scale_tril or the
+ * kernel variance leave the fp16 range (then pass GDRF_FLAG_FWD_BF16 to gdrf_elbo_step).
  * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39).          */
 int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
                   size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);

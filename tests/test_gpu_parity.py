@@ -110,6 +110,26 @@ def test_tensor_path_matches_plain_fma_checker():
         assert O.rel_err(g_tc[k], g_rf[k]) < (2 * HYPER_TOL if k in HYPER else 1e-3), k
 
 
+def test_fp16_forward_agrees_with_24bit_forward_and_falls_back_out_of_range():
+    """The default forward row-norm contraction uses 2 fp16 planes (22-bit operands, 3 MMAs per product); the
+    24-bit bf16 path (6 MMAs) is selected by flag and automatically when u_scale_tril leaves the fp16 range."""
+    from gdrf_b200 import _lib
+    from gdrf_b200.elbo import GDRFElbo
+    inp, d = load_golden("rbf2d")
+    t0, g0, _ = _run(inp)
+    t1, g1, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_FWD_BF16)
+    assert torch.allclose(t0, t1, rtol=1e-7, atol=1e-2)
+    for k in ("u_loc", "u_scale_tril", "phi", "noise"):
+        assert O.rel_err(g0[k], g1[k]) < 2e-4, k
+    big = O.OracleInputs(**{**inp.__dict__, "u_scale_tril": inp.u_scale_tril * 3.0e4})
+    assert big.u_scale_tril.abs().max() > 65504
+    o64 = O.elbo_terms(big.to(torch.float64), twice=False)
+    t2, g2, _ = _run(big)
+    elbo = (t2[0] + t2[3] + t2[2] - t2[1]).item()
+    assert abs(elbo - o64["elbo"].item()) <= 1e-4 * abs(o64["elbo"].item())
+    assert all(torch.isfinite(v).all() for v in g2.values())
+
+
 def test_chunk_streaming_and_sharding_are_exact_properties():
     """Size-independent properties: (i) the result does not depend on the streaming chunk size;
     (ii) observation shards sum to the whole (the multi-GPU decomposition), prior counted once."""
