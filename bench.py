@@ -252,6 +252,7 @@ def main():
     prm, jitter, maxjitter = params_for(cfg, dev)
     lib = _lib.load()
     flags = _lib.FLAG_CHOL_FP32_STATUS | (_lib.FLAG_INCLUDE_PRIOR if rank == 0 else 0)
+    flags |= int(os.environ.get("GDRF_BENCH_FLAGS", "0"))     # A/B switches (e.g. 32 = single-CTA contractions)
 
     def one_step(x, w, e):
         call = _Call(x, w, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],

@@ -19,6 +19,7 @@ FLAG_WANT_GRAD = 1
 FLAG_INCLUDE_PRIOR = 2
 FLAG_CHOL_FP32_STATUS = 4
 FLAG_FWD_BF16 = 16
+FLAG_SINGLE_CTA = 32
 FLAG_REF_G = {i: 1 << (7 + i) for i in range(1, 7)}
 FLAG_REF_ALL = 0x3F << 8
 

@@ -87,12 +87,12 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   if (s->n_local < 0) return fail(1, "n_local must be non-negative%s");
   if (s->ls_dim != 1 && s->ls_dim != s->d) return fail(1, "ls_dim must be 1 or d%s");
   if (s->kernel_id < 0 || s->kernel_id > 2) return fail(1, "unknown kernel_id%s");
-  if (s->chunk_rows < 0 || (s->chunk_rows % 128) != 0) return fail(1, "chunk_rows must be a multiple of 128%s");
+  if (s->chunk_rows < 0 || (s->chunk_rows % 256) != 0) return fail(1, "chunk_rows must be a multiple of 256%s");
   p.D = s->d; p.M = s->m; p.K = s->k; p.V = s->v;
   p.Mp = (int)round_up_ll(s->m, 256);
   p.MB = p.Mp / 64; p.JT = p.Mp / 256; p.MT = p.Mp / 128;
   long long chunk = s->chunk_rows ? s->chunk_rows : (long long)DEFAULT_SMS * 128;
-  const long long nneed = round_up_ll(s->n_local > 0 ? s->n_local : 1, 128);
+  const long long nneed = round_up_ll(s->n_local > 0 ? s->n_local : 1, 256);
   if (chunk > nneed) chunk = nneed;
   p.chunk_rows = (int)chunk;
   p.ncp = chunk;
@@ -218,6 +218,13 @@ int launch_du(const Plan& p, PlaneMat w, int RT, void* ws, int sms, cudaStream_t
   return 0;
 }
 
+// the four large contractions run on CTA pairs (cta_group::2) unless the checker or the single-CTA kernel is asked for
+template <class P>
+cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool use_ref, bool single_cta, cudaStream_t st) {
+  if (use_ref || single_cta) return launch_gemm<P>(g, n_items, sms, use_ref, st);
+  return launch_gemm2<P>(g, n_items, sms, st);
+}
+
 // forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
 int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
                   bool with_var, int sms, cudaStream_t st) {
@@ -246,7 +253,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp);
       g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
       g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
-      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
   }
   return 0;
@@ -460,14 +467,16 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   G6::Params g6{};
   if (want_grad) {
     int nt = 0;
+    // pair order: entries 2t, 2t+1 are the 128-row tiles (2 a2, b), (2 a2 + 1, b) of one 256 x 256 pair tile
     for (int b = 0; b < p.JT; ++b)
-      for (int a = 0; a < p.MT; ++a)
-        if (128 * a + 127 >= 256 * b && 128 * a < M && 256 * b < M) {
-          if (nt >= G6::MAX_TILES) return fail(1, "too many dS tiles%s");
-          g6.ta[nt] = (unsigned char)a;
-          g6.tb[nt] = (unsigned char)b;
-          ++nt;
-        }
+      for (int a2 = b; a2 < p.JT; ++a2)
+        if (256 * a2 < M && 256 * b < M)
+          for (int h = 0; h < 2; ++h) {
+            if (nt >= G6::MAX_TILES) return fail(1, "too many dS tiles%s");
+            g6.ta[nt] = (unsigned char)(2 * a2 + h);
+            g6.tb[nt] = (unsigned char)b;
+            ++nt;
+          }
     g6.ntile = nt;
   }
 
@@ -492,12 +501,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       G2<1>::Params g{};
       g.w = w; g.st = stm; g.r = rm; g.q = nullptr; g.g2 = at<float>(ws, p.g2);
       g.RT = RT; g.MB = p.MB; g.K = K; g.NT = Mp / G2<1>::BN; g.ncp = (int)p.ncp;
-      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_gemm<G2<1>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
+      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_big<G2<1>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
       G3::Params g{};
       g.r = rm; g.st = stm; g.dw = dwf; g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp;
-      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_gemm<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, st)); }
+      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
       const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
@@ -516,7 +525,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       int per = (NBt + splits - 1) / splits;
       splits = (NBt + per - 1) / per;
       g6.splits = splits; g6.nb_per_split = per;
-      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_gemm<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, st)); }
+      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
       G4::Params g{};

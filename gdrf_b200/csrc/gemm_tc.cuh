@@ -45,9 +45,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must end in a trap (reported as a CUDA error), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (clock64() - t0 > 4000000000LL) {     // ~2 s at 2 GHz: no legitimate wait in these kernels is that long
       printf("gdrf gemm: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -320,6 +321,271 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster on the two SMs of a TPC compute one 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and only HALF of B (128 of the 256 B rows), so the shared-memory fill
+// per MMA drops from 96 KB to 64 KB per k-block -- the L2 -> SM fabric (about 42 B/clk/SM), not the tensor pipe,
+// is what bounds the single-CTA kernel -- and the ring deepens to 3 stages.
+//   * logical item of CTA `rank` in cluster work item `item2` is 2 * item2 + rank (policies order their items so)
+//   * rank 0 issues every tcgen05.mma.cta_group::2; completion is multicast to both CTAs' barriers
+//   * rank 1 relays "my stage is full" and "my epilogue drained the accumulator" to rank 0's barriers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on `bar` in both CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <class P>
+struct Gemm2Cfg {
+  static_assert(P::BN == 256, "pair kernel computes 256 x 256 tiles");
+  static constexpr int A_BYTES = 16384;                  // one plane, this CTA's 128 rows x 64 k
+  static constexpr int B_BYTES = 16384;                  // one plane, this CTA's half of B (128 rows x 64 k)
+  static constexpr int STAGE_BYTES = P::PA * A_BYTES + P::PB * B_BYTES;
+  static constexpr int NSTAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) < 4 ? (GEMM_SMEM_BUDGET / STAGE_BYTES) : 4;
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(NSTAGES >= 2, "need at least a double-buffered ring");
+};
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ typename P::Params prm, int n_items1) {
+  using Cfg = Gemm2Cfg<P>;
+  constexpr int NST = Cfg::NSTAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + NST * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [NST] this CTA's stage landed
+  uint64_t* empty_bar = bars + NST;              // [NST] stage consumed (multicast commit from rank 0)
+  uint64_t* peer_full_bar = bars + 2 * NST;      // [NST] (rank 0 only) rank 1's stage landed
+  uint64_t* tfull_bar = bars + 3 * NST;          // [2]   accumulator complete (multicast commit)
+  uint64_t* tempty_bar = bars + 3 * NST + 2;     // [2]   (rank 0 only) both epilogues drained the accumulator
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NST + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&peer_full_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items2 = (n_items1 + 1) >> 1;
+  constexpr int B_HALF_K = 1;                    // K-major: one 128-row piece per CTA
+  constexpr int B_HALF_MN = 2;                   // MN-major: two 64-column pieces per CTA
+
+  if (warp == 0) {
+    // ------------------------------ bulk-copy producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
+        const int item = min(2 * item2 + (int)rank, n_items1 - 1);
+        const int nsub = P::num_subs(prm, item);
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int kn = P::k_iters(prm, item, sub);
+          for (int kit = 0; kit < kn; ++kit, ++it) {
+            const int s = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int pl = 0; pl < P::PA; ++pl) {
+              uint8_t* dst = st + pl * Cfg::A_BYTES;
+              if (!P::A_MN) {
+                bulk_g2s(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s]);
+              } else {
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc)
+                  bulk_g2s(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+              }
+            }
+#pragma unroll
+            for (int pl = 0; pl < P::PB; ++pl) {
+              uint8_t* dst = st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+              if (!P::B_MN) {
+                bulk_g2s(dst, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s]);
+              } else {
+#pragma unroll
+                for (int pc = 0; pc < B_HALF_MN; ++pc)
+                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
+                           &full_bar[s]);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (rank == 0) {
+        // ------------------------------ MMA issuer (leader CTA) ------------------------------
+        constexpr uint32_t idesc = make_idesc(256, 256, P::A_MN, P::B_MN, P::FMT);
+        constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
+        uint32_t it = 0, unit = 0;
+        for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
+          const int item = min(2 * item2, n_items1 - 1);
+          const int nsub = P::num_subs(prm, item);
+          for (int sub = 0; sub < nsub; ++sub, ++unit) {
+            const int acc = unit & 1;
+            const uint32_t aph = (unit >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            const int kn = P::k_iters(prm, item, sub);
+            for (int kit = 0; kit < kn; ++kit, ++it) {
+              const int s = it % NST;
+              const uint32_t ph = (it / NST) & 1;
+              mbar_wait(&full_bar[s], ph);
+              mbar_wait(&peer_full_bar[s], ph);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+              const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
+              bool first = (kit == 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int pa = 0; pa < P::PA; ++pa) {
+#pragma unroll
+                  for (int pb = 0; pb < P::PB; ++pb) {
+                    if (pa + pb > ORD) continue;
+                    const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                    const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                    const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                    const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                    umma2_f16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                    first = false;
+                  }
+                }
+              }
+              umma2_commit_mc(&empty_bar[s]);
+            }
+            umma2_commit_mc(&tfull_bar[acc]);
+          }
+        }
+      } else {
+        // ------------------------------ stage-full relay (rank 1 -> rank 0) ------------------------------
+        uint32_t it = 0;
+        for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
+          const int item = min(2 * item2 + 1, n_items1 - 1);
+          const int nsub = P::num_subs(prm, item);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kn = P::k_iters(prm, item, sub);
+            for (int kit = 0; kit < kn; ++kit, ++it) {
+              const int s = it % NST;
+              const uint32_t ph = (it / NST) & 1;
+              mbar_wait(&full_bar[s], ph);
+              mbar_arrive_remote(&peer_full_bar[s], 0);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    typename P::Epi epi;
+    uint32_t unit = 0;
+    for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
+      const int item_raw = 2 * item2 + (int)rank;
+      const bool valid = item_raw < n_items1;
+      const int item = valid ? item_raw : n_items1 - 1;
+      const int nsub = P::num_subs(prm, item);
+      if (valid) epi.item_begin(prm, item, row);
+      for (int sub = 0; sub < nsub; ++sub, ++unit) {
+        const int acc = unit & 1;
+        const uint32_t aph = (unit >> 1) & 1;
+        if (valid) epi.sub_begin(prm, item, sub, row);
+        mbar_wait(&tfull_bar[acc], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if (c == 7) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+              else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+          }
+          if (valid) epi.chunk(prm, item, sub, row, c * 32, v);
+        }
+        if (valid) epi.sub_end(prm, item, sub, row);
+      }
+      if (valid) epi.item_end(prm, item, row);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // plain-FMA checker with the same policy interface (tests only; 128 threads, thread = row)
 // ------------------------------------------------------------------------------------------
 template <class P>
@@ -378,6 +644,19 @@ inline cudaError_t launch_gemm(const typename P::Params& prm, int n_items, int n
   if (e != cudaSuccess) return e;
   const int grid = n_items < num_sms ? n_items : num_sms;
   gemm_tc_kernel<P><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+template <class P>
+inline cudaError_t launch_gemm2(const typename P::Params& prm, int n_items1, int num_sms, cudaStream_t stream) {
+  if (n_items1 <= 0) return cudaSuccess;
+  using Cfg = Gemm2Cfg<P>;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const int n_items2 = (n_items1 + 1) / 2;
+  int clusters = num_sms / 2;
+  if (clusters > n_items2) clusters = n_items2;
+  gemm_tc2_kernel<P><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm, n_items1);
   return cudaGetLastError();
 }
 

@@ -36,6 +36,8 @@ enum {
   GDRF_FLAG_FWD_BF16 = 16,        /* forward row-norm contraction on 3 bf16 planes / 6 products (24-bit operands,
                                      any fp32 range) instead of 2 fp16 planes / 3 products (22-bit, |x| < 6e4);
                                      required when gdrf_prologue reported status -1                          */
+  GDRF_FLAG_SINGLE_CTA = 32,      /* run the four large contractions on single CTAs (cta_group::1) instead of
+                                     CTA pairs (cta_group::2); same results, used for A/B measurement         */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
   GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
   GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,
@@ -52,7 +54,7 @@ typedef struct gdrf_shape {
   int32_t v;          /* observation categories                                                               */
   int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT rbf / matern32 / matern52)        */
   int32_t ls_dim;     /* 1 (isotropic lengthscale) or d                                                       */
-  int32_t chunk_rows; /* observations streamed per pass, multiple of 128; 0 = library default                 */
+  int32_t chunk_rows; /* observations streamed per pass, multiple of 256; 0 = library default                 */
   int32_t flags;      /* GDRF_FLAG_*                                                                          */
 } gdrf_shape;
 

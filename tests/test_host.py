@@ -47,7 +47,7 @@ def test_sizes_and_argument_validation():
     # workspace is O(chunk), independent of N beyond one chunk
     assert _lib.workspace_bytes(_shape(n_local=10 ** 7, n_eps=10 ** 7)) == b2
     for bad in (dict(d=0), dict(d=9), dict(m=5000), dict(k=0), dict(k=129), dict(ls_dim=3), dict(kernel_id=7),
-                dict(chunk_rows=100)):
+                dict(chunk_rows=128)):
         with pytest.raises(RuntimeError):
             _lib.workspace_bytes(_shape(**bad))
     assert _lib.load().gdrf_last_error() != b""
