@@ -369,7 +369,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": "observations/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (bf16x3/bf16x6 error-compensated tcgen05 products, f32 accumulate, f64 MxM prologue)",
+            "vs_baseline": None, "dtype": "f32 (error-compensated 16-bit-plane tcgen05 products: fp16x3 forward, bf16x3 backward, bf16x6 whitening; f32 accumulate; f64 per-observation chain and MxM prologue)",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: N={N} D={D} K={K} V={V} M={M} {cfg['kernel']}, sharded by "
                                    f"observation over {world} GPU(s)", "l2": "inputs (ws) exceed L2 every step",

@@ -533,8 +533,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
     }
     {
-      int rows_per_cta = (int)round_up_ll(((long long)nc * p.MT + 2 * sms - 1) / (2 * sms), 128);
-      if (rows_per_cta < 128) rows_per_cta = 128;
+      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
       k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
           dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
       LAUNCH_CHECK();
