@@ -349,12 +349,21 @@ def main():
     dom = max(kernel_ms, key=kernel_ms.get)
     dom_ms, dom_n = prof[dom]
     roofline = None
+    traffic = None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r01b_gemm_ncu_summary.json")))
+        tag = {"G2_fwd": "G2<2>", "G2_bwd": "G2<1>", "G3": "<G3>", "G6": "<G6>", "G1": "<G1>", "G4": "<G4>", "G5": "<G5>"}[dom]
+        traffic = next(v["dram_bytes"] for k, v in summ.items() if tag in k)
+    except Exception:
+        traffic = None
     if dom_n > 0 and dom_ms > 0:
         per_launch_ms = dom_ms / dom_n
         obs_per_launch = n_local * steps / dom_n
         achieved = alg[dom] * obs_per_launch / (per_launch_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "traffic_note": "dram__bytes_read+write per launch, ncu --set full, one 18 944-observation chunk (profiles/)",
+                    "peak_source": peak_src,
                     "avg_launch_ms": per_launch_ms, "launches": dom_n,
                     "share_of_step": dom_ms / (ms_dev if ms_dev > 0 else 1.0),
                     "note": "algorithmic flops: triangular-aware, each fp32 multiply-add counted once; the kernel "
