@@ -263,3 +263,39 @@ def test_full_width_shape_properties():
     assert torch.allclose(ta + tb, t, rtol=1e-9, atol=1e-3)
     for k in g:
         assert O.rel_err(ga[k] + gb[k], g[k]) < 1e-4, k
+
+
+def test_c2_shape_matern32_1d_m1000():
+    """BASELINE configs[1] shape (MVCO stand-in): 1-D Matern-3/2, M = 1000 inducing points (padded to 1024),
+    K = 8, V = 174 (not a multiple of 32), at N = 3000."""
+    inp = O.make_problem(N=3000, D=1, K=8, V=174, grid=[1000], kernel="matern32", seed=71)
+    o64, g64 = O.loss_and_grads(inp.to(torch.float64), twice=False)
+    o32, g32 = O.loss_and_grads(inp, twice=False)
+    t, g, _ = _run(inp)
+    N = inp.xs.shape[0]
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
+    for k in O.GRAD_NAMES:
+        err, err32 = O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k])
+        print("C2", k, f"{err:.1e} (fp32 oracle {err32:.1e})")
+        assert err <= (HYPER_TOL if k in HYPER else max(GRAD_TOL, 2.0 * err32)), (k, err, err32)
+
+
+def test_c5_shape_matern52_k64_v1024_m2048():
+    """BASELINE configs[4] shape (stress): 3-D Matern-5/2, M = 2048, K = 64, V = 1024 (two V-chunks in the
+    likelihood kernel), at N = 512: ELBO against the fp64 oracle, finite gradients, shard additivity."""
+    inp = O.make_problem(N=512, D=3, K=64, V=1024, grid=[16, 16, 8], kernel="matern52", seed=81)
+    with torch.no_grad():
+        o64 = O.elbo_terms(inp.to(torch.float64), twice=False)
+    t, g, _ = _run(inp)
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
+    for i, k in enumerate(("lp_mu", "lq", "ll", "lp_phi")):
+        assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * max(1.0, abs(o64[k].item())), k
+    assert all(torch.isfinite(v).all() for v in g.values())
+    ta, ga, _ = _run(O.OracleInputs(**{**inp.__dict__, "xs": inp.xs[:200], "ws": inp.ws[:200]}), n_global=512, eps=inp.eps)
+    tb, gb, _ = _run(O.OracleInputs(**{**inp.__dict__, "xs": inp.xs[200:], "ws": inp.ws[200:]}), n_global=512,
+                     n_offset=200, include_prior=False, eps=inp.eps)
+    assert torch.allclose(ta + tb, t, rtol=1e-9, atol=1e-3)
+    for k in g:
+        assert O.rel_err(ga[k] + gb[k], g[k]) < 1e-4, k
