@@ -63,7 +63,7 @@ struct Plan {
   int chunk_rows;
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, status_pad;
-  size_t L64, Linv64, tmpA, tmpB;
+  size_t L64, Linv64, tmpA, tmpB, dinv;
   size_t linv_pl, st_pl, st16_pl, w16_pl;
   // per chunk
   size_t kxz_pl, w_pl, r_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
@@ -94,6 +94,10 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   long long chunk = s->chunk_rows ? s->chunk_rows : (long long)DEFAULT_SMS * 128;
   const long long nneed = round_up_ll(s->n_local > 0 ? s->n_local : 1, 256);
   if (chunk > nneed) chunk = nneed;
+  if (!s->chunk_rows && s->n_local > chunk) {      // equal chunks: no short last wave (matters when N / ranks is small)
+    const long long nchunks = (s->n_local + chunk - 1) / chunk;
+    chunk = round_up_ll((s->n_local + nchunks - 1) / nchunks, 256);
+  }
   p.chunk_rows = (int)chunk;
   p.ncp = chunk;
   p.RTmax = (int)(chunk / 128);
@@ -112,6 +116,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.Linv64 = bump(off, sizeof(double) * Mp2);
   p.tmpA = bump(off, sizeof(double) * Mp2);
   p.tmpB = bump(off, sizeof(double) * Mp2);
+  p.dinv = bump(off, sizeof(double) * (size_t)p.Mp * NB);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
   p.st16_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
@@ -398,22 +403,25 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   CU(cudaMemsetAsync(dev_status, 0, sizeof(int), st));
   const dim3 g2d(ceil_div(p.Mp, 256), p.Mp);
   if (s->flags & GDRF_FLAG_CHOL_FP32_STATUS) {
+    // the reference's own fp32 arithmetic decides whether this jitter level "fails" (utils.py:31-37)
     float* k32 = at<float>(ws, p.tmpA);
+    float* l32 = at<float>(ws, p.tmpB);
     k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
     LAUNCH_CHECK();
-    cholesky_inplace<float>(k32, p.Mp, dev_status, st);
-    g_launches += 3 * (p.Mp / NB);
+    cholesky<float>(k32, l32, at<float>(ws, p.dinv), p.Mp, dev_status, st);
+    g_launches += 2 * (p.Mp / NB);
     LAUNCH_CHECK();
   }
   double* L = at<double>(ws, p.L64);
-  k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, L);
-  LAUNCH_CHECK();
-  cholesky_inplace<double>(L, p.Mp, dev_status, st);
-  g_launches += 3 * (p.Mp / NB);
-  LAUNCH_CHECK();
   double* Linv = at<double>(ws, p.Linv64);
-  tri_inverse(L, Linv, p.Mp, st);
-  g_launches += p.Mp / NB;
+  double* kuu = at<double>(ws, p.tmpA);
+  k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, kuu);
+  LAUNCH_CHECK();
+  cholesky<double>(kuu, L, at<double>(ws, p.dinv), p.Mp, dev_status, st);
+  g_launches += 2 * (p.Mp / NB);
+  LAUNCH_CHECK();
+  tri_inverse(L, at<double>(ws, p.dinv), Linv, p.Mp, st);
+  g_launches += 2 * (p.Mp / NB);
   LAUNCH_CHECK();
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
   k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv);
@@ -568,7 +576,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     dgemm<false, false>(tA, Linv, tB, Mp, st);
     g_launches += 5;
     LAUNCH_CHECK();
-    k_kuu_backward<<<ceil_div(M, 128), 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
+    k_kuu_backward<<<M, 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
     LAUNCH_CHECK();
   }
   const int include_prior = (s->flags & GDRF_FLAG_INCLUDE_PRIOR) ? 1 : 0;

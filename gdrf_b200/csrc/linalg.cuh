@@ -65,151 +65,142 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked right-looking Cholesky (lower), in place.  status: 0 ok, c+1 = pivot of column c not > 0.
+// Blocked right-looking Cholesky (lower), out of place: A holds Kuu and receives the trailing updates, L the
+// factor, Dinv the inverses of L's 32 x 32 diagonal blocks.  Two launches per block column:
+//   k_chol_diag : one warp, lane = row, the block lives in registers, columns exchanged by shuffles; also
+//                 inverts the triangular block.  status: 0 ok, c+1 = pivot of column c not > 0 (the
+//                 RuntimeError of torch.linalg.cholesky that gdrf/models/utils.py:31-37 catches).
+//   k_chol_trail: block (ib, jb), ib >= jb > kb: panel tiles P_i = A[ib][kb] Dinv^T, P_j likewise, then
+//                 A[ib][jb] -= P_i P_j^T; the jb == kb+1 blocks also store L[ib][kb] = P_i.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(NB * NB) k_chol_diag(T* __restrict__ A, int Mp, int kb, int* __restrict__ status) {
-  __shared__ T a[NB][NB + 1];
-  __shared__ int bad;
-  const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
-  T* blk = A + ((long long)kb * NB) * Mp + kb * NB;
-  a[r][c] = blk[(long long)r * Mp + c];
-  if (threadIdx.x == 0) bad = 0;
-  __syncthreads();
+__global__ void __launch_bounds__(32) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+                                                  int Mp, int kb, int* __restrict__ status) {
+  const int lane = threadIdx.x;
+  const T* blk = A + ((long long)kb * NB + lane) * Mp + kb * NB;
+  T a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = blk[c];
+  int bad = 0;
+#pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (threadIdx.x == 0) {
-      const T d = a[j][j];
-      if (!(d > T(0))) {
-        if (bad == 0) bad = kb * NB + j + 1;
-        a[j][j] = T(1);
-      } else {
-        a[j][j] = sqrt(d);
-      }
+    T d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > T(0))) {
+      if (bad == 0) bad = kb * NB + j + 1;
+      d = T(1);
     }
-    __syncthreads();
-    if (c == j && r > j) a[r][j] /= a[j][j];
-    __syncthreads();
-    if (c > j && r >= c) a[r][c] -= a[r][j] * a[c][j];
-    __syncthreads();
+    const T inv = T(1) / sqrt(d);
+    if (lane == j) a[j] = sqrt(d);
+    if (lane > j) a[j] *= inv;
+#pragma unroll
+    for (int c = j + 1; c < NB; ++c) {
+      const T lcj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] -= a[j] * lcj;
+    }
   }
-  blk[(long long)r * Mp + c] = (c <= r) ? a[r][c] : T(0);
-  if (threadIdx.x == 0 && bad != 0) atomicCAS(status, 0, bad);
-}
-
-// panel: A[ib][kb] <- A[ib][kb] * L_kk^-T   (one warp per 32-row block, thread = row)
-template <typename T>
-__global__ void __launch_bounds__(NB) k_chol_panel(T* __restrict__ A, int Mp, int kb) {
-  __shared__ T l[NB][NB + 1];
-  const int ib = kb + 1 + blockIdx.x;
-  const T* lk = A + ((long long)kb * NB) * Mp + kb * NB;
-  for (int t = threadIdx.x; t < NB * NB; t += NB) l[t / NB][t % NB] = lk[(long long)(t / NB) * Mp + (t % NB)];
-  __syncthreads();
-  T* row = A + ((long long)ib * NB + threadIdx.x) * Mp + kb * NB;
+  T* lb = L + ((long long)kb * NB + lane) * Mp + kb * NB;
+#pragma unroll
+  for (int c = 0; c < NB; ++c) lb[c] = (c <= lane) ? a[c] : T(0);
+  // row `lane` of the inverse: x L = e_lane, back-substituted over the columns from the right
   T x[NB];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) x[c] = row[c];
+  for (int c = 0; c < NB; ++c) x[c] = T(0);
 #pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    T s = x[c];
+  for (int j = NB - 1; j >= 0; --j) {
+    T sacc = (lane == j) ? T(1) : T(0);
 #pragma unroll
-    for (int t = 0; t < NB; ++t)
-      if (t < c) s -= x[t] * l[c][t];
-    x[c] = s / l[c][c];
+    for (int t = j + 1; t < NB; ++t) {
+      const T ltj = __shfl_sync(0xffffffffu, a[j], t);
+      sacc -= x[t] * ltj;
+    }
+    const T ljj = __shfl_sync(0xffffffffu, a[j], j);
+    x[j] = (j <= lane) ? sacc / ljj : T(0);
   }
+  T* db = Dinv + ((long long)kb * NB + lane) * NB;
 #pragma unroll
-  for (int c = 0; c < NB; ++c) row[c] = x[c];
+  for (int c = 0; c < NB; ++c) db[c] = x[c];
+  if (lane == 0 && bad != 0) atomicCAS(status, 0, bad);
 }
 
-// trailing update: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for ib >= jb > kb; also zeroes blocks above the diagonal
 template <typename T>
-__global__ void __launch_bounds__(NB * NB) k_chol_update(T* __restrict__ A, int Mp, int kb) {
+__global__ void __launch_bounds__(NB * NB) k_chol_trail(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
+                                                        int Mp, int kb) {
   const int ib = kb + 1 + blockIdx.y, jb = kb + 1 + blockIdx.x;
   if (jb > ib) return;
-  __shared__ T li[NB][NB + 1], lj[NB][NB + 1];
+  __shared__ T ai[NB][NB + 1], aj[NB][NB + 1], dd[NB][NB + 1];
   const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
-  li[r][c] = A[((long long)ib * NB + r) * Mp + kb * NB + c];
-  lj[r][c] = A[((long long)jb * NB + r) * Mp + kb * NB + c];
+  ai[r][c] = A[((long long)ib * NB + r) * Mp + kb * NB + c];
+  aj[r][c] = A[((long long)jb * NB + r) * Mp + kb * NB + c];
+  dd[r][c] = Dinv[((long long)kb * NB + r) * NB + c];
+  __syncthreads();
+  T pi = 0, pj = 0;
+#pragma unroll
+  for (int t = 0; t < NB; ++t) {
+    pi += ai[r][t] * dd[c][t];
+    pj += aj[r][t] * dd[c][t];
+  }
+  __syncthreads();
+  ai[r][c] = pi;
+  aj[r][c] = pj;
+  if (jb == kb + 1) L[((long long)ib * NB + r) * Mp + kb * NB + c] = pi;
   __syncthreads();
   T s = 0;
 #pragma unroll
-  for (int t = 0; t < NB; ++t) s += li[r][t] * lj[c][t];
+  for (int t = 0; t < NB; ++t) s += ai[r][t] * aj[c][t];
   A[((long long)ib * NB + r) * Mp + jb * NB + c] -= s;
 }
 
+// A: Kuu (destroyed), L: factor (zero above the diagonal), Dinv: [Mp/32][32][32]
 template <typename T>
-__global__ void k_zero_upper(T* __restrict__ A, int Mp) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-  if (j < Mp && j > i) A[(long long)i * Mp + j] = T(0);
-}
-
-template <typename T>
-inline void cholesky_inplace(T* A, int Mp, int* status, cudaStream_t st) {
+inline void cholesky(T* A, T* L, T* Dinv, int Mp, int* status, cudaStream_t st) {
+  cudaMemsetAsync(L, 0, sizeof(T) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
   for (int kb = 0; kb < nblk; ++kb) {
-    k_chol_diag<T><<<1, NB * NB, 0, st>>>(A, Mp, kb, status);
+    k_chol_diag<T><<<1, NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
     const int rem = nblk - kb - 1;
-    if (rem > 0) {
-      k_chol_panel<T><<<rem, NB, 0, st>>>(A, Mp, kb);
-      k_chol_update<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, Mp, kb);
-    }
+    if (rem > 0) k_chol_trail<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb);
   }
-  k_zero_upper<T><<<dim3(ceil_div(Mp, 256), Mp), 256, 0, st>>>(A, Mp);
 }
 
 // ---------------------------------------------------------------------------------------------
-// X = L^-1 (lower), blocked forward substitution by block rows.
+// X = L^-1 (lower): block forward substitution on the identity with rank-32 updates.  X doubles as the
+// right-hand side: before block row k is solved, X[k][j] (j < k) holds -sum_{t<k} L[k][t] X[t][j].
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB) k_trinv_diag(const double* __restrict__ L, double* __restrict__ X, int Mp) {
-  __shared__ double l[NB][NB + 1];
-  const int b = blockIdx.x;
-  const double* lb = L + ((long long)b * NB) * Mp + b * NB;
-  for (int t = threadIdx.x; t < NB * NB; t += NB) l[t / NB][t % NB] = lb[(long long)(t / NB) * Mp + (t % NB)];
-  __syncthreads();
-  const int c = threadIdx.x;   // column of the inverse
-  double x[NB];
-#pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    double s = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int t = 0; t < NB; ++t)
-      if (t < r) s -= l[r][t] * x[t];
-    x[r] = s / l[r][r];
-  }
-  double* xb = X + ((long long)b * NB) * Mp + b * NB;
-#pragma unroll
-  for (int r = 0; r < NB; ++r) xb[(long long)r * Mp + c] = (r >= c) ? x[r] : 0.0;
-}
-
-// X[ib][jb] = -X[ib][ib] * sum_{t=jb}^{ib-1} L[ib][t] X[t][jb]     grid = ib blocks (jb = blockIdx.x)
-__global__ void __launch_bounds__(NB * NB) k_trinv_row(const double* __restrict__ L, double* __restrict__ X, int Mp,
-                                                       int ib) {
-  __shared__ double a[NB][NB + 1], b[NB][NB + 1];
-  const int jb = blockIdx.x;
+__global__ void __launch_bounds__(NB * NB) k_trinv_solve(double* __restrict__ X, const double* __restrict__ Dinv,
+                                                         int Mp, int k) {
+  __shared__ double d[NB][NB + 1], b[NB][NB + 1];
+  const int j = blockIdx.x;   // 0..k
   const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
+  d[r][c] = Dinv[((long long)k * NB + r) * NB + c];
+  b[r][c] = (j == k) ? (r == c ? 1.0 : 0.0) : X[((long long)k * NB + r) * Mp + j * NB + c];
+  __syncthreads();
   double s = 0.0;
-  for (int t = jb; t < ib; ++t) {
-    __syncthreads();
-    a[r][c] = L[((long long)ib * NB + r) * Mp + t * NB + c];
-    b[r][c] = X[((long long)t * NB + r) * Mp + jb * NB + c];
-    __syncthreads();
 #pragma unroll
-    for (int e = 0; e < NB; ++e) s += a[r][e] * b[e][c];
-  }
-  __syncthreads();
-  a[r][c] = X[((long long)ib * NB + r) * Mp + ib * NB + c];
-  b[r][c] = s;
-  __syncthreads();
-  double o = 0.0;
-#pragma unroll
-  for (int e = 0; e < NB; ++e) o += a[r][e] * b[e][c];
-  X[((long long)ib * NB + r) * Mp + jb * NB + c] = -o;
+  for (int t = 0; t < NB; ++t) s += d[r][t] * b[t][c];
+  X[((long long)k * NB + r) * Mp + j * NB + c] = s;
 }
 
-inline void tri_inverse(const double* L, double* X, int Mp, cudaStream_t st) {
+__global__ void __launch_bounds__(NB * NB) k_trinv_update(const double* __restrict__ L, double* __restrict__ X, int Mp,
+                                                          int k) {
+  __shared__ double l[NB][NB + 1], x[NB][NB + 1];
+  const int i = k + 1 + blockIdx.y, j = blockIdx.x;   // i > k, j <= k
+  const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
+  l[r][c] = L[((long long)i * NB + r) * Mp + k * NB + c];
+  x[r][c] = X[((long long)k * NB + r) * Mp + j * NB + c];
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < NB; ++t) s += l[r][t] * x[t][c];
+  X[((long long)i * NB + r) * Mp + j * NB + c] -= s;
+}
+
+inline void tri_inverse(const double* L, const double* Dinv, double* X, int Mp, cudaStream_t st) {
   cudaMemsetAsync(X, 0, sizeof(double) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
-  k_trinv_diag<<<nblk, NB, 0, st>>>(L, X, Mp);
-  for (int ib = 1; ib < nblk; ++ib) k_trinv_row<<<ib, NB * NB, 0, st>>>(L, X, Mp, ib);
+  for (int k = 0; k < nblk; ++k) {
+    k_trinv_solve<<<k + 1, NB * NB, 0, st>>>(X, Dinv, Mp, k);
+    if (k + 1 < nblk) k_trinv_update<<<dim3(k + 1, nblk - k - 1), NB * NB, 0, st>>>(L, X, Mp, k);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -275,46 +266,47 @@ __global__ void __launch_bounds__(128) k_kuu_backward(const double* __restrict__
                                                       int M, Hyper hp, double* __restrict__ dz_acc,
                                                       double* __restrict__ acc) {
   __shared__ double scratch[32];
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.x;       // one block per row a; threads stride over j
   const int D = hp.D;
   double dz[MAX_D], dl[MAX_D], dv = 0.0;
-  for (int d = 0; d < D; ++d) dz[d] = dl[d] = 0.0;
-  if (a < M) {
-    const double var = hp.variance[0];
-    double za[MAX_D], il[MAX_D];
+  double za[MAX_D], il[MAX_D];
+  for (int d = 0; d < D; ++d) {
+    dz[d] = dl[d] = 0.0;
+    za[d] = Z[a * D + d];
+    il[d] = 1.0 / (double)hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+  }
+  const double var = hp.variance[0];
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const double g = 0.5 * (GK[(long long)a * Mp + j] + GK[(long long)j * Mp + a]);
+    double diff[MAX_D], r2 = 0.0;
     for (int d = 0; d < D; ++d) {
-      za[d] = Z[a * D + d];
-      il[d] = 1.0 / (double)hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+      diff[d] = (za[d] - (double)Z[j * D + d]) * il[d];
+      r2 += diff[d] * diff[d];
     }
-    for (int j = 0; j < M; ++j) {
-      const double g = 0.5 * (GK[(long long)a * Mp + j] + GK[(long long)j * Mp + a]);
-      double diff[MAX_D], r2 = 0.0;
-      for (int d = 0; d < D; ++d) {
-        diff[d] = (za[d] - (double)Z[j * D + d]) * il[d];
-        r2 += diff[d] * diff[d];
-      }
-      double k, dk;
-      kernel_eval<double>(hp.kid, r2, k, dk);
-      dv += g * k;
-      const double h = g * var * dk;
-      for (int d = 0; d < D; ++d) {
-        dz[d] += 4.0 * h * diff[d] * il[d];          // both arguments of k(z_a, z_j) move with z_a
-        dl[d] += -2.0 * h * diff[d] * diff[d] * il[d];
-      }
+    double k, dk;
+    kernel_eval<double>(hp.kid, r2, k, dk);
+    dv += g * k;
+    const double h = g * var * dk;
+    for (int d = 0; d < D; ++d) {
+      dz[d] += 4.0 * h * diff[d] * il[d];          // both arguments of k(z_a, z_j) move with z_a
+      dl[d] += -2.0 * h * diff[d] * diff[d] * il[d];
     }
-    for (int d = 0; d < D; ++d) atomicAdd(&dz_acc[a * D + d], dz[d]);
+  }
+  for (int d = 0; d < D; ++d) {
+    const double t = block_sum(dz[d], scratch);
+    if (threadIdx.x == 0) atomicAdd(&dz_acc[a * D + d], t);
   }
   dv = block_sum(dv, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dv);
   if (hp.ls_dim == 1) {
-    double s = 0.0;
-    for (int d = 0; d < D; ++d) s += dl[d];
-    s = block_sum(s, scratch);
-    if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS], s);
+    double t = 0.0;
+    for (int d = 0; d < D; ++d) t += dl[d];
+    t = block_sum(t, scratch);
+    if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS], t);
   } else {
     for (int d = 0; d < D; ++d) {
-      double s = block_sum(dl[d], scratch);
-      if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS + d], s);
+      const double t = block_sum(dl[d], scratch);
+      if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS + d], t);
     }
   }
 }
