@@ -44,8 +44,11 @@ def test_sizes_and_argument_validation():
     b1 = _lib.workspace_bytes(s)
     b2 = _lib.workspace_bytes(_shape(n_local=100000, n_eps=100000))
     assert 0 < b1 < b2
-    # workspace is O(chunk), independent of N beyond one chunk
-    assert _lib.workspace_bytes(_shape(n_local=10 ** 7, n_eps=10 ** 7)) == b2
+    # workspace is O(chunk): bounded by the default chunk of 148 * 128 observations however large N is
+    cap = _lib.workspace_bytes(_shape(n_local=148 * 128, n_eps=148 * 128))
+    assert b2 <= cap
+    assert _lib.workspace_bytes(_shape(n_local=10 ** 7, n_eps=10 ** 7)) <= cap
+    assert _lib.workspace_bytes(_shape(n_local=10 ** 9, n_eps=10 ** 9)) <= cap
     for bad in (dict(d=0), dict(d=9), dict(m=5000), dict(k=0), dict(k=129), dict(ls_dim=3), dict(kernel_id=7),
                 dict(chunk_rows=128)):
         with pytest.raises(RuntimeError):
