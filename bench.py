@@ -199,6 +199,13 @@ def run_reference(args, cfg_name, cfg):
     print(json.dumps(line), flush=True)
 
 
+def _flat_of(g):
+    """The gradient views returned by split_grad share one flat buffer; recover it for a single all-reduce."""
+    base = g["u_scale_tril"]
+    total = sum(v.numel() for v in g.values())
+    return base.reshape(-1).as_strided((total,), (1,))
+
+
 def _prod(xs):
     p = 1
     for x in xs:
@@ -305,12 +312,26 @@ def main():
     e2e = None
     if not args.no_e2e:
         hx, hw, he = (t_.cpu().pin_memory() for t_ in (xs, ws, eps))
-        dx, dw, de = torch.empty_like(xs), torch.empty_like(ws), torch.empty_like(eps)
         h_terms = torch.empty(4, dtype=torch.float64).pin_memory()
 
+        from gdrf_b200.elbo import elbo_value_and_grads_from_host
+        n_sub = max(2, min(8, n_local // 60000))
+        per = ((n_local + n_sub - 1) // n_sub + 255) // 256 * 256
+        staging = [dict(xs=torch.empty(per, D, dtype=torch.float32, device=dev),
+                        ws=torch.empty(per, V, dtype=torch.int32, device=dev),
+                        eps=torch.empty(K, per, dtype=torch.float32, device=dev)) for _ in range(2)]
+
+
         def e2e_step():
-            dx.copy_(hx, non_blocking=True); dw.copy_(hw, non_blocking=True); de.copy_(he, non_blocking=True)
-            tm, _ = one_step(dx, dw, de)
+            # public host-buffer API: sub-shards are copied H2D on a second stream while the previous one computes
+            tm, g_, _ = elbo_value_and_grads_from_host(
+                hx, hw, he, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],
+                prm["noise"], prm["phi"], prm["beta"], kernel=cfg["kernel"], jitter=jitter, maxjitter=maxjitter,
+                n_global=N, include_prior=(rank == 0), flags=flags & ~_lib.FLAG_INCLUDE_PRIOR, n_sub=n_sub,
+                staging=staging)
+            if world > 1:
+                dist.all_reduce(_flat_of(g_), op=dist.ReduceOp.SUM)
+                dist.all_reduce(tm, op=dist.ReduceOp.SUM)
             h_terms.copy_(tm, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return h_terms

@@ -20,6 +20,8 @@ FLAG_INCLUDE_PRIOR = 2
 FLAG_CHOL_FP32_STATUS = 4
 FLAG_FWD_BF16 = 16
 FLAG_SINGLE_CTA = 32
+FLAG_CONTINUE = 64
+FLAG_PARTIAL = 128
 FLAG_REF_G = {i: 1 << (7 + i) for i in range(1, 7)}
 FLAG_REF_ALL = 0x3F << 8
 

@@ -456,8 +456,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   const Hyper hp = make_hyper(s, in);
   const int K = p.K, M = p.M, Mp = p.Mp;
 
-  CU(cudaMemsetAsync(at<char>(ws, p.acc), 0, (size_t)p.zero_bytes, st));
-  if (want_grad) CU(cudaMemsetAsync(out->grad, 0, sizeof(float) * (size_t)K * M * M, st));
+  const bool cont = (s->flags & GDRF_FLAG_CONTINUE) != 0;   // accumulators carry over from the previous call
+  const bool partial = (s->flags & GDRF_FLAG_PARTIAL) != 0; // more sub-shards follow: skip the per-step epilogue
+  if (!cont) {
+    CU(cudaMemsetAsync(at<char>(ws, p.acc), 0, (size_t)p.zero_bytes, st));
+    if (want_grad) CU(cudaMemsetAsync(out->grad, 0, sizeof(float) * (size_t)K * M * M, st));
+  }
 
   PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
   PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
@@ -468,8 +472,10 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   float* dwf = at<float>(ws, p.dwf);
   double* acc = at<double>(ws, p.acc);
 
-  k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
-  LAUNCH_CHECK();
+  if (!cont) {
+    k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
+    LAUNCH_CHECK();
+  }
 
   // tiles of dS on / below the diagonal (i tile of 128 rows, j tile of 256 columns)
   G6::Params g6{};
@@ -560,7 +566,8 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     }
   }
 
-  if (want_grad && s->n_local > 0) {
+  if (partial) return 0;
+  if (want_grad) {
     // Cholesky adjoint (Murray 2016; torch cholesky_backward):  G_L = -tril(L^-T C5),
     // Phi = tril(L^T G_L) with halved diagonal, G_K = L^-T Phi L^-1, symmetrised inside k_kuu_backward.
     double* L = at<double>(ws, p.L64);

@@ -106,14 +106,15 @@ class _Call:
                 return nj
         raise RuntimeError("reached max jitter, covariance is unstable")
 
-    def step(self, want_grad: bool):
+    def step(self, want_grad: bool, terms=None, grad=None, extra_flags: int = 0):
         lib = _lib.load()
-        terms = torch.empty(4, dtype=torch.float64, device=self.device)
-        grad = None
-        flags = self.shape.flags & ~_lib.FLAG_WANT_GRAD
+        if terms is None:
+            terms = torch.empty(4, dtype=torch.float64, device=self.device)
+        flags = (self.shape.flags & ~_lib.FLAG_WANT_GRAD) | int(extra_flags)
         if want_grad:
             flags |= _lib.FLAG_WANT_GRAD
-            grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
+            if grad is None:
+                grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
         self.shape.flags = flags
         out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None)
         _lib.check(lib.gdrf_elbo_step(ctypes.byref(self.shape), ctypes.byref(self.inputs), ctypes.byref(out),
@@ -195,6 +196,73 @@ def elbo_value_and_grads(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, 
     nj = call.prologue(jitter, maxjitter)
     terms, grad = call.step(True)
     g = split_grad(grad, u_loc.shape[0], Z.shape[0], ws.shape[1], xs.shape[1], call.shape.ls_dim)
+    return terms, g, nj
+
+
+def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, lengthscale, u_loc, u_scale_tril, noise,
+                                   phi, beta, kernel: str = "rbf", jitter: float = 1e-8, maxjitter: int = 5,
+                                   n_global=None, n_offset: int = 0, include_prior: bool = True,
+                                   flags: int = _lib.FLAG_CHOL_FP32_STATUS, n_sub: int = 8, staging=None):
+    """Same result as :func:`elbo_value_and_grads`, with the observations (``xs_host`` [N, D] fp32, ``ws_host``
+    [N, V] int32, ``eps_host`` [K, >= n_offset + N] fp32) living in pinned HOST memory.  The shard is cut into
+    ``n_sub`` sub-shards; while sub-shard i is being evaluated on the compute stream, sub-shard i+1 is copied
+    host-to-device on a second stream into the other half of a double buffer (GDRF_FLAG_CONTINUE /
+    GDRF_FLAG_PARTIAL carry the accumulators across the calls).  Parameters are device tensors.
+    Returns (terms, grads dict, njitter)."""
+    dev = Z.device
+    N, D = xs_host.shape
+    V = ws_host.shape[1]
+    K, M = u_loc.shape
+    fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
+    n_sub = max(1, min(int(n_sub), (N + 255) // 256))
+    per = ((N + n_sub - 1) // n_sub + 255) // 256 * 256
+    bounds = [(lo, min(N, lo + per)) for lo in range(0, max(N, 1), per)]
+    rows = per if N > 0 else 1
+    if staging is None:
+        staging = [dict(xs=torch.empty(rows, D, dtype=torch.float32, device=dev),
+                        ws=torch.empty(rows, V, dtype=torch.int32, device=dev),
+                        eps=torch.empty(K, rows, dtype=torch.float32, device=dev)) for _ in range(2)]
+    compute = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    calls = []
+    for i, (lo, hi) in enumerate(bounds):
+        st_ = staging[i % 2]
+        n = hi - lo
+        calls.append(_Call(st_["xs"][:n], st_["ws"][:n], Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta,
+                           st_["eps"], _lib.KERNEL_IDS[kernel], 0, fl, 0))
+    free_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    copied_ev = [torch.cuda.Event() for _ in bounds]
+
+    def issue_copy(i):
+        lo, hi = bounds[i]
+        n = hi - lo
+        st_ = staging[i % 2]
+        with torch.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(free_ev[i % 2])
+            else:
+                copy_stream.wait_stream(compute)
+            st_["xs"][:n].copy_(xs_host[lo:hi], non_blocking=True)
+            st_["ws"][:n].copy_(ws_host[lo:hi], non_blocking=True)
+            for k in range(K):     # row by row: each source slice is contiguous pinned memory
+                st_["eps"][k, :n].copy_(eps_host[k, n_offset + lo:n_offset + hi], non_blocking=True)
+            copied_ev[i].record(copy_stream)
+
+    issue_copy(0)
+    nj = calls[0].prologue(jitter, maxjitter)
+    for c in calls[1:]:
+        c.shape.flags = calls[0].shape.flags
+    terms = torch.empty(4, dtype=torch.float64, device=dev)
+    grad = torch.empty(_lib.grad_elems(calls[0].shape), dtype=torch.float32, device=dev)
+    for i, call in enumerate(calls):
+        if i + 1 < len(calls):
+            issue_copy(i + 1)
+        compute.wait_event(copied_ev[i])
+        extra = (_lib.FLAG_CONTINUE if i > 0 else 0) | (_lib.FLAG_PARTIAL if i + 1 < len(calls) else 0)
+        call.shape.flags &= ~(_lib.FLAG_CONTINUE | _lib.FLAG_PARTIAL)
+        call.step(True, terms=terms, grad=grad, extra_flags=extra)
+        free_ev[i % 2].record(compute)
+    g = split_grad(grad, K, M, V, D, calls[0].shape.ls_dim)
     return terms, g, nj
 
 

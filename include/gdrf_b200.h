@@ -36,6 +36,10 @@ enum {
   GDRF_FLAG_FWD_BF16 = 16,        /* forward row-norm contraction on 3 bf16 planes / 6 products (24-bit operands,
                                      any fp32 range) instead of 2 fp16 planes / 3 products (22-bit, |x| < 6e4);
                                      required when gdrf_prologue reported status -1                          */
+  GDRF_FLAG_CONTINUE = 64,        /* gdrf_elbo_step: keep the accumulators of the previous call on this workspace
+                                     (second and later sub-shards of one step streamed from host memory)       */
+  GDRF_FLAG_PARTIAL = 128,        /* gdrf_elbo_step: more sub-shards follow; skip the per-step epilogue (Cholesky
+                                     adjoint, prior, gradient assembly, terms)                                 */
   GDRF_FLAG_SINGLE_CTA = 32,      /* run the four large contractions on single CTAs (cta_group::1) instead of
                                      CTA pairs (cta_group::2); same results, used for A/B measurement         */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
@@ -97,7 +101,9 @@ int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter,
 
 /* One evaluation of the ELBO terms (and, with GDRF_FLAG_WANT_GRAD, of the full gradient) over this shard,
  * streamed in chunks of chunk_rows observations.  Requires a successful gdrf_prologue on the same
- * workspace with the same z / variance / lengthscale.                                                       */
+ * workspace with the same z / variance / lengthscale.  A shard may be fed in several calls (sub-shards with
+ * the same chunk_rows, the same out->grad; GDRF_FLAG_PARTIAL on all but the last, GDRF_FLAG_CONTINUE on all but
+ * the first) so that host-to-device copies of the next sub-shard overlap the current one.                    */
 int gdrf_elbo_step(const gdrf_shape* shape, const gdrf_inputs* in, const gdrf_outputs* out, void* workspace,
                    size_t workspace_bytes, gdrf_stream_t stream);
 
