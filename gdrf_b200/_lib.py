@@ -94,7 +94,7 @@ def grad_elems(shape: Shape) -> int:
     return int(out.value)
 
 
-PROFILE_KINDS = ("G1", "G2_fwd", "G2_bwd", "G3", "G4", "G5", "G6")
+PROFILE_KINDS = ("G1", "G2_fwd", "scale_w", "G3", "G4", "G5", "G6")
 
 
 def profile_read():

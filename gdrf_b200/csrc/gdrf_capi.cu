@@ -66,7 +66,7 @@ struct Plan {
   size_t L64, Linv64, tmpA, tmpB, dinv;
   size_t linv_pl, st_pl, st16_pl, w16_pl;
   // per chunk
-  size_t kxz_pl, w_pl, r_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
+  size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
   size_t wsq, srow, arow, cnt, gv0, floc, q, fvar, theta, g_loc, g2, g1;
   size_t total;
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
@@ -124,7 +124,8 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w16_pl = bump(off, sizeof(bf16) * 2 * nm);
-  p.r_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
+  p.tp_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
+  p.wg_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.dwf = bump(off, sizeof(float) * nm);
   p.wsq = bump(off, sizeof(double) * p.ncp);
   p.srow = bump(off, sizeof(float) * p.ncp);
@@ -232,7 +233,7 @@ cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool u
 
 // forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
 int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
-                  bool with_var, int sms, cudaStream_t st) {
+                  bool with_var, bool store_t, int sms, cudaStream_t st) {
   const Hyper hp = make_hyper(s, in);
   PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, p.Mp);
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
@@ -250,14 +251,14 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   if (with_var) {
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
       G2<0>::Params g{};
-      g.w = w; g.st = stm; g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
-      g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<0>::BN; g.ncp = (int)p.ncp;
+      g.w = w; g.st = stm; g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
+      g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<0>::BN; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<0>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
     } else {                                 // fp16 2 x 2 planes (22-bit operands), 3 products
       G2<2>::Params g{};
       g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp);
-      g.r = plane_mat(ws, p.r_pl, p.ncp, (long long)p.K * p.Mp);
-      g.q = at<double>(ws, p.q); g.g2 = nullptr; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
+      g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
+      g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
   }
@@ -468,7 +469,8 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
   PlaneMat stm = plane_mat(ws, p.st_pl, (long long)K * Mp, Mp);
-  PlaneMat rm = plane_mat(ws, p.r_pl, p.ncp, (long long)K * Mp);
+  PlaneMat tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)K * Mp);
+  PlaneMat wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)K * Mp);
   float* dwf = at<float>(ws, p.dwf);
   double* acc = at<double>(ws, p.acc);
 
@@ -497,7 +499,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, sms, st)) return e;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
     k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
                                       at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
                                       at<float>(ws, p.phisum), at<float>(ws, p.fvar),
@@ -512,14 +514,14 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     LAUNCH_CHECK();
     if (!want_grad) continue;
     {
-      G2<1>::Params g{};
-      g.w = w; g.st = stm; g.r = rm; g.q = nullptr; g.g2 = at<float>(ws, p.g2);
-      g.RT = RT; g.MB = p.MB; g.K = K; g.NT = Mp / G2<1>::BN; g.ncp = (int)p.ncp;
-      { ProfScope ps(PK_G2B, st); ++g_launches; CU(launch_big<G2<1>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+      ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
+      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm);
+      LAUNCH_CHECK();
     }
     {
       G3::Params g{};
-      g.r = rm; g.st = stm; g.dw = dwf; g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp;
+      g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
+      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
@@ -531,7 +533,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     }
     if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
     {
-      g6.w = w; g6.r = rm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
+      g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
       const int base = K * g6.ntile;
       int splits = base >= sms ? 1 : (sms + base - 1) / base;
       const int NBt = 2 * RT;
@@ -626,7 +628,7 @@ int gdrf_marginal_mean(const gdrf_shape* s, const gdrf_inputs* in, float* out_fl
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, false, sms, st)) return e;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, false, false, sms, st)) return e;
     k_export_floc<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
                                                              out_floc + n0, (long long)s->n_local);
     LAUNCH_CHECK();

@@ -139,7 +139,9 @@ __host__ __device__ constexpr int num_products(int PA, int PB) {
   return n;
 }
 
-constexpr int GEMM_THREADS = 192;
+// warps: 0 = bulk-copy producer, 1 = MMA issuer / TMEM owner, 2.. = epilogue (P::EPI_WARPS of them, 4 or 8)
+template <class P>
+constexpr int gemm_threads() { return 64 + 32 * P::EPI_WARPS; }
 constexpr int GEMM_SMEM_BUDGET = 216 * 1024;
 
 template <class P>
@@ -158,7 +160,7 @@ struct GemmCfg {
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------
 template <class P>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ typename P::Params prm) {
+__global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __grid_constant__ typename P::Params prm) {
   using Cfg = GemmCfg<P>;
   constexpr int NST = Cfg::NSTAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], P::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -280,9 +282,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    // ------------------------------ epilogue (warps 2..) ------------------------------
+    // a warp may only read the TMEM lane quarter warp%4; with 8 epilogue warps the second four take the upper
+    // half of the accumulator columns
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // accumulator row owned by this thread
+    constexpr int NCH = (P::BN / 32) / (P::EPI_WARPS / 4);
+    const int c_begin = ((warp - 2) >> 2) * NCH;
     typename P::Epi epi;
     uint32_t unit = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -296,10 +302,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * P::BN;
 #pragma unroll 1
-        for (int c = 0; c < P::BN / 32; ++c) {
+        for (int c = c_begin; c < c_begin + NCH; ++c) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
-          if (c == P::BN / 32 - 1) {           // accumulator fully read: hand the TMEM stage back
+          if (c == c_begin + NCH - 1) {        // this warp's share is read: hand the TMEM stage back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -385,7 +391,7 @@ struct Gemm2Cfg {
 };
 
 template <class P>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1)
     gemm_tc2_kernel(const __grid_constant__ typename P::Params prm, int n_items1) {
   using Cfg = Gemm2Cfg<P>;
   constexpr int NST = Cfg::NSTAGES;
@@ -413,7 +419,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], 2 * P::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -538,9 +544,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
+    // ------------------------------ epilogue (warps 2.., both CTAs) ------------------------------
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    constexpr int NCH = 8 / (P::EPI_WARPS / 4);
+    const int c_begin = ((warp - 2) >> 2) * NCH;
     typename P::Epi epi;
     uint32_t unit = 0;
     for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
@@ -557,10 +565,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c_begin; c < c_begin + NCH; ++c) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
-          if (c == 7) {
+          if (c == c_begin + NCH - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -589,8 +597,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 // plain-FMA checker with the same policy interface (tests only; 128 threads, thread = row)
 // ------------------------------------------------------------------------------------------
 template <class P>
-__global__ void __launch_bounds__(128) gemm_ref_kernel(const typename P::Params prm) {
-  const int row = threadIdx.x;
+__global__ void __launch_bounds__(32 * P::EPI_WARPS) gemm_ref_kernel(const typename P::Params prm) {
+  const int row = threadIdx.x & 127;
+  constexpr int NCH = (P::BN / 32) / (P::EPI_WARPS / 4);
+  const int c_begin = (threadIdx.x >> 7) * NCH;
   const int n_items = P::num_items(prm);
   typename P::Epi epi;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -599,7 +609,7 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(const typename P::Params 
     for (int sub = 0; sub < nsub; ++sub) {
       epi.sub_begin(prm, item, sub, row);
       const int kn = P::k_iters(prm, item, sub);
-      for (int c = 0; c < P::BN / 32; ++c) {
+      for (int c = c_begin; c < c_begin + NCH; ++c) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -636,14 +646,14 @@ inline cudaError_t launch_gemm(const typename P::Params& prm, int n_items, int n
                                cudaStream_t stream) {
   if (n_items <= 0) return cudaSuccess;
   if (use_ref) {
-    gemm_ref_kernel<P><<<n_items < 4096 ? n_items : 4096, 128, 0, stream>>>(prm);
+    gemm_ref_kernel<P><<<n_items < 4096 ? n_items : 4096, 32 * P::EPI_WARPS, 0, stream>>>(prm);
     return cudaGetLastError();
   }
   using Cfg = GemmCfg<P>;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  gemm_tc_kernel<P><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm);
+  gemm_tc_kernel<P><<<grid, gemm_threads<P>(), Cfg::SMEM_BYTES, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -656,7 +666,7 @@ inline cudaError_t launch_gemm2(const typename P::Params& prm, int n_items1, int
   const int n_items2 = (n_items1 + 1) / 2;
   int clusters = num_sms / 2;
   if (clusters > n_items2) clusters = n_items2;
-  gemm_tc2_kernel<P><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(prm, n_items1);
+  gemm_tc2_kernel<P><<<2 * clusters, gemm_threads<P>(), Cfg::SMEM_BYTES, stream>>>(prm, n_items1);
   return cudaGetLastError();
 }
 

@@ -2,17 +2,18 @@
 //
 // Notation: n observation, i/j/m inducing index, k topic.
 //   Kxz = k(xs, Z)              W   = Kxz Linv^T            (Linv = chol(Kuu + jI)^-1, lower)
-//   T_k = W S_k                 q_kn = sum_j T_k[n,j]^2     (S_k lower triangular)
-//   R_k = diag(2 g_var[k,:]) T_k
-//   dW  = sum_k R_k S_k^T (+ mean / var0 terms added by k_dw_finalize)
-//   dS_k = tril(W^T R_k)        dKxz = dWtot Linv           C5 = dWtot^T W   (feeds the Cholesky adjoint)
+//   T_k = W S_k                 q_kn = sum_j T_k[n,j]^2     (S_k lower triangular; T is kept, 16-bit, for the backward)
+//   g2  = 2 dELBO/df_var        WG_k = diag(g2[k,:]) W
+//   dW  = sum_k diag(g2[k,:]) (T_k S_k^T) (+ mean / var0 terms added by k_dw_finalize)
+//   dS_k = tril(WG_k^T T_k)     dKxz = dWtot Linv           C5 = dWtot^T W   (feeds the Cholesky adjoint)
 //
 // Operand storage (all "tiled planes", common.cuh), per chunk of RT*128 observation rows, Mp = M
 // rounded up to 256, MB = Mp/64, JT = Mp/256:
 //   KXZ, W, DWT : [rows n][cols inducing]            3 planes
 //   LINV        : [rows m][cols i]                   3 planes   (zero above the diagonal / in padding)
-//   ST          : [rows (k, j)][cols i] = S_k[i, j]  3 planes   (zero for i < j; backward reads 2)
-//   R           : [rows n][cols (k, j)]              2 planes
+//   ST          : [rows (k, j)][cols i] = S_k[i, j]  3 bf16 planes (+ 2 fp16 planes for the forward); zero for i < j
+//   TP          : [rows n][cols (k, j)] = T_k[n, j]  2 planes   (written by the forward contraction's epilogue)
+//   WG          : [rows n][cols (k, m)] = g2[k,n] W  2 planes   (k_scale_w)
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -37,6 +38,7 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // G1:  W[n, m] = sum_{i <= m} Kxz[n, i] Linv[m, i]      epilogue: W planes + wsq[n] = sum_m W^2
 // ---------------------------------------------------------------------------------------------
 struct G1 {
+  static constexpr int EPI_WARPS = 4;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
@@ -81,28 +83,24 @@ struct G1 {
 
 // ---------------------------------------------------------------------------------------------
 // G2:  T[n, (k, j)] = sum_{i >= j} W[n, i] S_k[i, j]
-//   FWD epilogue: q[k, n] = sum_j T^2          BWD epilogue: R = 2 g_var[k, n] * T  (2 planes)
+//   epilogue: q[k, n] = sum_j T^2 (fp64) and, when the gradient is wanted, T itself as two bf16 planes (TP).
+//   T is needed to fp32 accuracy here: f_var enters mu = f_loc + f_var * eps as a *scale* of O(variance) and
+//   d ll / d mu is O(counts), so a 2^-17 relative error in q shows up as 1e-3 in the gradients.
+// MODE 0: bf16 3 x 3 planes / 6 products, 128-wide tiles (24-bit operands; any fp32 range)
+// MODE 2: fp16 2 x 2 planes / 3 products, 256-wide tiles (22-bit operands) -- the default
 // ---------------------------------------------------------------------------------------------
-// MODE 0: forward, bf16 3x3 planes / 6 products, 128-wide tiles (reference-precision path, also the fallback
-//         when an operand leaves the fp16 range)
-// MODE 1: backward, bf16 2x2 planes / 3 products, 256-wide tiles, R epilogue
-// MODE 2: forward, fp16 2x2 planes / 3 products (22-bit operands), 256-wide tiles -- the default forward
 template <int MODE>
 struct G2 {
-  static constexpr bool BWD = (MODE == 1);
+  static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
-  // The forward needs T to fp32 accuracy: f_var enters mu = f_loc + f_var * eps as a *scale* of O(variance),
-  // and d ll / d mu is O(counts), so a 2^-17 relative error in q shows up as 1e-3 in the gradients.
-  // Forward: 3 planes x 3 planes, 6 products, 128-wide tiles.  Backward (R only feeds averaged sums):
-  // 2 x 2 planes, 3 products, 256-wide tiles.
   static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int CB = BN / 64;      // 64-column blocks per tile
   static constexpr int PCS = BN / 128;    // 128-row pieces of ST per tile
   struct Params {
-    PlaneMat w, st, r;
-    double* q;         // [K][ncp]   (FWD out, fp64: q feeds mu = f_loc + f_var * eps)
-    const float* g2;   // [K][ncp]   (BWD in: 2 * dELBO/df_var)
+    PlaneMat w, st, tp;
+    double* q;         // [K][ncp]  (fp64: q feeds mu = f_loc + f_var * eps)
+    int store_t;       // write TP (gradient pass)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
@@ -117,76 +115,104 @@ struct G2 {
     return p.st.base + pl * p.st.plane_stride + p.st.block_off(sub * PCS + pc, CB * jt + kit);
   }
   struct Epi {
-    float acc;     // BWD: row scale 2 g_var
-    double qacc;   // FWD: running sum of squares
-    __device__ void item_begin(const Params&, int, int) { acc = 0.f; qacc = 0.0; }
-    __device__ void sub_begin(const Params& p, int item, int sub, int row) {
-      if (BWD) {
-        acc = p.g2[(long long)(sub / p.NT) * p.ncp + item * 128 + row];
-      } else if (sub % p.NT == 0) {
-        qacc = 0.0;
-      }
+    double qacc;
+    __device__ void item_begin(const Params&, int, int) { qacc = 0.0; }
+    __device__ void sub_begin(const Params& p, int, int sub, int) {
+      if (sub % p.NT == 0) qacc = 0.0;
     }
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
-      if (BWD) {
+      qacc += sumsq32(v);
+      if (p.store_t) {
         const int r = item * 128 + row;
         const int col0 = sub * BN + c0;     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float s[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s[j] = acc * v[g * 8 + j];
           uint4 pk[2];
-          split8<2>(s, pk);
+          split8<2>(&v[g * 8], pk);
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) store8(p.r.elem(pl, r, col0 + g * 8), pk[pl]);
+          for (int pl = 0; pl < 2; ++pl) store8(p.tp.elem(pl, r, col0 + g * 8), pk[pl]);
         }
-      } else {
-        qacc += sumsq32(v);
       }
     }
     __device__ void sub_end(const Params& p, int item, int sub, int row) {
-      if (!BWD && (sub % p.NT) == p.NT - 1) p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row] = qacc;
+      if ((sub % p.NT) == p.NT - 1) p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row] = qacc;
     }
     __device__ void item_end(const Params&, int, int) {}
   };
 };
 
 // ---------------------------------------------------------------------------------------------
-// G3:  dW[n, i] = sum_k sum_{j <= i} R[n, (k, j)] S_k[i, j]      (B = ST read MN-major)
+// G3:  dW[n, i] = sum_k g2[k, n] * sum_{j <= i} T_k[n, j] S_k[i, j]
+// One accumulation per (column tile, topic); the epilogue (8 warps: thread = row x column half) applies the
+// per-observation, per-topic scale in fp32 and keeps the running sum over topics in 128 registers, so neither a
+// rescaled copy of T nor a recompute of T is needed.  B = ST read MN-major.
 // ---------------------------------------------------------------------------------------------
 struct G3 {
+  static constexpr int EPI_WARPS = 8;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = false, B_MN = true;
   struct Params {
-    PlaneMat r, st;
-    float* dw;   // [ncp][Mp] fp32
-    int RT, MB, K, JT, Mp;
+    PlaneMat tp, st;
+    const float* g2;   // [K][ncp]
+    float* dw;         // [ncp][Mp] fp32
+    int RT, MB, K, JT, Mp, ncp;
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
-  __device__ static int num_subs(const Params& p, int) { return p.JT; }
-  __device__ static int k_iters(const Params& p, int, int sub) { return p.K * 4 * (sub + 1); }
+  __device__ static int num_subs(const Params& p, int) { return p.JT * p.K; }   // sub = it * K + k
+  __device__ static int k_iters(const Params& p, int, int sub) { return 4 * (sub / p.K + 1); }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
-    const int seg = 4 * (sub + 1);
-    const int k = kit / seg, jb = kit - k * seg;
-    return p.r.base + pl * p.r.plane_stride + p.r.block_off(item, k * p.MB + jb);
+    const int k = sub % p.K;
+    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(item, k * p.MB + kit);
   }
   __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
-    const int seg = 4 * (sub + 1);
-    const int k = kit / seg, jb = kit - k * seg;
-    return p.st.base + pl * p.st.plane_stride + p.st.block_off(k * 2 * p.JT + (jb >> 1), sub * 4 + pc) +
-           (jb & 1) * 4096;
+    const int it = sub / p.K, k = sub - it * p.K;
+    return p.st.base + pl * p.st.plane_stride + p.st.block_off(k * 2 * p.JT + (kit >> 1), it * 4 + pc) +
+           (kit & 1) * 4096;
   }
   struct Epi {
+    float acc[128];
+    float scale;
     __device__ void item_begin(const Params&, int, int) {}
-    __device__ void sub_begin(const Params&, int, int, int) {}
-    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
-      float4* dst = reinterpret_cast<float4*>(p.dw + (long long)(item * 128 + row) * p.Mp + sub * 256 + c0);
+    __device__ void sub_begin(const Params& p, int item, int sub, int row) {
+      const int k = sub % p.K;
+      if (k == 0) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      }
+      scale = p.g2[(long long)k * p.ncp + item * 128 + row];
     }
-    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void chunk(const Params&, int, int, int, int c0, const float (&v)[32]) {
+      // c0 is 0/32/64/96 (+128 for the upper-half warps); the unrolled switch keeps acc[] in registers
+      switch ((c0 & 127) >> 5) {
+        case 0:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(scale, v[j], acc[j]);
+          break;
+        case 1:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[32 + j] = fmaf(scale, v[j], acc[32 + j]);
+          break;
+        case 2:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[64 + j] = fmaf(scale, v[j], acc[64 + j]);
+          break;
+        default:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[96 + j] = fmaf(scale, v[j], acc[96 + j]);
+          break;
+      }
+      last_c0 = c0;
+    }
+    int last_c0;
+    __device__ void sub_end(const Params& p, int item, int sub, int row) {
+      if (sub % p.K != p.K - 1) return;
+      const int it = sub / p.K;
+      const int half = last_c0 >> 7;
+      float4* dst = reinterpret_cast<float4*>(p.dw + (long long)(item * 128 + row) * p.Mp + it * 256 + half * 128);
+#pragma unroll
+      for (int g = 0; g < 32; ++g) dst[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+    }
     __device__ void item_end(const Params&, int, int) {}
   };
 };
@@ -195,6 +221,7 @@ struct G3 {
 // G4:  dKxz[n, i] = sum_{m >= i} dWtot[n, m] Linv[m, i]          (B = LINV read MN-major)
 // ---------------------------------------------------------------------------------------------
 struct G4 {
+  static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = true;
@@ -230,6 +257,7 @@ struct G4 {
 // G5:  C5[a, b] += sum_n dWtot[n, a] W[n, b]        (both operands MN-major; split over n; fp64 atomics)
 // ---------------------------------------------------------------------------------------------
 struct G5 {
+  static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = true, B_MN = true;
@@ -269,15 +297,16 @@ struct G5 {
 };
 
 // ---------------------------------------------------------------------------------------------
-// G6:  dS_k[i, j] += sum_n W[n, i] R[n, (k, j)]   for j <= i   (both MN-major; tiles on/below the diagonal)
+// G6:  dS_k[i, j] += sum_n WG[n, (k, i)] T[n, (k, j)]   for j <= i   (both MN-major; tiles on/below the diagonal)
 // ---------------------------------------------------------------------------------------------
 struct G6 {
+  static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = true, B_MN = true;
   static constexpr int MAX_TILES = 512;
   struct Params {
-    PlaneMat w, r;
+    PlaneMat wg, tp;
     float* ds;   // [K][M][M] fp32, unpadded gradient accumulator
     int RT, MB, K, M, ntile, splits, nb_per_split;
     unsigned char ta[MAX_TILES], tb[MAX_TILES];
@@ -289,14 +318,14 @@ struct G6 {
     return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
   }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, t = rem % p.ntile;
+    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
     const int nb = s * p.nb_per_split + kit;
-    return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, p.ta[t] * 2 + pc) + (nb & 1) * 4096;
+    return p.wg.base + pl * p.wg.plane_stride + p.wg.block_off(nb >> 1, k * p.MB + p.ta[t] * 2 + pc) + (nb & 1) * 4096;
   }
   __device__ static const bf16* b_src(const Params& p, int item, int, int kit, int pl, int pc) {
     const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
     const int nb = s * p.nb_per_split + kit;
-    return p.r.base + pl * p.r.plane_stride + p.r.block_off(nb >> 1, k * p.MB + p.tb[t] * 4 + pc) + (nb & 1) * 4096;
+    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(nb >> 1, k * p.MB + p.tb[t] * 4 + pc) + (nb & 1) * 4096;
   }
   struct Epi {
     __device__ void item_begin(const Params&, int, int) {}

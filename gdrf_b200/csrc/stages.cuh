@@ -523,6 +523,38 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// WG[n, (k, m)] = g2[k, n] * W[n, m]  (2 bf16 planes): the per-topic row-weighted copies of W that turn
+// dS_k = W^T diag(g2_k) T_k into a plain contraction.  grid (MB, RT), 256 threads; W's block is rebuilt once
+// and rescaled K times.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __restrict__ g2, int K, int MB, int ncp,
+                                                 PlaneMat wg) {
+  const int cb = blockIdx.x, rt = blockIdx.y;
+#pragma unroll 1
+  for (int wv = 0; wv < 4; ++wv) {
+    const int idx = threadIdx.x + 256 * wv;
+    const int r = idx & 127, g = idx >> 7;
+    const int n = rt * 128 + r;
+    uint4 pk[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, n, cb * 64 + g * 8));
+    float wj[8];
+    join8<3>(pk, wj);
+    for (int k = 0; k < K; ++k) {
+      const float sc = g2[(long long)k * ncp + n];
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = sc * wj[j];
+      uint4 out[2];
+      split8<2>(v, out);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl)
+        *reinterpret_cast<uint4*>(wg.elem(pl, n, (k * MB + cb) * 64 + g * 8)) = out[pl];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 3 planes
 // grid (MB, RT), 256 threads.
 // ---------------------------------------------------------------------------------------------

@@ -123,7 +123,7 @@ int gdrf_perplexity_terms(const gdrf_shape* shape, const gdrf_inputs* in, const 
                           gdrf_stream_t stream);
 
 /* Instrumentation for bench.py: kernels launched by this process so far; CUDA-event timing of the six
- * contractions (ms[7] / launches[7] in the order G1, G2-forward, G2-backward, G3, G4, G5, G6, summed since
+ * contractions (ms[7] / launches[7] in the order G1, G2, k_scale_w, G3, G4, G5, G6, summed since
  * the previous read; the read synchronises the device).  Off by default.                                   */
 long long gdrf_launch_count(void);
 int gdrf_profile_enable(int on);
