@@ -36,8 +36,7 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
   const float var = hp.variance[0];
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    const int idx = threadIdx.x + 256 * w;
-    const int r = idx & 127, g = idx >> 7;
+    const int r = w * 32 + (threadIdx.x >> 3), g = threadIdx.x & 7;   // 8 lanes per 128-byte row
     const int n = rt * 128 + r;
     float x[MAX_D];
     if (n < nc)
@@ -530,16 +529,17 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
 __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __restrict__ g2, int K, int MB, int ncp,
                                                  PlaneMat wg) {
   const int cb = blockIdx.x, rt = blockIdx.y;
+  const int g = threadIdx.x & 7;            // 8 lanes cover the eight 16-byte chunks of one 128-byte row
 #pragma unroll 1
-  for (int wv = 0; wv < 4; ++wv) {
-    const int idx = threadIdx.x + 256 * wv;
-    const int r = idx & 127, g = idx >> 7;
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 32 + (threadIdx.x >> 3);
     const int n = rt * 128 + r;
     uint4 pk[3];
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, n, cb * 64 + g * 8));
     float wj[8];
     join8<3>(pk, wj);
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const float sc = g2[(long long)k * ncp + n];
       float v[8];
@@ -577,8 +577,7 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
   __syncthreads();
 #pragma unroll 1
   for (int wv = 0; wv < 4; ++wv) {
-    const int idx = threadIdx.x + 256 * wv;
-    const int r = idx & 127, g = idx >> 7;
+    const int r = wv * 32 + (threadIdx.x >> 3), g = threadIdx.x & 7;   // 8 lanes per 128-byte row
     const int n = rt * 128 + r;
     const int col = cb * 64 + g * 8;
     uint4 pk[3];
