@@ -249,6 +249,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
+    CU(cudaMemsetAsync(at<double>(ws, p.q), 0, sizeof(double) * (size_t)p.K * p.ncp, st));
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
       G2<0>::Params g{};
       g.w = w; g.st = stm; g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);

@@ -91,7 +91,7 @@ struct G1 {
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 struct G2 {
-  static constexpr int EPI_WARPS = 4;
+  static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: the T store must keep up with short tiles
   static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
   static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
@@ -99,7 +99,8 @@ struct G2 {
   static constexpr int PCS = BN / 128;    // 128-row pieces of ST per tile
   struct Params {
     PlaneMat w, st, tp;
-    double* q;         // [K][ncp]  (fp64: q feeds mu = f_loc + f_var * eps)
+    double* q;         // [K][ncp]  (fp64: q feeds mu = f_loc + f_var * eps); zeroed by the caller, the two column
+                       //           halves of a row add their partial sums
     int store_t;       // write TP (gradient pass)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
   };
@@ -135,7 +136,7 @@ struct G2 {
       }
     }
     __device__ void sub_end(const Params& p, int item, int sub, int row) {
-      if ((sub % p.NT) == p.NT - 1) p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row] = qacc;
+      if ((sub % p.NT) == p.NT - 1) atomicAdd(&p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row], qacc);
     }
     __device__ void item_end(const Params&, int, int) {}
   };
