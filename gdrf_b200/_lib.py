@@ -22,7 +22,6 @@ FLAG_FWD_BF16 = 16
 FLAG_SINGLE_CTA = 32
 FLAG_CONTINUE = 64
 FLAG_PARTIAL = 128
-FLAG_PIPELINE2 = 256
 FLAG_REF_G = {i: 1 << (7 + i) for i in range(1, 7)}
 FLAG_REF_ALL = 0x3F << 8
 
@@ -39,7 +38,7 @@ class Inputs(ctypes.Structure):
 
 
 class Outputs(ctypes.Structure):
-    _fields_ = [("terms", c_void_p), ("grad", c_void_p), ("aux_stream", c_void_p)]
+    _fields_ = [("terms", c_void_p), ("grad", c_void_p)]
 
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",

@@ -39,14 +39,6 @@ constexpr int PROF_MAX = 4096;
 ProfRec g_prof[PROF_MAX];
 int g_prof_n = 0;
 std::vector<cudaEvent_t> g_event_pool;
-cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;   // fork/join of the two-stream chunk pipeline
-
-cudaError_t fork_join_events() {
-  if (g_ev_fork) return cudaSuccess;
-  cudaError_t e = cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming);
-  if (e != cudaSuccess) return e;
-  return cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
-}
 
 cudaEvent_t prof_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
@@ -77,7 +69,6 @@ struct Plan {
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
   size_t wsq, srow, arow, cnt, gv0, floc, q, fvar, theta, g_loc, g2, g1;
   size_t total;
-  size_t chunk_begin, chunk_bytes;   // per-chunk scratch region (duplicated when two chunks are in flight)
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
 };
 
@@ -130,7 +121,6 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
   p.st16_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
-  p.chunk_begin = off;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w16_pl = bump(off, sizeof(bf16) * 2 * nm);
@@ -150,19 +140,8 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.g_loc = bump(off, sizeof(float) * kn);
   p.g2 = bump(off, sizeof(float) * kn);
   p.g1 = bump(off, sizeof(float) * kn);
-  p.chunk_bytes = off - p.chunk_begin;
-  if (s->flags & GDRF_FLAG_PIPELINE2) off += p.chunk_bytes;
   p.total = off;
   return 0;
-}
-
-// the plan addressing the second per-chunk scratch set
-Plan second_set(const Plan& p) {
-  Plan q = p;
-  size_t* f[] = {&q.kxz_pl, &q.w_pl, &q.w16_pl, &q.tp_pl, &q.wg_pl, &q.dwf, &q.wsq, &q.srow, &q.arow, &q.cnt, &q.gv0,
-                 &q.floc, &q.q, &q.fvar, &q.theta, &q.g_loc, &q.g2, &q.g1};
-  for (size_t* x : f) *x += p.chunk_bytes;
-  return q;
 }
 
 template <typename T>
@@ -362,93 +341,6 @@ __global__ void __launch_bounds__(256) k_perplexity(int N, int K, int V, const f
 
 }  // namespace
 
-// everything one chunk of observations contributes: forward contractions, per-observation stages, backward
-int run_chunk(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_outputs* out, const Plan& p, void* ws,
-              long long n0, int nc, bool want_grad, G6::Params g6, bool atomic_ds, int sms, cudaStream_t st) {
-  const Hyper hp = make_hyper(s, in);
-  const int K = p.K, M = p.M, Mp = p.Mp;
-  const int RT = (nc + 127) / 128;
-  PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
-  PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
-  PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
-  PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
-  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)K * Mp, Mp);
-  PlaneMat tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)K * Mp);
-  PlaneMat wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)K * Mp);
-  float* dwf = at<float>(ws, p.dwf);
-  double* acc = at<double>(ws, p.acc);
-  {
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
-    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
-                                      at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
-                                      at<float>(ws, p.phisum), at<float>(ws, p.fvar),
-                                      at<float>(ws, p.theta), at<float>(ws, p.srow), acc);
-    LAUNCH_CHECK();
-    if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
-    k_obs_finalize<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta),
-                                       at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),
-                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq), in->eps, hp,
-                                       at<float>(ws, p.phisum), at<float>(ws, p.g_loc), at<float>(ws, p.g2),
-                                       at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
-    LAUNCH_CHECK();
-    if (!want_grad) return 0;
-    {
-      ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
-      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm);
-      LAUNCH_CHECK();
-    }
-    {
-      G3::Params g{};
-      g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
-      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
-      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
-    }
-    {
-      const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
-      CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
-                                                       in->u_loc, K, M, (int)p.ncp, dwt);
-      LAUNCH_CHECK();
-    }
-    if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
-    {
-      g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
-      const int base = K * g6.ntile;
-      int splits = base >= sms ? 1 : (sms + base - 1) / base;
-      const int NBt = 2 * RT;
-      if (splits > NBt) splits = NBt;
-      int per = (NBt + splits - 1) / splits;
-      splits = (NBt + per - 1) / per;
-      g6.splits = splits; g6.nb_per_split = per; g6.atomic = (splits > 1 || atomic_ds) ? 1 : 0;
-      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
-    }
-    {
-      G4::Params g{};
-      g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
-      { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
-    }
-    {
-      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
-      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
-          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
-      LAUNCH_CHECK();
-    }
-    {
-      G5::Params g{};
-      g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
-      const int base = p.MT * p.MT;
-      int splits = base >= 2 * sms ? 1 : (2 * sms + base - 1) / base;
-      const int NBt = 2 * RT;
-      if (splits > NBt) splits = NBt;
-      int per = (NBt + splits - 1) / splits;
-      splits = (NBt + per - 1) / per;
-      g.splits = splits; g.nb_per_split = per;
-      { ProfScope ps(PK_G5, st); ++g_launches; CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st)); }
-    }
-  }
-  return 0;
-}
-
 extern "C" {
 
 const char* gdrf_last_error(void) { return g_err; }
@@ -573,6 +465,14 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     if (want_grad) CU(cudaMemsetAsync(out->grad, 0, sizeof(float) * (size_t)K * M * M, st));
   }
 
+  PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
+  PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
+  PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
+  PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
+  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)K * Mp, Mp);
+  PlaneMat tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)K * Mp);
+  PlaneMat wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)K * Mp);
+  float* dwf = at<float>(ws, p.dwf);
   double* acc = at<double>(ws, p.acc);
 
   if (!cont) {
@@ -597,28 +497,78 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     g6.ntile = nt;
   }
 
-  {
-    // chunks alternate between the caller's stream and (when given) the auxiliary stream, each with its own
-    // scratch set, so the HBM-bound per-observation stages of one chunk overlap the contractions of the other
-    cudaStream_t aux = (cudaStream_t)out->aux_stream;
-    const bool two = aux != nullptr && (s->flags & GDRF_FLAG_PIPELINE2) != 0 && s->n_local > p.chunk_rows;
-    const Plan p2 = (s->flags & GDRF_FLAG_PIPELINE2) ? second_set(p) : p;
-    if (two) {
-      CU(fork_join_events());
-      CU(cudaEventRecord(g_ev_fork, st));
-      CU(cudaStreamWaitEvent(aux, g_ev_fork, 0));
+  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
+    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
+    const int RT = (nc + 127) / 128;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
+    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
+                                      at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
+                                      at<float>(ws, p.phisum), at<float>(ws, p.fvar),
+                                      at<float>(ws, p.theta), at<float>(ws, p.srow), acc);
+    LAUNCH_CHECK();
+    if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
+    k_obs_finalize<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta),
+                                       at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),
+                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq), in->eps, hp,
+                                       at<float>(ws, p.phisum), at<float>(ws, p.g_loc), at<float>(ws, p.g2),
+                                       at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
+    LAUNCH_CHECK();
+    if (!want_grad) continue;
+    {
+      ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
+      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm);
+      LAUNCH_CHECK();
     }
-    int ci = 0;
-    for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows, ++ci) {
-      const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
-      const bool odd = two && (ci & 1);
-      if (int e = run_chunk(s, in, out, odd ? p2 : p, ws, n0, nc, want_grad, g6, two, sms, odd ? aux : st)) return e;
+    {
+      G3::Params g{};
+      g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
+      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
+      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
-    if (two) {
-      CU(cudaEventRecord(g_ev_join, aux));
-      CU(cudaStreamWaitEvent(st, g_ev_join, 0));
+    {
+      const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
+      CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
+                                                       in->u_loc, K, M, (int)p.ncp, dwt);
+      LAUNCH_CHECK();
+    }
+    if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
+    {
+      g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
+      const int base = K * g6.ntile;
+      int splits = base >= sms ? 1 : (sms + base - 1) / base;
+      const int NBt = 2 * RT;
+      if (splits > NBt) splits = NBt;
+      int per = (NBt + splits - 1) / splits;
+      splits = (NBt + per - 1) / per;
+      g6.splits = splits; g6.nb_per_split = per;
+      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+    }
+    {
+      G4::Params g{};
+      g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+      { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
+    }
+    {
+      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
+      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
+          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
+      LAUNCH_CHECK();
+    }
+    {
+      G5::Params g{};
+      g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+      const int base = p.MT * p.MT;
+      int splits = base >= 2 * sms ? 1 : (2 * sms + base - 1) / base;
+      const int NBt = 2 * RT;
+      if (splits > NBt) splits = NBt;
+      int per = (NBt + splits - 1) / splits;
+      splits = (NBt + per - 1) / per;
+      g.splits = splits; g.nb_per_split = per;
+      { ProfScope ps(PK_G5, st); ++g_launches; CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st)); }
     }
   }
+
   if (partial) return 0;
   if (want_grad) {
     // Cholesky adjoint (Murray 2016; torch cholesky_backward):  G_L = -tril(L^-T C5),

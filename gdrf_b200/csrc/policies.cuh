@@ -309,7 +309,7 @@ struct G6 {
   struct Params {
     PlaneMat wg, tp;
     float* ds;   // [K][M][M] fp32, unpadded gradient accumulator
-    int RT, MB, K, M, ntile, splits, nb_per_split, atomic;
+    int RT, MB, K, M, ntile, splits, nb_per_split;
     unsigned char ta[MAX_TILES], tb[MAX_TILES];
   };
   __device__ static int num_items(const Params& p) { return p.K * p.ntile * p.splits; }
@@ -337,7 +337,7 @@ struct G6 {
       const int j0 = p.tb[t] * 256 + c0;
       if (i >= p.M) return;
       float* dst = p.ds + ((long long)k * p.M + i) * p.M;
-      if (!p.atomic) {
+      if (p.splits == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j0 + j <= i) dst[j0 + j] += v[j];

@@ -20,15 +20,6 @@ import torch
 from . import _lib
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
-_AUX_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-
-
-def _aux_stream(device: torch.device) -> "torch.cuda.Stream":
-    """Second stream of the two-chunk pipeline (GDRF_FLAG_PIPELINE2), one per device."""
-    key = device.index or 0
-    if key not in _AUX_STREAMS:
-        _AUX_STREAMS[key] = torch.cuda.Stream(device)
-    return _AUX_STREAMS[key]
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -125,8 +116,7 @@ class _Call:
             if grad is None:
                 grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
         self.shape.flags = flags
-        aux = _aux_stream(self.device).cuda_stream if (flags & _lib.FLAG_PIPELINE2) else None
-        out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None, aux_stream=aux)
+        out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None)
         _lib.check(lib.gdrf_elbo_step(ctypes.byref(self.shape), ctypes.byref(self.inputs), ctypes.byref(out),
                                       self.workspace.data_ptr(), self.ws_bytes, self.stream))
         return terms, grad

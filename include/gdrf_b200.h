@@ -40,8 +40,6 @@ enum {
                                      (second and later sub-shards of one step streamed from host memory)       */
   GDRF_FLAG_PARTIAL = 128,        /* gdrf_elbo_step: more sub-shards follow; skip the per-step epilogue (Cholesky
                                      adjoint, prior, gradient assembly, terms)                                 */
-  GDRF_FLAG_PIPELINE2 = 256,      /* size the workspace for two chunks in flight; gdrf_elbo_step then alternates
-                                     chunks between `stream` and out->aux_stream (when non-NULL)              */
   GDRF_FLAG_SINGLE_CTA = 32,      /* run the four large contractions on single CTAs (cta_group::1) instead of
                                      CTA pairs (cta_group::2); same results, used for A/B measurement         */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
@@ -87,8 +85,6 @@ typedef struct gdrf_inputs {
 typedef struct gdrf_outputs {
   double* terms; /* [4]                      */
   float* grad;   /* [gdrf_grad_elems(shape)] or NULL when GDRF_FLAG_WANT_GRAD is clear                        */
-  gdrf_stream_t aux_stream; /* optional second stream for GDRF_FLAG_PIPELINE2 (NULL: everything on `stream`);
-                               the call returns with `stream` ordered after all work on it                   */
 } gdrf_outputs;
 
 /* Sizes.  HOST out-pointers. */
