@@ -180,7 +180,7 @@ int check_device() {
 template <int KPW, int VJ>
 int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st) {
   const int VC = VJ * 32;
-  const size_t smem = sizeof(float) * ((size_t)p.K * (VC + 1) + (size_t)LK_TN * VC + (size_t)LK_TN * (p.K + 1) + LK_TN);
+  const size_t smem = sizeof(float) * lk_smem_floats(p.K, VC);
   CU(cudaFuncSetAttribute(k_likelihood<KPW, VJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntiles = (nc + LK_TN - 1) / LK_TN;
   const int grid = ntiles < sms ? ntiles : sms;
@@ -526,7 +526,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
-      const size_t smem = sizeof(float) * (size_t)K * (64 + 128);
+      const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
       CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
                                                        in->u_loc, K, M, (int)p.ncp, dwt);

@@ -23,13 +23,13 @@ enum { ACC_LP_MU = 0, ACC_LQ = 1, ACC_LL = 2, ACC_LP_PHI = 3, ACC_DNOISE = 4, AC
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs, int nc, const float* __restrict__ Z,
                                                     int M, Hyper hp, PlaneMat kxz) {
-  __shared__ float zs[64][MAX_D];
+  __shared__ float zs[MAX_D][64 + 4];      // [d][c], row padded: column groups g*8 land in different banks
   __shared__ float inv_ls[MAX_D];
   const int cb = blockIdx.x, rt = blockIdx.y, D = hp.D;
   for (int t = threadIdx.x; t < 64 * D; t += blockDim.x) {
     const int c = t / D, d = t - c * D;
     const int col = cb * 64 + c;
-    zs[c][d] = (col < M) ? Z[col * D + d] : 0.f;
+    zs[d][c + (c >> 5) * 4] = (col < M) ? Z[col * D + d] : 0.f;
   }
   if (threadIdx.x < D) inv_ls[threadIdx.x] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : threadIdx.x];
   __syncthreads();
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
       if (n < nc && cb * 64 + c < M) {
         float r2 = 0.f;
         for (int d = 0; d < D; ++d) {
-          const float t = (x[d] - zs[c][d]) * inv_ls[d];
+          const float t = (x[d] - zs[d][c + (c >> 5) * 4]) * inv_ls[d];
           r2 = fmaf(t, t, r2);
         }
         float k, dk;
@@ -256,6 +256,14 @@ __global__ void __launch_bounds__(128) k_obs_prepare(int nc, int ncp, int K, lon
 // ---------------------------------------------------------------------------------------------
 constexpr int LK_THREADS = 512;
 constexpr int LK_TN = 32;
+constexpr int LK_TS = LK_TN + 4;   // row stride of the observation-minor tiles (float4 access, conflict-free)
+
+__host__ __device__ inline size_t lk_round4(size_t x) { return (x + 3) & ~(size_t)3; }
+// shared-memory floats: phi chunk [K][VC+1] | r tile [VC][TS] | theta tile [K][TS] | G1 tile [TN][K+1] | 4 x [TN]
+__host__ __device__ inline size_t lk_smem_floats(int K, int VC) {
+  return lk_round4((size_t)K * (VC + 1)) + (size_t)VC * LK_TS + (size_t)K * LK_TS + lk_round4((size_t)LK_TN * (K + 1)) +
+         4 * LK_TN;
+}
 
 template <int KPW, int VJ>
 __global__ void __launch_bounds__(LK_THREADS, 1)
@@ -264,13 +272,19 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
                  float* __restrict__ arow, float* __restrict__ cnt, double* __restrict__ dphi_acc /*[K][V]*/,
                  double* __restrict__ acc) {
   constexpr int VC = VJ * 32;
-  extern __shared__ float lk_smem[];
-  float* phis = lk_smem;                     // [K][VC + 1]
-  float* rt = phis + K * (VC + 1);           // [TN][VC]
-  float* th = rt + LK_TN * VC;               // [TN][K + 1]
-  float* sinv = th + LK_TN * (K + 1);        // [TN]
+  extern __shared__ __align__(16) float lk_smem[];
+  float* phis = lk_smem;                                    // [K][VC + 1]
+  float* rt = phis + lk_round4((size_t)K * (VC + 1));       // [VC][TS]   r[v][obs]
+  float* th = rt + VC * LK_TS;                              // [K][TS]    theta[k][obs]
+  float* g1s = th + K * LK_TS;                              // [TN][K + 1]
+  float* sinv = g1s + lk_round4((size_t)LK_TN * (K + 1));   // [TN]
+  float* sh_ll = sinv + LK_TN;                              // [TN] per-observation partial sums of this V chunk
+  float* sh_a = sh_ll + LK_TN;
+  float* sh_c = sh_a + LK_TN;
   __shared__ double scratch[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp & 7, vh = warp >> 3;                 // 4 observations x half of the chunk's columns per warp
+  const int i0 = grp * 4;
   const int ntiles = (nc + LK_TN - 1) / LK_TN;
   const float EPS32 = 1.1920928955078125e-07f;
   double ll_local = 0.0;
@@ -292,86 +306,129 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
       __syncthreads();
       for (int t = threadIdx.x; t < LK_TN * K; t += LK_THREADS) {
         const int k = t / LK_TN, i = t - k * LK_TN;
-        th[i * (K + 1) + k] = (nb + i < nc) ? theta[(long long)k * ncp + nb + i] : 0.f;
+        th[k * LK_TS + i] = (nb + i < nc) ? theta[(long long)k * ncp + nb + i] : 0.f;
       }
-      if (threadIdx.x < LK_TN) sinv[threadIdx.x] = (nb + threadIdx.x < nc) ? 1.f / srow[nb + threadIdx.x] : 0.f;
+      for (int t = threadIdx.x; t < LK_TN * (K + 1); t += LK_THREADS) g1s[t] = 0.f;
+      if (threadIdx.x < LK_TN) {
+        sinv[threadIdx.x] = (nb + threadIdx.x < nc) ? 1.f / srow[nb + threadIdx.x] : 0.f;
+        sh_ll[threadIdx.x] = 0.f;
+        sh_a[threadIdx.x] = 0.f;
+        sh_c[threadIdx.x] = 0.f;
+      }
       __syncthreads();
-      // ---- (b) p, log-likelihood, r ----
+      // ---- (b) p = theta phi for 4 observations at once, log-likelihood, r = w a / p ----
+      {
+        float llp[4] = {0.f, 0.f, 0.f, 0.f}, ap[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int i = warp * 2 + h;
-        const int n = nb + i;
-        float llp = 0.f, ap = 0.f, cp = 0.f;
-        const float* thi = th + i * (K + 1);
-        const float si = sinv[i];
-#pragma unroll 1
-        for (int j = 0; j < VJ; ++j) {
+        for (int j = vh * (VJ / 2); j < (vh + 1) * (VJ / 2); ++j) {
           const int v = lane + 32 * j;
-          float r = 0.f;
-          if (n < nc && v0 + v < V) {
-            const int c = ws[(long long)n * V + v0 + v];
-            if (c != 0) {
-              float p = 0.f;
-              for (int k = 0; k < K; ++k) p = fmaf(thi[k], phis[k * (VC + 1) + v], p);
-              const float ph = p * si;
-              const float pc = fminf(fmaxf(ph, EPS32), 1.f - EPS32);
-              const float cf = (float)c;
-              llp += cf * __logf(pc) - (c > 1 ? lgammaf(cf + 1.f) : 0.f);
-              cp += cf;
-              if (ph >= EPS32 && ph <= 1.f - EPS32) {
-                ap += cf;
-                r = cf / p;
+          int c[4];
+          bool any = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = nb + i0 + q;
+            c[q] = (n < nc && v0 + v < V) ? ws[(long long)n * V + v0 + v] : 0;
+            any |= (c[q] != 0);
+          }
+          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (any) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+            for (int k = 0; k < K; ++k) {
+              const float f = phis[k * (VC + 1) + v];
+              const float4 t4 = *reinterpret_cast<const float4*>(th + k * LK_TS + i0);
+              p0 = fmaf(t4.x, f, p0);
+              p1 = fmaf(t4.y, f, p1);
+              p2 = fmaf(t4.z, f, p2);
+              p3 = fmaf(t4.w, f, p3);
+            }
+            const float pq[4] = {p0, p1, p2, p3};
+            float rq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              rq[q] = 0.f;
+              if (c[q] != 0) {
+                const float ph = pq[q] * sinv[i0 + q];
+                const float pc = fminf(fmaxf(ph, EPS32), 1.f - EPS32);
+                const float cf = (float)c[q];
+                llp[q] += cf * __logf(pc) - (c[q] > 1 ? lgammaf(cf + 1.f) : 0.f);
+                cp[q] += cf;
+                if (ph >= EPS32 && ph <= 1.f - EPS32) {
+                  ap[q] += cf;
+                  rq[q] = cf / pq[q];
+                }
               }
             }
+            r4 = make_float4(rq[0], rq[1], rq[2], rq[3]);
           }
-          rt[i * VC + v] = r;
+          *reinterpret_cast<float4*>(rt + v * LK_TS + i0) = r4;
         }
-        llp = warp_sum(llp);
-        ap = warp_sum(ap);
-        cp = warp_sum(cp);
-        if (lane == 0 && n < nc) {
-          ll_local += (double)llp;
-          if (v0 == 0) {
-            arow[n] = ap;
-            cnt[n] = cp;
-          } else {
-            arow[n] += ap;
-            cnt[n] += cp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = warp_sum(llp[q]), b = warp_sum(ap[q]), d = warp_sum(cp[q]);
+          if (lane == 0) {
+            atomicAdd(&sh_ll[i0 + q], a);
+            atomicAdd(&sh_a[i0 + q], b);
+            atomicAdd(&sh_c[i0 + q], d);
           }
         }
       }
       __syncthreads();
-      // ---- (c) G1[n][k] = sum_v phi[k][v] r[n][v] : lanes = k, warps = observation pairs ----
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int i = warp * 2 + h;
-        const int n = nb + i;
-        for (int k = lane; k < K; k += 32) {
-          float a = 0.f;
-          const float* pk = phis + k * (VC + 1);
-          const float* ri = rt + i * VC;
-#pragma unroll 8
-          for (int v = 0; v < VC; ++v) a = fmaf(pk[v], ri[v], a);
-          if (n < nc) {
-            if (v0 == 0) g1[(long long)n * K + k] = a;
-            else g1[(long long)n * K + k] += a;
+      if (threadIdx.x < LK_TN && nb + threadIdx.x < nc) {
+        const int n = nb + threadIdx.x;
+        ll_local += (double)sh_ll[threadIdx.x];
+        if (v0 == 0) {
+          arow[n] = sh_a[threadIdx.x];
+          cnt[n] = sh_c[threadIdx.x];
+        } else {
+          arow[n] += sh_a[threadIdx.x];
+          cnt[n] += sh_c[threadIdx.x];
+        }
+      }
+      // ---- (c) G1[n][k] += sum_v phi[k][v] r[n][v] : lanes = k, warp = (4 observations, half of the columns) ----
+      for (int k = lane; k < K; k += 32) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* pk = phis + k * (VC + 1);
+#pragma unroll 4
+        for (int v = vh * (VC / 2); v < (vh + 1) * (VC / 2); ++v) {
+          const float f = pk[v];
+          const float4 r4 = *reinterpret_cast<const float4*>(rt + v * LK_TS + i0);
+          a0 = fmaf(f, r4.x, a0);
+          a1 = fmaf(f, r4.y, a1);
+          a2 = fmaf(f, r4.z, a2);
+          a3 = fmaf(f, r4.w, a3);
+        }
+        atomicAdd(&g1s[(i0 + 0) * (K + 1) + k], a0);
+        atomicAdd(&g1s[(i0 + 1) * (K + 1) + k], a1);
+        atomicAdd(&g1s[(i0 + 2) * (K + 1) + k], a2);
+        atomicAdd(&g1s[(i0 + 3) * (K + 1) + k], a3);
+      }
+      // ---- (d) dphi[k][v] += sum_n theta[n][k] r[n][v] : warps = k groups, lanes = v, 4 observations per load ----
+      {
+        const int kbase = warp * KPW;
+#pragma unroll 2
+        for (int n0 = 0; n0 < LK_TN; n0 += 4) {
+          float4 t4[KPW];
+#pragma unroll
+          for (int a = 0; a < KPW; ++a)
+            t4[a] = (kbase + a < K) ? *reinterpret_cast<const float4*>(th + (kbase + a) * LK_TS + n0)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < VJ; ++j) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rt + (lane + 32 * j) * LK_TS + n0);
+#pragma unroll
+            for (int a = 0; a < KPW; ++a)
+              dacc[a][j] += t4[a].x * r4.x + t4[a].y * r4.y + t4[a].z * r4.z + t4[a].w * r4.w;
           }
         }
       }
-      // ---- (d) dphi[k][v] += sum_n theta[n][k] r[n][v] : warps = k groups, lanes = v ----
-      {
-        const int kbase = warp * KPW;
-#pragma unroll 4
-        for (int i = 0; i < LK_TN; ++i) {
-          float rv[VJ];
-#pragma unroll
-          for (int j = 0; j < VJ; ++j) rv[j] = rt[i * VC + lane + 32 * j];
-#pragma unroll
-          for (int a = 0; a < KPW; ++a) {
-            const float t = (kbase + a < K) ? th[i * (K + 1) + kbase + a] : 0.f;
-#pragma unroll
-            for (int j = 0; j < VJ; ++j) dacc[a][j] = fmaf(t, rv[j], dacc[a][j]);
-          }
+      __syncthreads();
+      for (int t = threadIdx.x; t < LK_TN * K; t += LK_THREADS) {
+        const int i = t / K, k = t - i * K;
+        const int n = nb + i;
+        if (n < nc) {
+          const float a = g1s[i * (K + 1) + k];
+          if (v0 == 0) g1[(long long)n * K + k] = a;
+          else g1[(long long)n * K + k] += a;
         }
       }
     }
@@ -562,13 +619,13 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
                                                      const float* __restrict__ g_loc, const float* __restrict__ gv0,
                                                      const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt) {
   extern __shared__ float dwf_smem[];
-  float* us = dwf_smem;            // [K][64]
-  float* gs = us + K * 64;         // [K][128]
+  float* us = dwf_smem;            // [K][72]: 64 columns, the upper 32 shifted by 4 words (bank spread)
+  float* gs = us + K * 72;         // [K][128]
   const int cb = blockIdx.x, rt = blockIdx.y;
   for (int t = threadIdx.x; t < K * 64; t += 256) {
     const int k = t >> 6, c = t & 63;
     const int m = cb * 64 + c;
-    us[t] = (m < M) ? u[(long long)k * M + m] : 0.f;
+    us[k * 72 + c + (c >> 5) * 4] = (m < M) ? u[(long long)k * M + m] : 0.f;
   }
   for (int t = threadIdx.x; t < K * 128; t += 256) {
     const int k = t >> 7, r = t & 127;
@@ -594,7 +651,7 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     for (int k = 0; k < K; ++k) {
       const float gk = gs[k * 128 + r];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(gk, us[k * 64 + g * 8 + j], v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(gk, us[k * 72 + g * 8 + (g >> 2) * 4 + j], v[j]);
     }
     uint4 out[3];
     split8<3>(v, out);
