@@ -21,6 +21,21 @@ namespace gdrf {
 
 __device__ __forceinline__ void store8(bf16* dst, const uint4& pk) { *reinterpret_cast<uint4*>(dst) = pk; }
 
+// Two adjacent 8-element packets (columns col .. col+15, col a multiple of 16) of row r as ONE 32-byte store.
+// The 128-byte swizzle only permutes 16-byte chunks with XOR (row & 7), so the two chunks of a 32-byte sector stay
+// in the same sector (possibly swapped): a full-sector store needs no read-for-fill in L2 (a pair of 16-byte stores
+// cost a DRAM read per written sector -- measured 2.3 GB per launch on the T store).
+__device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int col, const uint4& lo, const uint4& hi) {
+  bf16* p = m.elem(plane, r, col);                       // address of the chunk holding columns col .. col+7
+  const bool swapped = (r & 1) != 0;                     // chunk index parity flips with row parity
+  bf16* sector = swapped ? p - 8 : p;
+  const uint4& a = swapped ? hi : lo;
+  const uint4& b = swapped ? lo : hi;
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // sum of 32 squares: four independent fp32 partial sums of 8 terms, combined in fp64
 __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -63,16 +78,18 @@ struct G1 {
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
       const int r = item * 128 + row;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 pk[3];
-        split8<3>(&v[g * 8], pk);
+      for (int g = 0; g < 4; g += 2) {
+        uint4 pa[3], pb[3];
+        split8<3>(&v[g * 8], pa);
+        split8<3>(&v[g * 8 + 8], pb);
         const int col = sub * 128 + c0 + g * 8;
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) store8(p.w.elem(pl, r, col), pk[pl]);
-        uint4 hk[2];
-        split8h<2>(&v[g * 8], hk);
+        for (int pl = 0; pl < 3; ++pl) store16(p.w, pl, r, col, pa[pl], pb[pl]);
+        uint4 ha[2], hb[2];
+        split8h<2>(&v[g * 8], ha);
+        split8h<2>(&v[g * 8 + 8], hb);
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) store8(p.w16.elem(pl, r, col), hk[pl]);
+        for (int pl = 0; pl < 2; ++pl) store16(p.w16, pl, r, col, ha[pl], hb[pl]);
       }
       acc += sumsq32(v);
     }
@@ -127,11 +144,12 @@ struct G2 {
         const int r = item * 128 + row;
         const int col0 = sub * BN + c0;     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk[2];
-          split8<2>(&v[g * 8], pk);
+        for (int g = 0; g < 4; g += 2) {
+          uint4 pa[2], pb[2];
+          split8<2>(&v[g * 8], pa);
+          split8<2>(&v[g * 8 + 8], pb);
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) store8(p.tp.elem(pl, r, col0 + g * 8), pk[pl]);
+          for (int pl = 0; pl < 2; ++pl) store16(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
         }
       }
     }
