@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgdrf_b200.so")
 
-KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2}
+KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3}
 
 FLAG_WANT_GRAD = 1
 FLAG_INCLUDE_PRIOR = 2

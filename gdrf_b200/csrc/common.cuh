@@ -155,11 +155,11 @@ __host__ __device__ __forceinline__ long long round_up_ll(long long a, long long
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // kernel ids shared with the host API (include/gdrf_b200.h)
-enum { KERNEL_RBF = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2 };
+enum { KERNEL_RBF = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2, KERNEL_EXPONENTIAL = 3 };
 constexpr int MAX_D = 8;
 
 // k(r2)/variance and d k / d r2 / variance for the three isotropic kernels
-// (pyro.contrib.gp.kernels.{RBF,Matern32,Matern52}; r = sqrt(r2 + 1e-12) as in Isotropy._scaled_dist)
+// (pyro.contrib.gp.kernels.{RBF,Matern32,Matern52,Exponential}; r = sqrt(r2 + 1e-12) as in Isotropy._scaled_dist)
 template <typename T>
 __host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_dr2) {
   if (kid == KERNEL_RBF) {
@@ -170,11 +170,15 @@ __host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_
     T e = exp(-s);
     k = (T(1) + s) * e;
     dk_dr2 = T(-1.5) * e;
-  } else {
+  } else if (kid == KERNEL_MATERN52) {
     T s = sqrt(T(5) * (r2 + T(1e-12)));
     T e = exp(-s);
     k = (T(1) + s + (T(5) / T(3)) * r2) * e;
     dk_dr2 = -(T(5) / T(6)) * (T(1) + s) * e;
+  } else {   // Exponential: exp(-r)
+    T r = sqrt(r2 + T(1e-12));
+    k = exp(-r);
+    dk_dr2 = T(-0.5) * k / r;
   }
 }
 

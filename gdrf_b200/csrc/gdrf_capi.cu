@@ -86,7 +86,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   if (s->v < 1) return fail(1, "v must be positive%s");
   if (s->n_local < 0) return fail(1, "n_local must be non-negative%s");
   if (s->ls_dim != 1 && s->ls_dim != s->d) return fail(1, "ls_dim must be 1 or d%s");
-  if (s->kernel_id < 0 || s->kernel_id > 2) return fail(1, "unknown kernel_id%s");
+  if (s->kernel_id < 0 || s->kernel_id > 3) return fail(1, "unknown kernel_id%s");
   if (s->chunk_rows < 0 || (s->chunk_rows % 256) != 0) return fail(1, "chunk_rows must be a multiple of 256%s");
   p.D = s->d; p.M = s->m; p.K = s->k; p.V = s->v;
   p.Mp = (int)round_up_ll(s->m, 256);

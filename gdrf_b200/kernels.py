@@ -1,5 +1,5 @@
 """Isotropic stationary kernels with the surface of ``pyro.contrib.gp.kernels`` that the reference uses
-(``gdrf/train_script.py:93-99`` KERNEL_DICT: ``RBF``, ``Matern32``, ``Matern52``): constructor
+(``gdrf/train_script.py:93-99`` KERNEL_DICT: ``RBF``, ``Matern32``, ``Matern52``, ``Exponential``): constructor
 ``(input_dim, variance=None, lengthscale=None, active_dims=None)``, positive-constrained learnable
 ``variance`` / ``lengthscale`` (stored as ``<name>_unconstrained`` like ``PyroParam``), and
 ``__call__(X, Z=None, diag=False)``.
@@ -58,6 +58,8 @@ class Isotropy(nn.Module):
         if self.kind == "rbf":
             return self.variance * torch.exp(-0.5 * r2)
         r = (r2 + 1e-12).sqrt()
+        if self.kind == "exponential":
+            return self.variance * torch.exp(-r)
         if self.kind == "matern32":
             s = (3 ** 0.5) * r
             return self.variance * (1 + s) * torch.exp(-s)
@@ -77,7 +79,12 @@ class Matern52(Isotropy):
     kind = "matern52"
 
 
-KERNEL_DICT = {"rbf": RBF, "matern32": Matern32, "matern52": Matern52}
+class Exponential(Isotropy):
+    kind = "exponential"
+
+
+# train_script.py:93-99 also lists "rationalquadratic" (an extra learnable scale_mixture parameter): not accelerated.
+KERNEL_DICT = {"rbf": RBF, "matern32": Matern32, "matern52": Matern52, "exponential": Exponential}
 
 
 def kernel_kind(kernel) -> str:
@@ -85,4 +92,5 @@ def kernel_kind(kernel) -> str:
     name = type(kernel).__name__.lower()
     if name in KERNEL_IDS:
         return name
-    raise NotImplementedError(f"kernel {type(kernel).__name__} is not accelerated (rbf, matern32, matern52 are)")
+    raise NotImplementedError(f"kernel {type(kernel).__name__} is not accelerated "
+                              "(rbf, matern32, matern52, exponential are)")

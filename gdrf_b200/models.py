@@ -212,11 +212,21 @@ class SparseMultinomialGDRF(nn.Module):
         if eps is None:
             eps = torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
         n_global = N if n_global is None else int(n_global)
-        return GDRFElbo.apply(x, ws.to(self.device), self._inducing_points, self._kernel.variance,
-                              self._kernel.lengthscale, self.u_loc, self.u_scale_tril, self.noise,
-                              self._word_topic_matrix_map, self._dirichlet_param, eps,
-                              _lib.KERNEL_IDS[self._kernel_kind], self._jitter, self._maxjitter, n_global,
-                              n_offset, include_prior, flags, chunk_rows)
+        ws = ws.to(self.device)
+
+        def one(e):
+            return GDRFElbo.apply(x, ws, self._inducing_points, self._kernel.variance, self._kernel.lengthscale,
+                                  self.u_loc, self.u_scale_tril, self.noise, self._word_topic_matrix_map,
+                                  self._dirichlet_param, e, _lib.KERNEL_IDS[self._kernel_kind], self._jitter,
+                                  self._maxjitter, n_global, n_offset, include_prior, flags, chunk_rows)
+
+        if eps.dim() == 3:      # [P, K, N]: Trace_ELBO(num_particles=P) averages the particles' ELBOs
+            return torch.stack([one(e) for e in eps]).mean()
+        if self.num_particles > 1:
+            extra = [torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
+                     for _ in range(self.num_particles - 1)]
+            return torch.stack([one(e) for e in [eps] + extra]).mean()
+        return one(eps)
 
     def model(self, xs, ws, subsample=False):
         """sparse_gdrf.py:322-373.  Under Pyro: one factor carrying N * (ELBO / N); the enclosing

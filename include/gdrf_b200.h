@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st* gdrf_stream_t; /* == cudaStream_t */
 
-enum { GDRF_KERNEL_RBF = 0, GDRF_KERNEL_MATERN32 = 1, GDRF_KERNEL_MATERN52 = 2 };
+enum { GDRF_KERNEL_RBF = 0, GDRF_KERNEL_MATERN32 = 1, GDRF_KERNEL_MATERN52 = 2, GDRF_KERNEL_EXPONENTIAL = 3 };
 
 enum {
   GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
@@ -56,7 +56,7 @@ typedef struct gdrf_shape {
   int32_t m;          /* inducing points (<= 4096)                                                            */
   int32_t k;          /* topics (<= 128)                                                                      */
   int32_t v;          /* observation categories                                                               */
-  int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT rbf / matern32 / matern52)        */
+  int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT rbf/matern32/matern52/exponential)  */
   int32_t ls_dim;     /* 1 (isotropic lengthscale) or d                                                       */
   int32_t chunk_rows; /* observations streamed per pass, multiple of 256; 0 = library default                 */
   int32_t flags;      /* GDRF_FLAG_*                                                                          */

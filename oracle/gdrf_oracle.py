@@ -31,7 +31,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2}
+KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3}
 
 
 # --------------------------------------------------------------------------------------
@@ -53,6 +53,8 @@ def kernel_matrix(kind: str, X: torch.Tensor, Z: torch.Tensor, variance: torch.T
     if kind == "rbf":
         return variance * torch.exp(-0.5 * r2)
     r = (r2 + 1e-12).sqrt()
+    if kind == "exponential":            # pyro.contrib.gp.kernels.Exponential: variance * exp(-r)
+        return variance * torch.exp(-r)
     if kind == "matern32":
         s = (3 ** 0.5) * r
         return variance * (1 + s) * torch.exp(-s)

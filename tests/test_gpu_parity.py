@@ -317,3 +317,62 @@ def test_c5_shape_matern52_k64_v1024_m2048():
     assert torch.allclose(ta + tb, t, rtol=1e-9, atol=1e-3)
     for k in g:
         assert O.rel_err(ga[k] + gb[k], g[k]) < 1e-4, k
+
+
+def test_exponential_kernel_and_particles():
+    """Exponential kernel (train_script.py:93-99 KERNEL_DICT) against the oracle; num_particles > 1 averages ELBOs."""
+    inp = O.make_problem(N=1100, D=2, K=3, V=30, grid=[6, 6], kernel="exponential", seed=91)
+    o64, g64 = O.loss_and_grads(inp.to(torch.float64), twice=False)
+    o32, g32 = O.loss_and_grads(inp, twice=False)
+    t, g, _ = _run(inp)
+    N = inp.xs.shape[0]
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
+    for k in O.GRAD_NAMES:
+        err, err32 = O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k])
+        assert err <= (HYPER_TOL if k in HYPER else max(GRAD_TOL, 2.0 * err32)), (k, err, err32)
+    from gdrf_b200 import Exponential, SparseMultinomialGDRF
+    m = SparseMultinomialGDRF(num_observation_categories=30, num_topic_categories=3, world=[(0.0, 1.0)] * 2,
+                              kernel=Exponential(2, variance=inp.variance, lengthscale=inp.lengthscale),
+                              dirichlet_param=0.01, n_points=6, inducing_init="grid", device="cuda:0", jitter=1e-4,
+                              maxjitter=15, fixed_inducing_points=True)
+    eps = torch.randn(2, 3, N, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(3))
+    both = m.elbo(inp.xs.cuda(), inp.ws.cuda(), eps=eps)
+    e0 = m.elbo(inp.xs.cuda(), inp.ws.cuda(), eps=eps[0])
+    e1 = m.elbo(inp.xs.cuda(), inp.ws.cuda(), eps=eps[1])
+    assert abs(both.item() - 0.5 * (e0.item() + e1.item())) < 1e-5 * abs(both.item())
+    both.backward()
+    assert m.u_loc_unconstrained.grad is not None and torch.isfinite(m.u_loc_unconstrained.grad).all()
+
+
+SWEEP = [
+    # N, D, K, V, grid, kernel
+    (129, 1, 1, 5, [7], "rbf"),                 # one topic: softmax is constant, d/dmu vanishes
+    (257, 2, 2, 1, [3, 4], "matern32"),         # one category: phat = 1 hits the 1 - eps clamp of Multinomial
+    (300, 2, 3, 2, [5, 7], "matern52"),
+    (255, 4, 5, 37, [3, 3, 2, 2], "rbf"),       # D = 4, M = 36
+    (1000, 3, 17, 65, [5, 3, 3], "exponential"),
+    (513, 2, 40, 300, [9, 9], "rbf"),           # K > 32 (two topics per lane), V > 256
+    (2049, 1, 6, 31, [300], "matern52"),        # M = 300 -> padded to 512, N = 16 tiles + 1 row
+]
+
+
+@pytest.mark.parametrize("N,D,K,V,grid,kernel", SWEEP)
+def test_shape_sweep_against_fp64_oracle(N, D, K, V, grid, kernel):
+    inp = O.make_problem(N=N, D=D, K=K, V=V, grid=grid, kernel=kernel, seed=100 + N)
+    o64, g64 = O.loss_and_grads(inp.to(torch.float64), twice=False)
+    o32, g32 = O.loss_and_grads(inp, twice=False)
+    t, g, nj = _run(inp)
+    assert nj == int(o64["njitter"])
+    for i, k in enumerate(("lp_mu", "lq", "ll", "lp_phi")):
+        assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * max(1.0, abs(o64[k].item())), k
+    for k in ("u_loc", "u_scale_tril", "phi", "noise"):
+        ref = g64[k]
+        if ref.norm() < 1e-12:
+            assert (-g[k] / N).norm() < 1e-6, k
+            continue
+        err, err32 = O.rel_err(-g[k] / N, ref), O.rel_err(g32[k], ref)
+        assert err <= max(2 * GRAD_TOL, 2.0 * err32), (k, err, err32)
+    for k in HYPER:
+        if g64[k].norm() > 1e-12:
+            assert O.rel_err(-g[k] / N, g64[k]) <= 2 * HYPER_TOL, k

@@ -166,3 +166,19 @@ def test_two_rank_sharded_step_equals_single_rank(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_csv_ingest_matches_reference_recipe(tmp_path):
+    """gdrf_b200.data.load_counts_csv == the pandas recipe of gdrf/train_script.py:251-273."""
+    from gdrf_b200.data import load_counts_csv
+    p = tmp_path / "d.csv"
+    p.write_text("x,y,a,b,c\n0,0,1,2,3\n0,2,4,,6\n3,1,7,8,9\n")
+    xs, ws, world = load_counts_csv(str(p), 2)
+    assert xs.dtype == torch.float32 and ws.dtype == torch.int32
+    assert torch.allclose(xs, torch.tensor([[0.0, 0.0], [0.0, 1.0], [1.0, 0.5]]))
+    assert ws.tolist() == [[1, 2, 3], [4, 0, 6], [7, 8, 9]]
+    assert world == [(0.0, 1.0), (0.0, 1.0)]
+    p1 = tmp_path / "t.csv"
+    p1.write_text("t,a,b\n10,1,0\n20,0,5\n40,2,2\n")
+    xs1, ws1, world1 = load_counts_csv(str(p1), 1)
+    assert xs1.shape == (3, 1) and torch.allclose(xs1[:, 0], torch.tensor([0.0, 1.0 / 3.0, 1.0]))

@@ -19,12 +19,14 @@ def _direct_kernel(kind, X, Z, var, ls):
     r = r2.sqrt()
     if kind == "rbf":
         return var * torch.exp(-0.5 * r2)
+    if kind == "exponential":
+        return var * torch.exp(-r)
     if kind == "matern32":
         return var * (1 + math.sqrt(3) * r) * torch.exp(-math.sqrt(3) * r)
     return var * (1 + math.sqrt(5) * r + 5.0 / 3.0 * r2) * torch.exp(-math.sqrt(5) * r)
 
 
-@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52", "exponential"])
 def test_kernels_match_closed_form(kind):
     g = torch.Generator().manual_seed(0)
     X = torch.rand(50, 3, generator=g, dtype=torch.float64)
