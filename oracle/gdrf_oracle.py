@@ -115,6 +115,23 @@ def conditional_whitened(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tr
     return loc, var
 
 
+EPS32 = 1.1920928955078125e-07   # torch.finfo(torch.float32).eps: the reference runs in fp32 (train_script.py:265)
+
+
+def multinomial_log_prob(probs: torch.Tensor, value: torch.Tensor) -> torch.Tensor:
+    """torch.distributions.Multinomial(probs=probs, validate_args=False).log_prob(value), restated
+    (Categorical normalises probs; probs_to_logits clamps to [eps, 1 - eps]; log_prob adds the lgamma terms) with
+    the clamp pinned to the *fp32* eps the reference sees, so that the fp64 evaluation of the oracle is the same
+    function in higher precision (tests/test_oracle.py checks it against torch's class in fp32)."""
+    p = probs / probs.sum(-1, keepdim=True)
+    logits = torch.log(p.clamp(min=EPS32, max=1 - EPS32))
+    v = value.to(probs.dtype)
+    log_factorial_n = torch.lgamma(v.sum(-1) + 1)
+    log_factorial_xs = torch.lgamma(v + 1).sum(-1)
+    logits = logits.masked_fill((v == 0) & (logits == -float("inf")), 0)
+    return log_factorial_n - log_factorial_xs + (logits * v).sum(-1)
+
+
 @dataclass
 class OracleInputs:
     xs: torch.Tensor            # [N, D]   already scaled to the unit cube
@@ -186,7 +203,7 @@ def elbo_terms(inp: OracleInputs, params: Optional[Dict[str, torch.Tensor]] = No
     lp_phi = torch.distributions.Dirichlet(inp.beta, validate_args=False).log_prob(phi).sum()
     topic_probs = torch.softmax(mu, -2).transpose(-2, -1)
     probs = torch.matmul(topic_probs, phi)
-    ll = torch.distributions.Multinomial(probs=probs, validate_args=False).log_prob(inp.ws).sum()
+    ll = multinomial_log_prob(probs, inp.ws).sum()
     n_scale = inp.n_global if inp.n_global is not None else N
     elbo = lp_mu + lp_phi + ll - lq
     return {"lp_mu": lp_mu, "lp_phi": lp_phi, "ll": ll, "lq": lq, "elbo": elbo,

@@ -73,6 +73,17 @@ def test_multinomial_and_dirichlet_terms_match_manual_and_scipy():
     assert np.isfinite(gammaln(1.0))
 
 
+def test_multinomial_restatement_equals_torch_class_in_fp32():
+    g = torch.Generator().manual_seed(3)
+    probs = torch.rand(40, 9, generator=g) + 1e-3
+    probs[0] = torch.tensor([1.0] + [0.0] * 8)          # exercises both clamp ends
+    ws = torch.randint(0, 7, (40, 9), generator=g).int()
+    ws[0, 1:] = 0
+    ref = torch.distributions.Multinomial(probs=probs, validate_args=False).log_prob(ws)
+    assert torch.allclose(O.multinomial_log_prob(probs, ws), ref, rtol=1e-6, atol=1e-5)
+    assert O.EPS32 == torch.finfo(torch.float32).eps
+
+
 def test_elbo_matches_closed_form():
     inp = O.make_problem(N=80, D=1, K=2, V=5, grid=[6], kernel="matern32").to(torch.float64)
     out = O.elbo_terms(inp)
