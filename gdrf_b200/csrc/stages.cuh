@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
                 const float ph = pq[q] * sinv[i0 + q];
                 const float pc = fminf(fmaxf(ph, EPS32), 1.f - EPS32);
                 const float cf = (float)c[q];
-                llp[q] += cf * __logf(pc) - (c[q] > 1 ? lgammaf(cf + 1.f) : 0.f);
+                llp[q] += cf * logf(pc) - (c[q] > 1 ? lgammaf(cf + 1.f) : 0.f);   // logf, not __logf: phat may sit at the 1 - eps clamp
                 cp[q] += cf;
                 if (ph >= EPS32 && ph <= 1.f - EPS32) {
                   ap[q] += cf;
