@@ -364,8 +364,12 @@ def test_shape_sweep_against_fp64_oracle(N, D, K, V, grid, kernel):
     o32, g32 = O.loss_and_grads(inp, twice=False)
     t, g, nj = _run(inp)
     assert nj == int(o64["njitter"])
+    # atol: with V = 1 the log-likelihood is an exact cancellation of lgamma terms of size ~ N * lgamma(10); the
+    # per-count lgammaf of the kernel is fp32, so 1e-3 absolute on top of the relative gate
     for i, k in enumerate(("lp_mu", "lq", "ll", "lp_phi")):
-        assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * max(1.0, abs(o64[k].item())), k
+        assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * abs(o64[k].item()) + 1e-3, k
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
     for k in ("u_loc", "u_scale_tril", "phi", "noise"):
         ref = g64[k]
         if ref.norm() < 1e-12:
