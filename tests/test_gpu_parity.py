@@ -369,7 +369,7 @@ def test_shape_sweep_against_fp64_oracle(N, D, K, V, grid, kernel):
     for i, k in enumerate(("lp_mu", "lq", "ll", "lp_phi")):
         assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * abs(o64[k].item()) + 1e-3, k
     elbo = (t[0] + t[3] + t[2] - t[1]).item()
-    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
+    assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item()) + 1e-3
     for k in ("u_loc", "u_scale_tril", "phi", "noise"):
         ref = g64[k]
         if ref.norm() < 1e-12:
