@@ -25,15 +25,23 @@ __device__ __forceinline__ void store8(bf16* dst, const uint4& pk) { *reinterpre
 // The 128-byte swizzle only permutes 16-byte chunks with XOR (row & 7), so the two chunks of a 32-byte sector stay
 // in the same sector (possibly swapped): a full-sector store needs no read-for-fill in L2 (a pair of 16-byte stores
 // cost a DRAM read per written sector -- measured 2.3 GB per launch on the T store).
+// STREAM: evict-first hint for multi-GB outputs that are not re-read before they fall out of L2 anyway (the T
+// planes); without it they push the re-used B operand (ST) out of L2.
+template <bool STREAM = false>
 __device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int col, const uint4& lo, const uint4& hi) {
   bf16* p = m.elem(plane, r, col);                       // address of the chunk holding columns col .. col+7
   const bool swapped = (r & 1) != 0;                     // chunk index parity flips with row parity
   bf16* sector = swapped ? p - 8 : p;
   const uint4& a = swapped ? hi : lo;
   const uint4& b = swapped ? lo : hi;
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y), "r"(a.z),
-               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
+  if (STREAM)
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y),
+                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+  else
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
 }
 
 // sum of 32 squares: four independent fp32 partial sums of 8 terms, combined in fp64
@@ -149,7 +157,7 @@ struct G2 {
           split8<2>(&v[g * 8], pa);
           split8<2>(&v[g * 8 + 8], pb);
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) store16(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
+          for (int pl = 0; pl < 2; ++pl) store16<true>(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
         }
       }
     }

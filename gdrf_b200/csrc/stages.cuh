@@ -605,8 +605,8 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
       uint4 out[2];
       split8<2>(v, out);
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl)
-        *reinterpret_cast<uint4*>(wg.elem(pl, n, (k * MB + cb) * 64 + g * 8)) = out[pl];
+      for (int pl = 0; pl < 2; ++pl)      // streaming store: 2.4 GB per chunk, read back only after it left L2
+        __stcs(reinterpret_cast<uint4*>(wg.elem(pl, n, (k * MB + cb) * 64 + g * 8)), out[pl]);
     }
   }
 }
