@@ -332,9 +332,6 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
 // per MMA drops from 96 KB to 64 KB per k-block -- the L2 -> SM fabric (about 42 B/clk/SM), not the tensor pipe,
 // is what bounds the single-CTA kernel -- and the ring deepens to 3 stages.
 //   * logical item of CTA `rank` in cluster work item `item2` is 2 * item2 + rank (policies order their items so)
-//   * the 256 B columns are issued as two N = 128 MMAs per k-step: half h covers the 64-column groups (2h, 2h+1),
-//     rank r stages group 2h + r, so that accumulator columns stay in natural order and a policy can skip a half
-//     in k-blocks where a triangular operand makes it all zero (P::half_mask)
 //   * rank 0 issues every tcgen05.mma.cta_group::2; completion is multicast to both CTAs' barriers
 //   * rank 1 relays "my stage is full" and "my epilogue drained the accumulator" to rank 0's barriers
 // ------------------------------------------------------------------------------------------
@@ -434,6 +431,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_items2 = (n_items1 + 1) >> 1;
+  constexpr int B_HALF_K = 1;                    // K-major: one 128-row piece per CTA
+  constexpr int B_HALF_MN = 2;                   // MN-major: two 64-column pieces per CTA
 
   if (warp == 0) {
     // ------------------------------ bulk-copy producer (both CTAs) ------------------------------
@@ -465,14 +464,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
             for (int pl = 0; pl < P::PB; ++pl) {
               uint8_t* dst = st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES;
               if (!P::B_MN) {
-                // K-major: 64-row group g = 2h + rank is the rank-th half of 128-row block h
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                  bulk_g2s(dst + h * 8192, P::b_src(prm, item, sub, kit, pl, h) + (int)rank * 4096, 8192, &full_bar[s]);
+                bulk_g2s(dst, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s]);
               } else {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                  bulk_g2s(dst + h * 8192, P::b_src(prm, item, sub, kit, pl, 2 * h + (int)rank), 8192, &full_bar[s]);
+                for (int pc = 0; pc < B_HALF_MN; ++pc)
+                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
+                           &full_bar[s]);
               }
             }
           }
@@ -484,7 +481,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
     if (lane == 0) {
       if (rank == 0) {
         // ------------------------------ MMA issuer (leader CTA) ------------------------------
-        constexpr uint32_t idesc = make_idesc(256, 128, P::A_MN, P::B_MN, P::FMT);
+        constexpr uint32_t idesc = make_idesc(256, 256, P::A_MN, P::B_MN, P::FMT);
         constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
         uint32_t it = 0, unit = 0;
         for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
@@ -497,33 +494,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             const int kn = P::k_iters(prm, item, sub);
-            bool first[2] = {true, true};
             for (int kit = 0; kit < kn; ++kit, ++it) {
               const int s = it % NST;
               const uint32_t ph = (it / NST) & 1;
-              const int mask = P::half_mask(prm, item, sub, kit);
               mbar_wait(&full_bar[s], ph);
               mbar_wait(&peer_full_bar[s], ph);
               tc_fence_after();
               const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
               const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
+              bool first = (kit == 0);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (!((mask >> h) & 1)) continue;
+              for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int pa = 0; pa < P::PA; ++pa) {
 #pragma unroll
-                  for (int pa = 0; pa < P::PA; ++pa) {
-#pragma unroll
-                    for (int pb = 0; pb < P::PB; ++pb) {
-                      if (pa + pb > ORD) continue;
-                      const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
-                      const uint32_t b_addr = sb + pb * Cfg::B_BYTES + h * 8192 + (P::B_MN ? ks * 2048 : ks * 32);
-                      const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
-                      const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
-                      umma2_f16(d_tmem + h * 128, da, db, idesc, first[h] ? 0u : 1u);
-                      first[h] = false;
-                    }
+                  for (int pb = 0; pb < P::PB; ++pb) {
+                    if (pa + pb > ORD) continue;
+                    const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                    const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                    const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                    const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                    umma2_f16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                    first = false;
                   }
                 }
               }

@@ -73,8 +73,6 @@ struct G1 {
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
   __device__ static int k_iters(const Params& p, int, int sub) { return min(p.MB, 2 * (sub + 1)); }
-  // both halves always (see gemm_tc2_kernel)
-  __device__ static int half_mask(const Params&, int, int, int) { return 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int) {
     return p.kxz.base + pl * p.kxz.plane_stride + p.kxz.block_off(item, kit);
   }
@@ -134,8 +132,6 @@ struct G2 {
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.K * p.NT; }
   __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - CB * (sub % p.NT); }
-  // S_k is lower triangular: i-blocks 4 jt, 4 jt + 1 of the diagonal block only reach the first 128 columns
-  __device__ static int half_mask(const Params&, int, int, int kit) { return (BN == 256 && kit < 2) ? 1 : 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
     const int jt = sub % p.NT;
     return p.w.base + pl * p.w.plane_stride + p.w.block_off(item, CB * jt + kit);
@@ -192,8 +188,6 @@ struct G3 {
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.JT * p.K; }   // sub = it * K + k
   __device__ static int k_iters(const Params& p, int, int sub) { return 4 * (sub / p.K + 1); }
-  // j-blocks 4 it + 2, 4 it + 3 (the last two of a segment) only reach columns i >= 128 of the tile
-  __device__ static int half_mask(const Params& p, int, int sub, int kit) { return kit >= 4 * (sub / p.K) + 2 ? 2 : 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
     const int k = sub % p.K;
     return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(item, k * p.MB + kit);
@@ -266,7 +260,6 @@ struct G4 {
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
   __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - 2 * sub; }
-  __device__ static int half_mask(const Params&, int, int, int) { return 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
     return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(item, 2 * sub + kit);
   }
@@ -306,7 +299,6 @@ struct G5 {
     const int s = item / (p.MT * p.MT);
     return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
   }
-  __device__ static int half_mask(const Params&, int, int, int) { return 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
     const int s = item / (p.MT * p.MT), t = item - s * p.MT * p.MT, at = t / p.MT;
     const int nb = s * p.nb_per_split + kit;
@@ -352,7 +344,6 @@ struct G6 {
     const int s = item / (p.K * p.ntile);
     return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
   }
-  __device__ static int half_mask(const Params&, int, int, int) { return 3; }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
     const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
     const int nb = s * p.nb_per_split + kit;
