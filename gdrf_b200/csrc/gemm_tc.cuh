@@ -60,31 +60,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// same, with an L2 eviction-priority hint (createpolicy): evict_last for an operand every CTA re-reads (the packed
-// S matrices), evict_first for operands that stream through once per use
-template <int HINT>
-__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
-                                              uint64_t policy) {
-  if (HINT == 0) {
-    bulk_g2s(smem_dst, gsrc, bytes, bar);
-    return;
-  }
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -462,9 +437,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
   if (warp == 0) {
     // ------------------------------ bulk-copy producer (both CTAs) ------------------------------
     if (lane == 0) {
-      // 0 = default priority, 1 = evict_first (streams through), 2 = evict_last (re-read by every cluster)
-      const uint64_t pol_a = P::HINT_A == 1 ? l2_policy_evict_first() : l2_policy_evict_last();
-      const uint64_t pol_b = P::HINT_B == 1 ? l2_policy_evict_first() : l2_policy_evict_last();
       uint32_t it = 0;
       for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
         const int item = min(2 * item2 + (int)rank, n_items1 - 1);
@@ -481,23 +453,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
             for (int pl = 0; pl < P::PA; ++pl) {
               uint8_t* dst = st + pl * Cfg::A_BYTES;
               if (!P::A_MN) {
-                bulk_g2s_hint<P::HINT_A>(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s], pol_a);
+                bulk_g2s(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < 2; ++pc)
-                  bulk_g2s_hint<P::HINT_A>(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s], pol_a);
+                  bulk_g2s(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
               }
             }
 #pragma unroll
             for (int pl = 0; pl < P::PB; ++pl) {
               uint8_t* dst = st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES;
               if (!P::B_MN) {
-                bulk_g2s_hint<P::HINT_B>(dst, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s], pol_b);
+                bulk_g2s(dst, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < B_HALF_MN; ++pc)
-                  bulk_g2s_hint<P::HINT_B>(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
-                                         &full_bar[s], pol_b);
+                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
+                           &full_bar[s]);
               }
             }
           }

@@ -62,7 +62,6 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------
 struct G1 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int HINT_A = 0, HINT_B = 0;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
@@ -118,7 +117,6 @@ struct G1 {
 template <int MODE>
 struct G2 {
   static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: the T store must keep up with short tiles
-  static constexpr int HINT_A = 0, HINT_B = 2;   // L2 hints: the packed S is re-read by every cluster -> evict_last
   static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
   static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
@@ -178,7 +176,6 @@ struct G2 {
 // ---------------------------------------------------------------------------------------------
 struct G3 {
   static constexpr int EPI_WARPS = 8;
-  static constexpr int HINT_A = 1, HINT_B = 2;   // T streams through (evict_first), the packed S stays (evict_last)
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = false, B_MN = true;
@@ -252,7 +249,6 @@ struct G3 {
 // ---------------------------------------------------------------------------------------------
 struct G4 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int HINT_A = 0, HINT_B = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = true;
@@ -289,7 +285,6 @@ struct G4 {
 // ---------------------------------------------------------------------------------------------
 struct G5 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int HINT_A = 0, HINT_B = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = true, B_MN = true;
@@ -333,7 +328,6 @@ struct G5 {
 // ---------------------------------------------------------------------------------------------
 struct G6 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int HINT_A = 0, HINT_B = 0;   // both operands are shared by the tiles of one topic: default priority
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = true, B_MN = true;
