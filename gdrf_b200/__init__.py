@@ -1,9 +1,11 @@
 """gdrf_b200: B200-native ELBO + gradient of the sparse multinomial GDRF (san-soucie/gdrf hot path)."""
 from . import _lib
-from .elbo import GDRFElbo, elbo_value_and_grads, marginal_mean, perplexity_from_mean
+from .elbo import (GDRFElbo, elbo_value_and_grads, elbo_value_and_grads_from_host, marginal_mean, marginal_moments,
+                   perplexity_from_mean)
 from .kernels import KERNEL_DICT, RBF, Exponential, Matern32, Matern52
 from .models import SparseMultinomialGDRF
 from .svi import SVI, shard_bounds
 
-__all__ = ["GDRFElbo", "elbo_value_and_grads", "marginal_mean", "perplexity_from_mean", "RBF", "Matern32",
+__all__ = ["GDRFElbo", "elbo_value_and_grads", "elbo_value_and_grads_from_host", "marginal_mean", "marginal_moments",
+           "perplexity_from_mean", "RBF", "Matern32",
            "Matern52", "Exponential", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "shard_bounds", "_lib"]

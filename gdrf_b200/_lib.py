@@ -42,7 +42,8 @@ class Outputs(ctypes.Structure):
 
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
-           "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_perplexity_terms", "gdrf_last_error",
+           "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_marginal_moments", "gdrf_perplexity_terms",
+           "gdrf_last_error",
            "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
 _lib = None
@@ -63,8 +64,9 @@ def load() -> ctypes.CDLL:
     lib.gdrf_elbo_step.argtypes = [P(Shape), P(Inputs), P(Outputs), c_void_p, c_size_t, c_void_p]
     lib.gdrf_elbo_backward.argtypes = [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p]
     lib.gdrf_marginal_mean.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.gdrf_marginal_moments.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.gdrf_perplexity_terms.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p]
-    for n in EXPORTS[:7]:
+    for n in EXPORTS[:8]:
         getattr(lib, n).restype = c_int
     lib.gdrf_launch_count.restype = ctypes.c_longlong
     lib.gdrf_profile_enable.argtypes = [c_int]

@@ -279,6 +279,14 @@ __global__ void k_export_floc(const double* __restrict__ floc, int ncp, int nc, 
   if (n < nc) out[(long long)k * n_stride + n] = (float)floc[(long long)k * ncp + n];
 }
 
+// f_var[k, n] = clamp(variance - |W_n|^2, 0) + q[k, n]   (pyro conditional, full_cov=False)
+__global__ void k_export_fvar(const double* __restrict__ q, const double* __restrict__ wsq,
+                              const float* __restrict__ variance, int ncp, int nc, float* __restrict__ out,
+                              long long n_stride) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (n < nc) out[(long long)k * n_stride + n] = (float)(fmax((double)variance[0] - wsq[n], 0.0) + q[(long long)k * ncp + n]);
+}
+
 // status stays >0 on a failed factorisation; otherwise -1 flags an fp16-range overflow of S or W (|W| <= sigma)
 __global__ void k_merge_status(const int* __restrict__ range_flag, const float* __restrict__ variance,
                                int* __restrict__ status) {
@@ -619,20 +627,32 @@ int gdrf_elbo_backward(const float* grad, int64_t elems, const float* scale_dev,
 
 int gdrf_marginal_mean(const gdrf_shape* s, const gdrf_inputs* in, float* out_floc, void* ws, size_t ws_bytes,
                        gdrf_stream_t stream) {
+  return gdrf_marginal_moments(s, in, out_floc, nullptr, ws, ws_bytes, stream);
+}
+
+int gdrf_marginal_moments(const gdrf_shape* s, const gdrf_inputs* in, float* out_floc, float* out_fvar, void* ws,
+                          size_t ws_bytes, gdrf_stream_t stream) {
   Plan p;
   if (int e = make_plan(s, p)) return e;
   if (int e = check_device()) return e;
   if (!in || !ws || !out_floc) return fail(1, "null pointer argument%s");
+  if (out_fvar && !in->u_scale_tril) return fail(1, "the marginal variance needs u_scale_tril%s");
   if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = num_sms();
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, false, false, sms, st)) return e;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, out_fvar != nullptr, false, sms, st)) return e;
     k_export_floc<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
                                                              out_floc + n0, (long long)s->n_local);
     LAUNCH_CHECK();
+    if (out_fvar) {
+      k_export_fvar<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.q), at<double>(ws, p.wsq),
+                                                               in->variance, (int)p.ncp, nc, out_fvar + n0,
+                                                               (long long)s->n_local);
+      LAUNCH_CHECK();
+    }
   }
   return 0;
 }

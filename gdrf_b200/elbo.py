@@ -284,6 +284,24 @@ def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitt
     return out
 
 
+def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: str = "rbf", jitter: float = 1e-8,
+                     maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+    """(f_loc, f_var), each [K, N]: ``SparseGDRF.forward(Xnew, full_cov=False)`` (sparse_gdrf.py:277-319)."""
+    K, M = u_loc.shape
+    N = xs.shape[0]
+    dev = xs.device
+    dummy_ws = torch.zeros(N, 1, dtype=torch.int32, device=dev)
+    call = _Call(xs, dummy_ws, Z, variance, lengthscale, u_loc, u_scale_tril, torch.ones((), device=dev),
+                 torch.ones(K, 1, device=dev), torch.ones(K, 1, device=dev), torch.zeros(K, N, device=dev),
+                 _lib.KERNEL_IDS[kernel], 0, flags, chunk_rows)
+    call.prologue(jitter, maxjitter)
+    floc = torch.empty(K, N, dtype=torch.float32, device=dev)
+    fvar = torch.empty(K, N, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().gdrf_marginal_moments(ctypes.byref(call.shape), ctypes.byref(call.inputs), floc.data_ptr(),
+                                                 fvar.data_ptr(), call.workspace.data_ptr(), call.ws_bytes, call.stream))
+    return floc, fvar
+
+
 def perplexity_from_mean(floc: torch.Tensor, ws: torch.Tensor, phi: torch.Tensor) -> torch.Tensor:
     """exp(-sum w log(word_probs) / sum w)  (abstract_gdrf.py:137-139) without the N x V matrix."""
     K, N = floc.shape

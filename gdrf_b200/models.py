@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .elbo import GDRFElbo, marginal_mean, perplexity_from_mean
+from .elbo import GDRFElbo, marginal_mean, marginal_moments, perplexity_from_mean
 from .kernels import kernel_kind
 
 try:  # optional: the reference's inference driver
@@ -265,9 +265,15 @@ class SparseMultinomialGDRF(nn.Module):
         return perplexity_from_mean(self.log_topic_probs(x), w.to(self.device), self.word_topic_matrix)
 
     def forward(self, Xnew, full_cov=False):
+        """sparse_gdrf.py:277-319: (loc, var) of the GP marginal at Xnew (the mean function is zero)."""
         if full_cov:
             raise NotImplementedError("full_cov=True is not accelerated")
-        raise NotImplementedError("forward(): use log_topic_probs for the marginal mean")
+        Xnew = Xnew.to(self.device)
+        self._check_Xnew_shape(Xnew)
+        with torch.no_grad():
+            return marginal_moments(self._scaled(Xnew), self._inducing_points, self._kernel.variance,
+                                    self._kernel.lengthscale, self.u_loc, self.u_scale_tril, self._kernel_kind,
+                                    self._jitter, self._maxjitter)
 
     def artifacts(self, xs, ws, all: bool = False):
         ret = {"kernel variance": self.kernel_variance, "kernel lengthscale": self.kernel_lengthscale}

@@ -117,6 +117,12 @@ int gdrf_elbo_backward(const float* grad, int64_t elems, const float* scale_dev,
 int gdrf_marginal_mean(const gdrf_shape* shape, const gdrf_inputs* in, float* out_floc, void* workspace,
                        size_t workspace_bytes, gdrf_stream_t stream);
 
+/* Mean and variance of the sparse-GP marginal at new inputs: SparseGDRF.forward(Xnew, full_cov=False)
+ * (sparse_gdrf.py:277-319) = pyro conditional(...) -> (f_loc, f_var), both [k, n_local] fp32; out_fvar may be
+ * NULL.  Requires gdrf_prologue (which packs u_scale_tril).                                                 */
+int gdrf_marginal_moments(const gdrf_shape* shape, const gdrf_inputs* in, float* out_floc, float* out_fvar,
+                          void* workspace, size_t workspace_bytes, gdrf_stream_t stream);
+
 /* perplexity pieces (abstract_gdrf.py:137-139): out[0] = sum w log(word_probs), out[1] = sum w  (fp64),
  * from f_loc [k, n_local]; the N x V word-probability matrix is never materialised.                        */
 int gdrf_perplexity_terms(const gdrf_shape* shape, const gdrf_inputs* in, const float* floc, double* out,

@@ -262,6 +262,11 @@ def test_evaluation_path_matches_oracle():
                          inp.jitter, inp.maxjitter)
     ref = torch.from_numpy(d["f64_f_loc"])
     assert O.rel_err(floc.cpu(), ref) < 1e-5
+    from gdrf_b200.elbo import marginal_moments
+    fl2, fv2 = marginal_moments(c(inp.xs), c(inp.Z), c(inp.variance), c(inp.lengthscale), c(inp.u_loc),
+                                c(inp.u_scale_tril), inp.kernel, inp.jitter, inp.maxjitter)
+    assert O.rel_err(fl2.cpu(), ref) < 1e-5
+    assert O.rel_err(fv2.cpu(), torch.from_numpy(d["f64_f_var"])) < 1e-6
     ppl = perplexity_from_mean(floc, c(inp.ws), c(inp.phi))
     assert abs(ppl.item() - float(d["f64_perplexity"])) < 1e-4 * float(d["f64_perplexity"])
 
