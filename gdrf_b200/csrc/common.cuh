@@ -40,20 +40,9 @@ struct PlaneMat {
   __device__ __forceinline__ bf16* elem(int plane, int r, int c) const {
     return base + plane * plane_stride + block_off(r >> 7, c >> 6) + tile_off(r & 127, c & 63);
   }
-  __host__ __device__ long long plane_elems() const { return (long long)row_tiles * col_blocks * TILE_ELEMS; }
 };
 
-// error-compensated split of an fp32 value into up to three bf16 planes
-template <int P>
-__device__ __forceinline__ void split_bf16(float x, bf16 (&out)[P]) {
-  float r = x;
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    out[p] = __float2bfloat16_rn(r);
-    r -= __bfloat162float(out[p]);
-  }
-}
-
+// error-compensated split of fp32 values into up to three bf16 planes:
 // 8 consecutive fp32 values -> one 16-byte packet per plane
 template <int P>
 __device__ __forceinline__ void split8(const float* v, uint4 (&pk)[P]) {

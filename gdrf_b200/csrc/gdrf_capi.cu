@@ -58,7 +58,7 @@ struct ProfScope {
 
 struct Plan {
   // dims
-  int D, M, Mp, MB, JT, MT, K, V, RTmax;
+  int D, M, Mp, MB, JT, MT, K, V;
   long long ncp;          // padded rows per chunk (stride of the [K][ncp] arrays)
   int chunk_rows;
   // persistent
@@ -100,7 +100,6 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   }
   p.chunk_rows = (int)chunk;
   p.ncp = chunk;
-  p.RTmax = (int)(chunk / 128);
   const size_t Mp2 = (size_t)p.Mp * p.Mp;
   size_t off = 0;
   p.acc = bump(off, sizeof(double) * ACC_HEAD);

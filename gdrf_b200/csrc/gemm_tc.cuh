@@ -129,15 +129,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
          | ((uint32_t)(M >> 4) << 24); // [24,29) M >> 4
 }
 
-// number of (plane_a, plane_b) products kept: all pairs with pa + pb <= max(PA,PB)-1
-__host__ __device__ constexpr int num_products(int PA, int PB) {
-  int n = 0;
-  const int ord = (PA > PB ? PA : PB) - 1;
-  for (int a = 0; a < PA; ++a)
-    for (int b = 0; b < PB; ++b)
-      if (a + b <= ord) ++n;
-  return n;
-}
+// (plane_a, plane_b) products kept by the issue loops: all pairs with pa + pb <= max(PA, PB) - 1
 
 // warps: 0 = bulk-copy producer, 1 = MMA issuer / TMEM owner, 2.. = epilogue (P::EPI_WARPS of them, 4 or 8)
 template <class P>
