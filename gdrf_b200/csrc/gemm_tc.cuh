@@ -60,19 +60,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// shared -> global bulk store of a finished 16 KB block image (epilogue staging), tracked by bulk groups
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -390,10 +377,9 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = 16384;                  // one plane, this CTA's half of B (128 rows x 64 k)
   static constexpr int STAGE_BYTES = P::PA * A_BYTES + P::PB * B_BYTES;
   static constexpr int NSTAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) < 4 ? (GEMM_SMEM_BUDGET / STAGE_BYTES) : 4;
-  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + P::EPI_STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 512;
   static_assert(NSTAGES >= 2, "need at least a double-buffered ring");
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 template <class P>
@@ -403,8 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
   constexpr int NST = Cfg::NSTAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* epi_stage = smem + NST * Cfg::STAGE_BYTES;    // P::EPI_STAGE_BYTES of epilogue store staging
-  uint64_t* bars = (uint64_t*)(epi_stage + P::EPI_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + NST * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [NST] this CTA's stage landed
   uint64_t* empty_bar = bars + NST;              // [NST] stage consumed (multicast commit from rank 0)
   uint64_t* peer_full_bar = bars + 2 * NST;      // [NST] (rank 0 only) rank 1's stage landed
@@ -557,11 +542,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
     constexpr int NCH = 8 / (P::EPI_WARPS / 4);
     const int c_begin = ((warp - 2) >> 2) * NCH;
     typename P::Epi epi;
-    if constexpr (P::EPI_STAGE_BYTES > 0) {
-      const int half = (warp - 2) >> 2;       // group of four warps sharing one staging buffer and named barrier
-      epi.attach_stage(epi_stage + half * (P::EPI_STAGE_BYTES / (P::EPI_WARPS / 4)), 1 + half,
-                       ((warp - 2) & 3) == 0 && lane == 0);
-    }
     uint32_t unit = 0;
     for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
       const int item_raw = 2 * item2 + (int)rank;
@@ -594,7 +574,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
       }
       if (valid) epi.item_end(prm, item, row);
     }
-    if constexpr (P::EPI_STAGE_BYTES > 0) epi.finish_stage();
   }
 
   tc_fence_before();

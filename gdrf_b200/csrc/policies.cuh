@@ -62,7 +62,6 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------
 struct G1 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int EPI_STAGE_BYTES = 0;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
@@ -118,10 +117,6 @@ struct G1 {
 template <int MODE>
 struct G2 {
   static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: the T store must keep up with short tiles
-  // pair kernel: each group of four epilogue warps assembles finished 128 x 64 plane blocks (16 KB) in shared memory
-  // and writes them with one cp.async.bulk shared -> global (whole lines; row-per-thread stores cost a DRAM read per
-  // written sector)
-  static constexpr int EPI_STAGE_BYTES = (MODE == 2) ? 32768 : 0;
   static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
   static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
@@ -147,58 +142,23 @@ struct G2 {
   }
   struct Epi {
     double qacc;
-    uint8_t* stage = nullptr;   // 16 KB staging block of this thread's warp group (pair kernel only)
-    int bar_id = 0;
-    bool leader = false;
-    uint4 keep[2][4];           // the left 32 columns of the 64-column block being assembled, per plane
-    __device__ void attach_stage(uint8_t* s, int id, bool lead) { stage = s; bar_id = id; leader = lead; }
-    __device__ void finish_stage() { if (leader) bulk_wait_all0(); }
     __device__ void item_begin(const Params&, int, int) { qacc = 0.0; }
     __device__ void sub_begin(const Params& p, int, int sub, int) {
       if (sub % p.NT == 0) qacc = 0.0;
     }
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
       qacc += sumsq32(v);
-      if (!p.store_t) return;
-      const int r = item * 128 + row;
-      const int col0 = sub * BN + c0;     // (k * NT + jt) * BN == k * Mp + jt * BN
-      uint4 pk[2][4];
+      if (p.store_t) {
+        const int r = item * 128 + row;
+        const int col0 = sub * BN + c0;     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 t2[2];
-        split8<2>(&v[g * 8], t2);
-        pk[0][g] = t2[0];
-        pk[1][g] = t2[1];
-      }
-      if (stage == nullptr) {             // single-CTA / checker kernels: direct full-sector stores
+        for (int g = 0; g < 4; g += 2) {
+          uint4 pa[2], pb[2];
+          split8<2>(&v[g * 8], pa);
+          split8<2>(&v[g * 8 + 8], pb);
 #pragma unroll
-        for (int g = 0; g < 4; g += 2)
-#pragma unroll
-          for (int pl = 0; pl < 2; ++pl) store16<true>(p.tp, pl, r, col0 + g * 8, pk[pl][g], pk[pl][g + 1]);
-        return;
-      }
-      if (((c0 >> 5) & 1) == 0) {         // left half of a 64-column block: keep it until the right half arrives
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-          for (int g = 0; g < 4; ++g) keep[pl][g] = pk[pl][g];
-        return;
-      }
-      uint8_t* rowp = stage + ((row >> 3) << 10) + ((row & 7) << 7);
-      const int sw = row & 7;
-#pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        if (leader) bulk_wait_read0();    // the previous block image has been read out of the staging buffer
-        named_bar_sync(bar_id, 128);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = keep[pl][g];
-          *reinterpret_cast<uint4*>(rowp + (((4 + g) ^ sw) << 4)) = pk[pl][g];
+          for (int pl = 0; pl < 2; ++pl) store16<true>(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (leader)
-          bulk_s2g(p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(item, (col0 - 32) >> 6), stage, 16384);
       }
     }
     __device__ void sub_end(const Params& p, int item, int sub, int row) {
@@ -216,7 +176,6 @@ struct G2 {
 // ---------------------------------------------------------------------------------------------
 struct G3 {
   static constexpr int EPI_WARPS = 8;
-  static constexpr int EPI_STAGE_BYTES = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = false, B_MN = true;
@@ -290,7 +249,6 @@ struct G3 {
 // ---------------------------------------------------------------------------------------------
 struct G4 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int EPI_STAGE_BYTES = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = false, B_MN = true;
@@ -327,7 +285,6 @@ struct G4 {
 // ---------------------------------------------------------------------------------------------
 struct G5 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int EPI_STAGE_BYTES = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 3, PB = 3, BN = 128;
   static constexpr bool A_MN = true, B_MN = true;
@@ -371,7 +328,6 @@ struct G5 {
 // ---------------------------------------------------------------------------------------------
 struct G6 {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int EPI_STAGE_BYTES = 0;
   static constexpr int FMT = FMT_BF16;
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = true, B_MN = true;
