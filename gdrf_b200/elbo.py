@@ -20,6 +20,15 @@ import torch
 from . import _lib
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
+    """Host-to-device copy stream of the sub-shard pipeline, one per device."""
+    key = device.index or 0
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -223,7 +232,7 @@ def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, leng
                         ws=torch.empty(rows, V, dtype=torch.int32, device=dev),
                         eps=torch.empty(K, rows, dtype=torch.float32, device=dev)) for _ in range(2)]
     compute = torch.cuda.current_stream(dev)
-    copy_stream = torch.cuda.Stream(dev)
+    copy_stream = _copy_stream(dev)
     calls = []
     for i, (lo, hi) in enumerate(bounds):
         st_ = staging[i % 2]
