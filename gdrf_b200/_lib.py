@@ -38,7 +38,7 @@ class Inputs(ctypes.Structure):
 
 
 class Outputs(ctypes.Structure):
-    _fields_ = [("terms", c_void_p), ("grad", c_void_p), ("aux_stream", c_void_p)]
+    _fields_ = [("terms", c_void_p), ("grad", c_void_p)]
 
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",

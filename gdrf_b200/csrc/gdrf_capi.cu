@@ -40,36 +40,6 @@ ProfRec g_prof[PROF_MAX];
 int g_prof_n = 0;
 std::vector<cudaEvent_t> g_event_pool;
 
-// Optional second stream (gdrf_outputs::aux_stream): small HBM-bound kernels that only need a sliver of each SM run
-// on it underneath a contraction of the same chunk.  fork(): aux waits for the main stream; join(): main waits for aux.
-struct Side {
-  cudaStream_t main = nullptr, aux = nullptr;
-  static constexpr int NEV = 8;
-  cudaEvent_t* ev = nullptr;
-  int next = 0;
-  bool on() const { return aux != nullptr; }
-  cudaStream_t side() const { return aux ? aux : main; }
-  cudaError_t init(cudaStream_t m, cudaStream_t a) {
-    static cudaEvent_t pool[NEV] = {};
-    main = m; aux = a; ev = pool;
-    if (a && !pool[0])
-      for (int i = 0; i < NEV; ++i) {
-        cudaError_t e = cudaEventCreateWithFlags(&pool[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-      }
-    return cudaSuccess;
-  }
-  cudaError_t link(cudaStream_t from, cudaStream_t to) {
-    if (!aux) return cudaSuccess;
-    cudaEvent_t e = ev[next++ % NEV];
-    cudaError_t r = cudaEventRecord(e, from);
-    if (r != cudaSuccess) return r;
-    return cudaStreamWaitEvent(to, e, 0);
-  }
-  cudaError_t fork() { return link(main, aux); }
-  cudaError_t join() { return link(aux, main); }
-};
-
 cudaEvent_t prof_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -262,8 +232,7 @@ cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool u
 
 // forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
 int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
-                  bool with_var, bool store_t, int sms, Side& sd) {
-  cudaStream_t st = sd.main;
+                  bool with_var, bool store_t, int sms, cudaStream_t st) {
   const Hyper hp = make_hyper(s, in);
   PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, p.Mp);
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
@@ -276,13 +245,8 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
     g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
     { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
   }
-  const bool under = with_var && sd.on();     // f_loc (fp32 FMA, 4 KB smem) runs underneath the T contraction
-  if (!under) {
-    k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
-    LAUNCH_CHECK();
-  } else {
-    CU(sd.fork());
-  }
+  k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
+  LAUNCH_CHECK();
   if (with_var) {
     CU(cudaMemsetAsync(at<double>(ws, p.q), 0, sizeof(double) * (size_t)p.K * p.ncp, st));
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
@@ -297,11 +261,6 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
-  }
-  if (under) {
-    k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, sd.aux>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
-    LAUNCH_CHECK();
-    CU(sd.join());
   }
   return 0;
 }
@@ -545,12 +504,10 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     g6.ntile = nt;
   }
 
-  Side sd;
-  CU(sd.init(st, (cudaStream_t)out->aux_stream));
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, sd)) return e;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
     k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
                                       at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
                                       at<float>(ws, p.phisum), at<float>(ws, p.fvar),
@@ -564,21 +521,16 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
                                        at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
     LAUNCH_CHECK();
     if (!want_grad) continue;
-    CU(sd.fork());
+    {
+      ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
+      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm);
+      LAUNCH_CHECK();
+    }
     {
       G3::Params g{};
       g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
       g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
-    }
-    {
-      // the row-weighted copies of W (2.4 GB of HBM writes) are only needed by G6: with a side stream they are
-      // produced by one CTA per SM underneath G3 (launched after it, so G3's CTAs are placed first)
-      ProfScope ps(PK_G2B, sd.side());
-      const int nblocks = p.MB * RT;
-      k_scale_w<<<sd.on() ? (nblocks < sms ? nblocks : sms) : nblocks, 256, 0, sd.side()>>>(
-          w, at<float>(ws, p.g2), K, p.MB, nblocks, (int)p.ncp, wgm);
-      LAUNCH_CHECK();
     }
     {
       const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
@@ -588,7 +540,6 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       LAUNCH_CHECK();
     }
     if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
-    CU(sd.join());
     {
       g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
       const int base = K * g6.ntile;
@@ -605,7 +556,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
       { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
     }
-    CU(sd.fork());
+    {
+      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
+      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
+          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
+      LAUNCH_CHECK();
+    }
     {
       G5::Params g{};
       g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
@@ -618,13 +574,6 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       g.splits = splits; g.nb_per_split = per;
       { ProfScope ps(PK_G5, st); ++g_launches; CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st)); }
     }
-    {
-      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
-      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, sd.side()>>>(
-          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
-      LAUNCH_CHECK();
-    }
-    CU(sd.join());
   }
 
   if (partial) return 0;
@@ -693,9 +642,7 @@ int gdrf_marginal_moments(const gdrf_shape* s, const gdrf_inputs* in, float* out
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
-    Side sd;
-    CU(sd.init(st, nullptr));
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, out_fvar != nullptr, false, sms, sd)) return e;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, out_fvar != nullptr, false, sms, st)) return e;
     k_export_floc<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
                                                              out_floc + n0, (long long)s->n_local);
     LAUNCH_CHECK();

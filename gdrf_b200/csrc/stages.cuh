@@ -583,13 +583,10 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
 // dS_k = W^T diag(g2_k) T_k into a plain contraction.  grid (MB, RT), 256 threads; W's block is rebuilt once
 // and rescaled K times.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __restrict__ g2, int K, int MB, int nblocks,
-                                                 int ncp, PlaneMat wg) {
+__global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __restrict__ g2, int K, int MB, int ncp,
+                                                 PlaneMat wg) {
+  const int cb = blockIdx.x, rt = blockIdx.y;
   const int g = threadIdx.x & 7;            // 8 lanes cover the eight 16-byte chunks of one 128-byte row
-  // grid-stride over the 128 x 64 blocks: a one-CTA-per-SM grid lets the kernel run underneath a contraction
-#pragma unroll 1
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-  const int cb = blk % MB, rt = blk / MB;
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int r = it * 32 + (threadIdx.x >> 3);
@@ -611,7 +608,6 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
       for (int pl = 0; pl < 2; ++pl)      // streaming store: 2.4 GB per chunk, read back only after it left L2
         __stcs(reinterpret_cast<uint4*>(wg.elem(pl, n, (k * MB + cb) * 64 + g * 8)), out[pl]);
     }
-  }
   }
 }
 

@@ -13,7 +13,6 @@ shard); the reference's loss (``poutine.scale(1/N)``, ``train_script.py:365``) i
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -22,18 +21,6 @@ from . import _lib
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
 _COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
-USE_SIDE_STREAM = os.environ.get("GDRF_SIDE_STREAM", "1") != "0"
-
-
-def _side_stream(device: torch.device):
-    """Second stream handed to gdrf_elbo_step (gdrf_outputs.aux_stream), one per device."""
-    if not USE_SIDE_STREAM:
-        return None
-    key = device.index or 0
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
-    return _SIDE_STREAMS[key].cuda_stream
 
 
 def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
@@ -138,8 +125,7 @@ class _Call:
             if grad is None:
                 grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
         self.shape.flags = flags
-        out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None,
-                           aux_stream=_side_stream(self.device))
+        out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None)
         _lib.check(lib.gdrf_elbo_step(ctypes.byref(self.shape), ctypes.byref(self.inputs), ctypes.byref(out),
                                       self.workspace.data_ptr(), self.ws_bytes, self.stream))
         return terms, grad

@@ -85,10 +85,6 @@ typedef struct gdrf_inputs {
 typedef struct gdrf_outputs {
   double* terms; /* [4]                      */
   float* grad;   /* [gdrf_grad_elems(shape)] or NULL when GDRF_FLAG_WANT_GRAD is clear                        */
-  gdrf_stream_t aux_stream; /* optional second stream: small HBM-bound kernels of a chunk (f_loc, the weighted
-                               copies of W, the kernel hyper-parameter reduction) then run underneath that chunk's
-                               contractions; NULL = everything on `stream`.  The call returns with `stream`
-                               ordered after all work on it.                                               */
 } gdrf_outputs;
 
 /* Sizes.  HOST out-pointers. */
