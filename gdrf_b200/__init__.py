@@ -4,8 +4,8 @@ from .elbo import (GDRFElbo, elbo_value_and_grads, elbo_value_and_grads_from_hos
                    perplexity_from_mean)
 from .kernels import KERNEL_DICT, RBF, Exponential, Matern32, Matern52
 from .models import SparseMultinomialGDRF
-from .svi import SVI, shard_bounds
+from .svi import SVI, FusedSVI, shard_bounds
 
 __all__ = ["GDRFElbo", "elbo_value_and_grads", "elbo_value_and_grads_from_host", "marginal_mean", "marginal_moments",
            "perplexity_from_mean", "RBF", "Matern32",
-           "Matern52", "Exponential", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "shard_bounds", "_lib"]
+           "Matern52", "Exponential", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "FusedSVI", "shard_bounds", "_lib"]

@@ -43,7 +43,7 @@ class Outputs(ctypes.Structure):
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
            "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_marginal_moments", "gdrf_perplexity_terms",
-           "gdrf_last_error",
+           "gdrf_constrain", "gdrf_adam_step", "gdrf_last_error",
            "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
 _lib = None
@@ -66,7 +66,10 @@ def load() -> ctypes.CDLL:
     lib.gdrf_marginal_mean.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.gdrf_marginal_moments.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.gdrf_perplexity_terms.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p]
-    for n in EXPORTS[:8]:
+    lib.gdrf_constrain.argtypes = [P(Shape), c_void_p, c_void_p, c_int, c_void_p]
+    lib.gdrf_adam_step.argtypes = [P(Shape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                   c_float, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]
+    for n in EXPORTS[:10]:
         getattr(lib, n).restype = c_int
     lib.gdrf_launch_count.restype = ctypes.c_longlong
     lib.gdrf_profile_enable.argtypes = [c_int]

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "linalg.cuh"
+#include "optimizer.cuh"
 #include "policies.cuh"
 #include "stages.cuh"
 
@@ -375,6 +376,46 @@ int gdrf_profile_read(double* ms, long long* launches) {
     g_event_pool.push_back(g_prof[i].b);
   }
   g_prof_n = 0;
+  return 0;
+}
+
+int gdrf_constrain(const gdrf_shape* s, const float* theta_u, float* theta_c, int learn_z, gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!theta_u || !theta_c) return fail(1, "null pointer argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim);
+  long long blocks = (f.total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_constrain<<<(int)blocks, 256, 0, st>>>(f, theta_u, theta_c, learn_z);
+  LAUNCH_CHECK();
+  k_softmax_rows<<<p.K, 256, 0, st>>>(theta_u + f.oP, theta_c + f.oP, p.V);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int gdrf_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, const float* grad, float* m, float* v,
+                   float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, int learn_z, gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!theta_u || !theta_c || !grad || !m || !v || !row_scratch) return fail(1, "null pointer argument%s");
+  if (step < 1) return fail(1, "step counts from 1%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim);
+  k_phi_rowdot<<<p.K, 256, 0, st>>>(theta_c + f.oP, grad + f.oP, p.V, row_scratch);
+  LAUNCH_CHECK();
+  AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  h.bc1 = 1.f - powf(beta1, (float)step);
+  h.bc2 = 1.f - powf(beta2, (float)step);
+  h.grad_scale = grad_scale;
+  long long blocks = (f.total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_adam<<<(int)blocks, 256, 0, st>>>(f, theta_u, theta_c, grad, row_scratch, m, v, h, learn_z);
+  LAUNCH_CHECK();
   return 0;
 }
 

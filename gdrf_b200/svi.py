@@ -57,3 +57,93 @@ class SVI:
         if self.optim is not None:
             self.optim.step()
         return float(loss.item())
+
+
+class FusedSVI:
+    """SVI step with everything after the data on the device and fused: the ELBO + gradient op on the flat
+    constrained buffer, then ONE kernel for the chain rule through the PyroParam constraints and the Adam / AdamW
+    update of the flat unconstrained buffer (the reference does this with a per-parameter
+    Python loop, ``train_script.py:325-327``).  Parameters are taken from / written back to a
+    :class:`gdrf_b200.models.SparseMultinomialGDRF`.
+    """
+
+    def __init__(self, module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 group=None):
+        import ctypes
+        from . import _lib
+        self._ct, self._lib = ctypes, _lib
+        self.m = module
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.group = group
+        self.t = 0
+        dev = module.device
+        K, M, V, D = module.K, module.M, module.V, module.D
+        self.ls_dim = int(module._kernel.lengthscale.numel())
+        self.learn_z = 0 if module._fixed_inducing_points else 1
+        with torch.no_grad():
+            z_u = module._inducing_points_fixed if not self.learn_z else module._inducing_points_unconstrained
+            parts = [module.u_scale_tril_unconstrained.reshape(-1), module.u_loc_unconstrained.reshape(-1),
+                     module._word_topic_matrix_map_unconstrained.reshape(-1), z_u.reshape(-1),
+                     module._kernel.variance_unconstrained.reshape(-1), module._kernel.lengthscale_unconstrained.reshape(-1),
+                     module.noise_unconstrained.reshape(-1)]
+            self.theta_u = torch.cat([p.detach().float() for p in parts]).contiguous().to(dev)
+        self.theta_c = torch.empty_like(self.theta_u)
+        self.mom1 = torch.zeros_like(self.theta_u)
+        self.mom2 = torch.zeros_like(self.theta_u)
+        self.row_scratch = torch.empty(K, dtype=torch.float32, device=dev)
+        self.shape = _lib.Shape(n_local=1, n_offset=0, n_eps=1, d=D, m=M, k=K, v=V,
+                                kernel_id=_lib.KERNEL_IDS[module._kernel_kind], ls_dim=self.ls_dim, chunk_rows=0, flags=0)
+
+    def _views(self):
+        from .elbo import split_grad
+        K, M, V, D = self.m.K, self.m.M, self.m.V, self.m.D
+        return split_grad(self.theta_c, K, M, V, D, self.ls_dim)
+
+    def constrain(self):
+        st = torch.cuda.current_stream(self.theta_u.device).cuda_stream
+        self._lib.check(self._lib.load().gdrf_constrain(self._ct.byref(self.shape), self.theta_u.data_ptr(),
+                                                        self.theta_c.data_ptr(), self.learn_z, st))
+        return self._views()
+
+    def step(self, xs, ws, subsample=False, eps=None, n_global=None, n_offset=0) -> float:
+        from .elbo import elbo_value_and_grads
+        m = self.m
+        c = self.constrain()
+        x = m._scaled(xs)
+        N = x.shape[0]
+        n_global = N if n_global is None else int(n_global)
+        if eps is None:
+            eps = torch.randn(m.K, N, device=m.device, generator=m._eps_generator)
+        rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
+        terms, g, _ = elbo_value_and_grads(x, ws.to(m.device), c["Z"], c["variance"], c["lengthscale"], c["u_loc"],
+                                           c["u_scale_tril"], c["noise"], c["phi"], m._dirichlet_param, eps,
+                                           kernel=m._kernel_kind, jitter=m._jitter, maxjitter=m._maxjitter,
+                                           n_global=n_global, n_offset=n_offset, include_prior=(rank == 0))
+        flat = g["u_scale_tril"].reshape(-1).as_strided((self.theta_u.numel(),), (1,))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=self.group)
+        self.t += 1
+        st = torch.cuda.current_stream(self.theta_u.device).cuda_stream
+        self._lib.check(self._lib.load().gdrf_adam_step(
+            self._ct.byref(self.shape), self.theta_u.data_ptr(), self.theta_c.data_ptr(), flat.data_ptr(),
+            self.mom1.data_ptr(), self.mom2.data_ptr(), self.row_scratch.data_ptr(), self.lr, self.betas[0],
+            self.betas[1], self.eps, self.weight_decay, self.t, -1.0 / n_global, self.learn_z, st))
+        elbo = terms[0] + terms[3] + terms[2] - terms[1]
+        return float((-elbo / n_global).item())
+
+    def write_back(self) -> None:
+        """Copies the flat unconstrained buffer back into the module's parameters."""
+        m = self.m
+        K, M, V, D = m.K, m.M, m.V, m.D
+        o = 0
+        with torch.no_grad():
+            targets = [(m.u_scale_tril_unconstrained, K * M * M), (m.u_loc_unconstrained, K * M),
+                       (m._word_topic_matrix_map_unconstrained, K * V),
+                       (m._inducing_points_unconstrained if self.learn_z else None, M * D),
+                       (m._kernel.variance_unconstrained, 1), (m._kernel.lengthscale_unconstrained, self.ls_dim),
+                       (m.noise_unconstrained, 1)]
+            for p, n in targets:
+                if p is not None:
+                    p.copy_(self.theta_u[o:o + n].view_as(p))
+                o += n

@@ -128,6 +128,18 @@ int gdrf_marginal_moments(const gdrf_shape* shape, const gdrf_inputs* in, float*
 int gdrf_perplexity_terms(const gdrf_shape* shape, const gdrf_inputs* in, const float* floc, double* out,
                           gdrf_stream_t stream);
 
+/* Fused SVI tail (the step either side of the path: train_script.py:325-327 optimiser on PyroParam-constrained
+ * parameters).  theta_u / theta_c are the flat unconstrained / constrained parameter buffers in the layout of
+ * gdrf_outputs::grad.  gdrf_constrain maps theta_u -> theta_c (lower_cholesky, identity, row softmax, sigmoid [or
+ * identity when learn_z == 0: fixed inducing points], exp).  gdrf_adam_step chains `grad` (d ELBO / d constrained,
+ * as written by gdrf_elbo_step) to the unconstrained parameters with loss = grad_scale * ELBO (grad_scale = -1/N)
+ * and applies one Adam update (decoupled weight decay when weight_decay > 0, i.e. AdamW); m, v: moment buffers of
+ * gdrf_grad_elems floats, zero before step 1; row_scratch: k floats; step counts from 1.                     */
+int gdrf_constrain(const gdrf_shape* shape, const float* theta_u, float* theta_c, int learn_z, gdrf_stream_t stream);
+int gdrf_adam_step(const gdrf_shape* shape, float* theta_u, const float* theta_c, const float* grad, float* m,
+                   float* v, float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int step, float grad_scale, int learn_z, gdrf_stream_t stream);
+
 /* Instrumentation for bench.py: kernels launched by this process so far; CUDA-event timing of the six
  * contractions (ms[7] / launches[7] in the order G1, G2, k_scale_w, G3, G4, G5, G6, summed since
  * the previous read; the read synchronises the device).  Off by default.                                   */
