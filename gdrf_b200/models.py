@@ -106,7 +106,8 @@ class SparseMultinomialGDRF(nn.Module):
         if fixed_inducing_points:
             self.register_buffer("_inducing_points_fixed", scaled)
         else:   # interval(0, 1) per dimension -> sigmoid
-            sc = scaled.clamp(1e-6, 1 - 1e-6)
+            fi = torch.finfo(scaled.dtype)      # the clamp of torch's SigmoidTransform inverse (grid end points are 0 and 1)
+            sc = scaled.clamp(min=fi.tiny, max=1.0 - fi.eps)
             self._inducing_points_unconstrained = nn.Parameter(torch.log(sc) - torch.log1p(-sc))
         self._jitter = float(jitter)
         self._maxjitter = int(maxjitter)
@@ -115,7 +116,9 @@ class SparseMultinomialGDRF(nn.Module):
         self.D = scaled.size(-1)
         self.u_loc_unconstrained = nn.Parameter(torch.zeros(self._K, self.M, device=self.device))
         with torch.no_grad():
-            L = host_jittercholesky(self._kernel(scaled).contiguous(), self.M, self._jitter, self._maxjitter)
+            # the reference factorises k(self._inducing_points): the constrained round trip, not the raw grid (:101-106)
+            L = host_jittercholesky(self._kernel(self._inducing_points.detach()).contiguous(), self.M, self._jitter,
+                                    self._maxjitter)
         S0 = L.float().repeat(self._K, 1, 1)
         # lower_cholesky: strictly-lower entries free, diagonal through exp
         unc = S0.tril(-1) + S0.diagonal(dim1=-2, dim2=-1).log().diag_embed()

@@ -1,0 +1,177 @@
+"""The oracle against what the reference's own model code computed.
+
+tests/golden/ref_*.npz were written by oracle/make_ref_fixtures.py, which executes the unmodified
+``gdrf/models/sparse_gdrf.py`` (constructor, ``model``, ``guide``, ``log_topic_probs``, ``perplexity``, and a 3-step
+SVI run wired as ``train_script.py:365-371``) with pyro-ppl replaced by the restatement in oracle/pyro_shim.  The
+reference ran in fp32; the oracle is evaluated in fp64 and in fp32 and must agree to fp32 round-off."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gdrf_oracle as O
+from tests.helpers import REF_CASES, load_ref_fixture, ref_constrained, ref_oracle_inputs
+
+TERM_TOL = 2e-5          # each ELBO term, relative (reference = fp32 sums over N*K or N*V elements)
+GRAD_TOL = 3e-4          # well-conditioned gradients; else 3x the oracle's own fp32-vs-fp64 distance
+HYPER = ("_kernel.variance_unconstrained", "_kernel.lengthscale_unconstrained", "_inducing_points_unconstrained")
+
+
+def _oracle_loss_and_grads(spec, u, d, eps, dtype):
+    leaves, params = ref_constrained(spec, u, d, dtype)
+    inp = ref_oracle_inputs(spec, params, d, eps, dtype)
+    out = O.elbo_terms(inp, params, twice=True)
+    out["loss"].backward()
+    return out, {k: v.grad for k, v in leaves.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_reproduces_reference_elbo_terms_and_gradients(name):
+    spec, u, d = load_ref_fixture(name)
+    o64, g64 = _oracle_loss_and_grads(spec, u, d, d["eps"], torch.float64)
+    o32, g32 = _oracle_loss_and_grads(spec, u, d, d["eps"], torch.float32)
+    assert o64["njitter"] == o32["njitter"]
+    for term in ("lq", "lp_mu", "ll", "lp_phi"):
+        ref = float(d[term])
+        assert abs(o64[term].item() - ref) <= TERM_TOL * max(abs(ref), 1.0), (term, o64[term].item(), ref)
+    assert abs(o64["loss"].item() - float(d["loss"])) <= TERM_TOL * abs(float(d["loss"]))
+    assert np.allclose(o64["mu"].numpy(), d["mu"], rtol=1e-4, atol=1e-4)
+    for k in u:
+        if spec["fixed"] and k == "_inducing_points_unconstrained":
+            continue
+        ref = torch.from_numpy(d["grad/" + k])
+        e, e32 = O.rel_err(ref, g64[k]), O.rel_err(g32[k], g64[k])
+        assert e <= max(GRAD_TOL, 3.0 * e32) * (10.0 if k in HYPER else 1.0), (k, e, e32)
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_reproduces_reference_evaluation_path(name):
+    spec, u, d = load_ref_fixture(name)
+    _, params = ref_constrained(spec, u, d, torch.float64)
+    inp = ref_oracle_inputs(spec, params, d, d["eps"], torch.float64)
+    ltp = O.log_topic_probs(inp)
+    assert O.rel_err(torch.from_numpy(d["log_topic_probs"]), ltp) < 1e-4
+    assert abs(O.perplexity(inp).item() - float(d["perplexity"])) < 1e-4 * float(d["perplexity"])
+    wp = torch.softmax(ltp, -2).T @ inp.phi
+    assert O.rel_err(torch.from_numpy(d["word_probs"]), wp) < 1e-4
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_follows_reference_svi_trajectory(name):
+    """3 steps of Adam(lr=0.01) on the unconstrained parameters, with the reference's own draws."""
+    spec, u, d = load_ref_fixture(name)
+    leaves = {k: v.double().clone().requires_grad_(True) for k, v in u.items()
+              if not (spec["fixed"] and k == "_inducing_points_unconstrained")}
+    opt = torch.optim.Adam(list(leaves.values()), lr=0.01)
+    for step in range(len(d["svi_losses"])):
+        cur = {k: v for k, v in leaves.items()}
+        Z = torch.from_numpy(d["Z_fixed"]).double() if spec["fixed"] else O.unit_interval(cur["_inducing_points_unconstrained"])
+        params = {"Z": Z, "variance": O.positive(cur["_kernel.variance_unconstrained"]),
+                  "lengthscale": O.positive(cur["_kernel.lengthscale_unconstrained"]).reshape(-1),
+                  "u_loc": cur["u_loc_unconstrained"], "u_scale_tril": O.lower_cholesky(cur["u_scale_tril_unconstrained"]),
+                  "noise": O.positive(cur["noise_unconstrained"]),
+                  "phi": O.simplex_rows(cur["_word_topic_matrix_map_unconstrained"])}
+        inp = ref_oracle_inputs(spec, params, d, d["svi_eps"][step])
+        opt.zero_grad()
+        out = O.elbo_terms(inp, params, twice=False)
+        out["loss"].backward()
+        opt.step()
+        ref = float(d["svi_losses"][step])
+        assert abs(out["loss"].item() - ref) <= 1e-4 * abs(ref), (step, out["loss"].item(), ref)
+    for k, v in leaves.items():
+        ref = torch.from_numpy(d["svi_param/" + k]).double()
+        if k == "u_scale_tril_unconstrained":
+            ref, v = ref.tril(), v.detach().tril()
+        # Adam moves every coordinate by ~lr per step whatever the gradient's size, so a coordinate whose gradient
+        # is fp32 noise (the reference ran in fp32) may go the other way: compare the bulk; the ill-conditioned
+        # kernel hyper-parameter / inducing-point gradients get the looser bound
+        diff = (v.detach() - ref).abs()
+        assert diff.mean().item() < (5e-3 if k in HYPER else 2e-4) and diff.max().item() < 6.1e-2, \
+            (k, diff.mean().item(), diff.max().item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the drop-in class against the same fixtures
+# ---------------------------------------------------------------------------------------------------------------
+def _dropin(spec, d, device):
+    import gdrf_b200
+    kcls = getattr(gdrf_b200, spec["kernel_class"])
+    D = spec["D"]
+    ls = torch.tensor([0.35, 0.5, 0.7][:D]) if spec["ard"] else torch.tensor(0.4)       # make_ref_fixtures.run_case
+    return gdrf_b200.SparseMultinomialGDRF(
+        num_observation_categories=spec["V"], num_topic_categories=spec["K"], world=[(0.0, 1.0)] * D,
+        kernel=kcls(D, variance=torch.tensor(1.3), lengthscale=ls), dirichlet_param=0.1, n_points=spec["n_points"],
+        fixed_inducing_points=spec["fixed"], inducing_init="grid", device=device, jitter=spec["jitter"],
+        maxjitter=spec["maxjitter"])
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_dropin_constructor_initialises_like_the_reference(name):
+    """Same parameter names and the same initial (unconstrained) values as ``SparseGDRF.__init__``
+    (sparse_gdrf.py:51-122) produced under the shim -- host logic, no GPU involved."""
+    spec, u, d = load_ref_fixture(name)
+    m = _dropin(spec, d, "cpu")
+    mine = dict(m.named_parameters())
+    ref_names = {k[len("init/"):] for k in d.files if k.startswith("init/")}
+    assert set(mine) == ref_names
+    for k in ref_names:
+        ref = torch.from_numpy(d["init/" + k])
+        assert mine[k].shape == ref.shape, k
+        assert torch.allclose(mine[k].detach(), ref, rtol=1e-4, atol=2e-5), (k, (mine[k] - ref).abs().max().item())
+    if spec["fixed"]:
+        assert torch.allclose(m._inducing_points, torch.from_numpy(d["Z_fixed"]), atol=1e-7)
+    assert torch.equal(m._dirichlet_param.cpu(), torch.from_numpy(d["beta"]))
+
+
+def _load_params(m, d, prefix="param/"):
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            p.copy_(torch.from_numpy(d[prefix + k]).to(p.device))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_CASES)
+def test_cuda_dropin_reproduces_reference_loss_gradients_and_evaluation(name):
+    spec, u, d = load_ref_fixture(name)
+    m = _dropin(spec, d, "cuda:0")
+    _load_params(m, d)
+    xs, ws = torch.from_numpy(d["xs"]).cuda(), torch.from_numpy(d["ws"]).cuda()
+    loss = -m.elbo(xs, ws, eps=torch.from_numpy(d["eps"]).cuda())
+    loss.backward()
+    assert abs(loss.item() - float(d["loss"])) <= TERM_TOL * abs(float(d["loss"]))
+    # the fp64 oracle arbitrates: we must be at least as close to it as 3x the reference's own fp32 run is
+    o64, g64 = _oracle_loss_and_grads(spec, u, d, d["eps"], torch.float64)
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(d["grad/" + k])
+        e_ref = O.rel_err(ref, g64[k])
+        e = O.rel_err(p.grad.cpu(), g64[k])
+        assert e <= max(1e-4, 3.0 * e_ref) * (10.0 if k in HYPER else 1.0), (k, e, e_ref)
+    with torch.no_grad():
+        assert O.rel_err(m.log_topic_probs(xs).cpu(), torch.from_numpy(d["log_topic_probs"])) < 1e-4
+        assert abs(m.perplexity(xs, ws).item() - float(d["perplexity"])) < 1e-4 * float(d["perplexity"])
+        assert O.rel_err(m.word_probs(xs).cpu(), torch.from_numpy(d["word_probs"])) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name", REF_CASES)
+def test_cuda_svi_follows_reference_trajectory(name, fused):
+    """The reference's 3 SVI steps (Adam lr 0.01, its own draws) through SVI + torch.optim.Adam and through FusedSVI."""
+    from gdrf_b200 import SVI, FusedSVI
+    spec, u, d = load_ref_fixture(name)
+    m = _dropin(spec, d, "cuda:0")
+    _load_params(m, d)
+    xs, ws = torch.from_numpy(d["xs"]).cuda(), torch.from_numpy(d["ws"]).cuda()
+    svi = FusedSVI(m, lr=0.01) if fused else SVI(m.model, m.guide, torch.optim.Adam(m.parameters(), lr=0.01), loss=None)
+    for step, ref in enumerate(d["svi_losses"]):
+        eps = torch.from_numpy(d["svi_eps"][step]).cuda()
+        loss = svi.step(xs, ws, eps=eps) if fused else svi.step(xs=xs, ws=ws, subsample=False, eps=eps)
+        assert abs(loss - float(ref)) <= 1e-4 * abs(float(ref)), (step, loss, float(ref))
+    if fused:
+        svi.write_back()
+    for k, p in m.named_parameters():
+        ref, v = torch.from_numpy(d["svi_param/" + k]), p.detach().cpu()
+        if k == "u_scale_tril_unconstrained":
+            ref, v = ref.tril(), v.tril()
+        diff = (v - ref).abs()
+        assert diff.mean().item() < (5e-3 if k in HYPER else 2e-4) and diff.max().item() < 6.1e-2, \
+            (k, diff.mean().item(), diff.max().item())
