@@ -16,6 +16,7 @@ registers nothing to sample, so ``pyro.infer.SVI(model=scale(m.model), guide=sca
 """
 from __future__ import annotations
 
+import warnings
 from typing import Callable, List, Optional, Tuple, Union
 
 import torch
@@ -84,6 +85,8 @@ class SparseMultinomialGDRF(nn.Module):
         self._upper_bounds = torch.tensor([b[1] for b in world], dtype=torch.float32, device=self.device)
         self._delta_bounds = self._upper_bounds - self._lower_bounds
         self._n_dims = len(world)
+        self._unit_world = all(float(b[0]) == 0.0 and float(b[1]) == 1.0 for b in world)
+        self._warned_world = False
         self._kernel = kernel.to(self.device)
         self._kernel_kind = kernel_kind(kernel)
         if isinstance(dirichlet_param, float):
@@ -211,6 +214,13 @@ class SparseMultinomialGDRF(nn.Module):
         xs = xs.to(self.device)
         self._check_Xnew_shape(xs)
         x = xs.float() if scaled else self._scaled(xs)
+        if not scaled and not self._unit_world and not self._warned_world:
+            # sparse_gdrf.py:380: the reference's guide applies scale() a second time on top of scale_decorator, so
+            # for a world other than [0,1]^D its guide and model condition on different inputs.  train() always
+            # hands over unit-cube data (train_script.py:263-271); here xs is scaled once for both.
+            warnings.warn("world is not the unit cube: the reference's guide rescales xs twice "
+                          "(sparse_gdrf.py:380); gdrf_b200 scales once for model and guide")
+            self._warned_world = True
         N = x.shape[0]
         if eps is None:
             eps = torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
