@@ -239,7 +239,10 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
   PlaneMat stm = plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp);
-  k_kxz_planes<<<dim3(p.MB, RT), 256, 0, st>>>(in->xs + n0 * p.D, nc, in->z, p.M, hp, kxz);
+#define GDRF_KXZ_PLANES(DT, KID) \
+  k_kxz_planes<DT, KID><<<dim3(p.MB, RT), 256, 0, st>>>(in->xs + n0 * p.D, nc, in->z, p.M, hp, kxz)
+  GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_PLANES);
+#undef GDRF_KXZ_PLANES
   LAUNCH_CHECK();
   {
     G1::Params g{};
@@ -599,8 +602,11 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     }
     {
       const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
-      k_kxz_backward<<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
-          dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc);
+#define GDRF_KXZ_BACKWARD(DT, KID)                                                                  \
+  k_kxz_backward<DT, KID><<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(      \
+      dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc)
+      GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_BACKWARD);
+#undef GDRF_KXZ_BACKWARD
       LAUNCH_CHECK();
     }
     {

@@ -16,47 +16,66 @@ struct Hyper {
 enum { ACC_LP_MU = 0, ACC_LQ = 1, ACC_LL = 2, ACC_LP_PHI = 3, ACC_DNOISE = 4, ACC_DVAR = 5, ACC_DLS = 6,
        ACC_HEAD = ACC_DLS + MAX_D + 2 };
 
+// compile-time (input dimension, kernel id) dispatch for the two kernels that evaluate k(x, z) element by element;
+// DT = 0 keeps the run-time dimension loop (D > 3)
+#define GDRF_DISPATCH_DK(D_, KID_, F_)                                                        \
+  switch ((KID_) * 4 + ((D_) <= 3 ? (D_) : 0)) {                                               \
+    case 0: F_(0, 0); break;  case 1: F_(1, 0); break;  case 2: F_(2, 0); break;  case 3: F_(3, 0); break;   \
+    case 4: F_(0, 1); break;  case 5: F_(1, 1); break;  case 6: F_(2, 1); break;  case 7: F_(3, 1); break;   \
+    case 8: F_(0, 2); break;  case 9: F_(1, 2); break;  case 10: F_(2, 2); break; case 11: F_(3, 2); break;  \
+    default:                                                                                   \
+      switch ((D_) <= 3 ? (D_) : 0) {                                                          \
+        case 0: F_(0, 3); break;  case 1: F_(1, 3); break;  case 2: F_(2, 3); break;  default: F_(3, 3); break; \
+      }                                                                                        \
+  }
+
 // ---------------------------------------------------------------------------------------------
 // K_xz = k(xs, Z) for one 128 x 64 block per CTA, written as three bf16 planes.
 // Direct differences (more accurate than the reference's |x|^2 - 2xz + |z|^2 expansion,
 // pyro Isotropy._square_scaled_dist); padding rows / columns are written as zeros.
+// 8 lanes per 128-byte row; a thread keeps its 8 inducing points in registers.
 // ---------------------------------------------------------------------------------------------
+template <int DT, int KID>
 __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs, int nc, const float* __restrict__ Z,
                                                     int M, Hyper hp, PlaneMat kxz) {
-  __shared__ float zs[MAX_D][64 + 4];      // [d][c], row padded: column groups g*8 land in different banks
-  __shared__ float inv_ls[MAX_D];
-  const int cb = blockIdx.x, rt = blockIdx.y, D = hp.D;
-  for (int t = threadIdx.x; t < 64 * D; t += blockDim.x) {
-    const int c = t / D, d = t - c * D;
-    const int col = cb * 64 + c;
-    zs[d][c + (c >> 5) * 4] = (col < M) ? Z[col * D + d] : 0.f;
+  constexpr int DM = DT ? DT : MAX_D;
+  const int D = DT ? DT : hp.D;
+  const int cb = blockIdx.x, rt = blockIdx.y;
+  const int g = threadIdx.x & 7;
+  float il[DM], zl[8][DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d)
+    if (d < D) il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = cb * 64 + g * 8 + j;
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) zl[j][d] = (col < M) ? Z[col * D + d] : 0.f;
   }
-  if (threadIdx.x < D) inv_ls[threadIdx.x] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : threadIdx.x];
-  __syncthreads();
   const float var = hp.variance[0];
+  const int cvalid = min(8, M - (cb * 64 + g * 8));     // columns of this thread inside M (may be <= 0)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    const int r = w * 32 + (threadIdx.x >> 3), g = threadIdx.x & 7;   // 8 lanes per 128-byte row
+    const int r = w * 32 + (threadIdx.x >> 3);
     const int n = rt * 128 + r;
-    float x[MAX_D];
-    if (n < nc)
-      for (int d = 0; d < D; ++d) x[d] = xs[(long long)n * D + d];
+    float x[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) x[d] = (n < nc) ? xs[(long long)n * D + d] : 0.f;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      float val = 0.f;
-      if (n < nc && cb * 64 + c < M) {
-        float r2 = 0.f;
-        for (int d = 0; d < D; ++d) {
-          const float t = (x[d] - zs[d][c + (c >> 5) * 4]) * inv_ls[d];
+      float r2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DM; ++d)
+        if (d < D) {
+          const float t = (x[d] - zl[j][d]) * il[d];     // difference first: exact for nearby points
           r2 = fmaf(t, t, r2);
         }
-        float k, dk;
-        kernel_eval<float>(hp.kid, r2, k, dk);
-        val = var * k;
-      }
-      v[j] = val;
+      float k, dk;
+      kernel_eval<float>(KID, r2, k, dk);
+      v[j] = (n < nc && j < cvalid) ? var * k : 0.f;
     }
     uint4 pk[3];
     split8<3>(v, pk);
@@ -662,29 +681,35 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
 
 // ---------------------------------------------------------------------------------------------
 // Chain dKxz into the kernel hyper-parameters and the inducing points:
-//   K_xz[n,i] = variance * f(r2),  r2 = sum_d ((x_nd - z_id) / l_d)^2
-//   dvariance += dKxz f ;  dl_d += dKxz variance f' (-2 (x-z)^2 / l_d^3) ;  dZ[i,d] += dKxz variance f' (-2 (x-z)/l_d^2)
-// grid (Mp/128, row splits), 128 threads = columns i.
+//   K_xz[n,i] = variance * f(r2),  r2 = sum_d ((x_nd - z_id) / l_d)^2 = sum_d t_d^2
+//   dvariance += dKxz f ;  dl_d += dKxz variance f' (-2 t_d^2 / l_d) ;  dZ[i,d] += dKxz variance f' (-2 t_d / l_d)
+// grid (Mp/128, row splits), 128 threads = columns i; the constant factors (variance, -2 / l_d) are applied once
+// per thread after the row loop.
 // ---------------------------------------------------------------------------------------------
+template <int DT, int KID>
 __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ dkxz, int Mp, const float* __restrict__ xs,
                                                       int nc, const float* __restrict__ Z, int M, Hyper hp,
                                                       int rows_per_cta, double* __restrict__ dz_acc,
                                                       double* __restrict__ acc) {
+  constexpr int DM = DT ? DT : MAX_D;
+  const int D = DT ? DT : hp.D;
   __shared__ double scratch[32];
-  __shared__ float xsh[128][MAX_D];
+  __shared__ float xsh[128][DM];
   const int i = blockIdx.x * 128 + threadIdx.x;
-  const int D = hp.D;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(nc, r0 + rows_per_cta);
-  float z[MAX_D], il[MAX_D];
-  for (int d = 0; d < D; ++d) {
-    z[d] = (i < M) ? Z[i * D + d] : 0.f;
-    il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
-  }
-  const float var = hp.variance[0];
-  float dz[MAX_D], dl[MAX_D];
-  for (int d = 0; d < D; ++d) dz[d] = dl[d] = 0.f;
+  float z[DM], il[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d)
+    if (d < D) {
+      il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+      z[d] = (i < M) ? Z[i * D + d] : 0.f;
+    }
+  float dz[DM], dl[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) dz[d] = dl[d] = 0.f;
   float dv = 0.f;
+  const float* col = dkxz + i;
   for (int rb = r0; rb < r1; rb += 128) {
     __syncthreads();
     for (int t = threadIdx.x; t < 128 * D; t += 128) {
@@ -694,37 +719,48 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
     __syncthreads();
     const int rn = min(128, r1 - rb);
     if (i < M) {
+#pragma unroll 4
       for (int r = 0; r < rn; ++r) {
-        const float g = dkxz[(long long)(rb + r) * Mp + i];
-        float diff[MAX_D];
+        const float g = col[(long long)(rb + r) * Mp];
+        float t[DM];
         float r2 = 0.f;
-        for (int d = 0; d < D; ++d) {
-          diff[d] = (xsh[r][d] - z[d]) * il[d];
-          r2 = fmaf(diff[d], diff[d], r2);
-        }
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+          if (d < D) {
+            t[d] = (xsh[r][d] - z[d]) * il[d];
+            r2 = fmaf(t[d], t[d], r2);
+          }
         float k, dk;
-        kernel_eval<float>(hp.kid, r2, k, dk);
+        kernel_eval<float>(KID, r2, k, dk);
         dv = fmaf(g, k, dv);
-        const float h = g * var * dk;
-        for (int d = 0; d < D; ++d) {
-          dz[d] = fmaf(h, -2.f * diff[d] * il[d], dz[d]);
-          dl[d] = fmaf(h, -2.f * diff[d] * diff[d] * il[d], dl[d]);
-        }
+        const float h = g * dk;
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+          if (d < D) {
+            const float ht = h * t[d];
+            dz[d] += ht;
+            dl[d] = fmaf(ht, t[d], dl[d]);
+          }
       }
     }
   }
+  const float c = -2.f * hp.variance[0];
   if (i < M)
-    for (int d = 0; d < D; ++d) atomicAdd(&dz_acc[i * D + d], (double)dz[d]);
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) atomicAdd(&dz_acc[i * D + d], (double)(c * il[d] * dz[d]));
   double dvs = block_sum((double)dv, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dvs);
   if (hp.ls_dim == 1) {
     float s = 0.f;
-    for (int d = 0; d < D; ++d) s += dl[d];
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+      if (d < D) s += c * il[d] * dl[d];
     double t = block_sum((double)s, scratch);
     if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS], t);
   } else {
     for (int d = 0; d < D; ++d) {
-      double t = block_sum((double)dl[d], scratch);
+      double t = block_sum((double)(c * il[d] * dl[d]), scratch);
       if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS + d], t);
     }
   }
