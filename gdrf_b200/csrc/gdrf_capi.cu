@@ -203,22 +203,33 @@ int dispatch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long 
 #undef LK
 }
 
+// topics per lane for the 8-lanes-per-observation kernels (K <= 128)
+#define GDRF_DISPATCH_KQ(K_, F_)       \
+  do {                                 \
+    if ((K_) <= 8) F_(1);              \
+    else if ((K_) <= 16) F_(2);        \
+    else if ((K_) <= 32) F_(4);        \
+    else if ((K_) <= 64) F_(8);        \
+    else F_(16);                       \
+  } while (0)
+
 int launch_du(const Plan& p, PlaneMat w, int RT, void* ws, int sms, cudaStream_t st) {
-  int tiles_per_cta = (RT * p.MB + 2 * sms - 1) / (2 * sms);
+  int tiles_per_cta = (RT * p.MB + 4 * sms - 1) / (4 * sms);   // ~4 CTAs per SM: one CTA's tile rebuild hides under another's FMAs
   if (tiles_per_cta < 1) tiles_per_cta = 1;
   const dim3 grid(p.MB, (RT + tiles_per_cta - 1) / tiles_per_cta);
   const float* g = at<float>(ws, p.g_loc);
   double* du = at<double>(ws, p.du);
-#define DU(KQ)                                                                                              \
+#define DU(KGP)                                                                                             \
   do {                                                                                                      \
-    const size_t smem = sizeof(float) * (128 * 65 + 4 * KQ * 128);                                          \
-    CU(cudaFuncSetAttribute(k_du<KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    k_du<KQ><<<grid, 256, smem, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);                   \
+    const size_t smem = sizeof(float) * (128 * 68 + 8 * KGP * 128);                                         \
+    CU(cudaFuncSetAttribute(k_du<KGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    k_du<KGP><<<grid, 256, smem, st>>>(w, g, p.K, p.M, RT, (int)p.ncp, tiles_per_cta, du);                  \
   } while (0)
-  if (p.K <= 16) DU(4);
-  else if (p.K <= 32) DU(8);
-  else if (p.K <= 64) DU(16);
-  else DU(32);
+  if (p.K <= 8) DU(1);
+  else if (p.K <= 16) DU(2);
+  else if (p.K <= 32) DU(4);
+  else if (p.K <= 64) DU(8);
+  else DU(16);
 #undef DU
   LAUNCH_CHECK();
   return 0;
@@ -249,7 +260,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
     g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
     { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
   }
-  k_floc<<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
+  k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
     CU(cudaMemsetAsync(at<double>(ws, p.q), 0, sizeof(double) * (size_t)p.K * p.ncp, st));
@@ -552,17 +563,24 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
     if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
-    k_obs_prepare<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<double>(ws, p.floc),
-                                      at<double>(ws, p.q), at<double>(ws, p.wsq), in->eps, hp,
-                                      at<float>(ws, p.phisum), at<float>(ws, p.fvar),
-                                      at<float>(ws, p.theta), at<float>(ws, p.srow), acc);
+#define GDRF_OBS_PREPARE(KQ)                                                                                   \
+  k_obs_prepare<KQ><<<(nc + 31) / 32, 256, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps,                \
+                                                    at<double>(ws, p.floc), at<double>(ws, p.q), at<double>(ws, p.wsq), \
+                                                    in->eps, hp, at<float>(ws, p.phisum), at<float>(ws, p.fvar),   \
+                                                    at<float>(ws, p.theta), at<float>(ws, p.srow), acc)
+    GDRF_DISPATCH_KQ(K, GDRF_OBS_PREPARE);
+#undef GDRF_OBS_PREPARE
     LAUNCH_CHECK();
     if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
-    k_obs_finalize<<<RT, 128, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta),
-                                       at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),
-                                       at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq), in->eps, hp,
-                                       at<float>(ws, p.phisum), at<float>(ws, p.g_loc), at<float>(ws, p.g2),
-                                       at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, RT * 128);
+#define GDRF_OBS_FINALIZE(KQ)                                                                                  \
+  k_obs_finalize<KQ><<<RT * 4, 256, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta), \
+                                             at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),    \
+                                             at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq),   \
+                                             in->eps, hp, at<float>(ws, p.phisum), at<float>(ws, p.g_loc),         \
+                                             at<float>(ws, p.g2), at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, \
+                                             RT * 128)
+    GDRF_DISPATCH_KQ(K, GDRF_OBS_FINALIZE);
+#undef GDRF_OBS_FINALIZE
     LAUNCH_CHECK();
     if (!want_grad) continue;
     {

@@ -141,28 +141,29 @@ __global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Li
 
 // ---------------------------------------------------------------------------------------------
 // f_loc[k, n] = sum_m W[n, m] u_loc[k, m]   (pyro conditional: loc = W @ v_2D; mean function is zero,
-// abstract_gdrf.py:17-18).  grid (RT, ceil(K/16)), 128 threads = rows; W rebuilt from its 3 planes.
+// abstract_gdrf.py:17-18).  grid (RT, ceil(K/KT)), 128 threads = rows; W rebuilt from its 3 planes.
 // ---------------------------------------------------------------------------------------------
+template <int KT>   // topics per CTA
 __global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restrict__ u, int K, int M, int MB,
                                               double* __restrict__ floc, int ncp) {
-  __shared__ float us[16][64];
+  __shared__ __align__(16) float us[KT][64];
   const int rt = blockIdx.x, kg = blockIdx.y;
   const int n = rt * 128 + threadIdx.x;
-  double acc[16];     // fp32 dot products over 64 columns, summed across blocks in fp64
+  double acc[KT];     // fp32 dot products over 64 columns, summed across blocks in fp64
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int i = 0; i < KT; ++i) acc[i] = 0.0;
   for (int mb = 0; mb < MB; ++mb) {
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * 64; t += 128) {
+    for (int t = threadIdx.x; t < KT * 64; t += 128) {
       const int kk = t >> 6, c = t & 63;
-      const int k = kg * 16 + kk, m = mb * 64 + c;
+      const int k = kg * KT + kk, m = mb * 64 + c;
       us[kk][c] = (k < K && m < M) ? u[(long long)k * M + m] : 0.f;
     }
     __syncthreads();
-    float part[16];
+    float part[KT];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) part[i] = 0.f;
-#pragma unroll 1
+    for (int i = 0; i < KT; ++i) part[i] = 0.f;
+#pragma unroll 2
     for (int g = 0; g < 8; ++g) {
       uint4 pk[3];
 #pragma unroll
@@ -170,19 +171,25 @@ __global__ void __launch_bounds__(128) k_floc(PlaneMat w, const float* __restric
       float wv[8];
       join8<3>(pk, wv);
 #pragma unroll
-      for (int kk = 0; kk < 16; ++kk) {
-        float a = part[kk];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a = fmaf(wv[j], us[kk][g * 8 + j], a);
-        part[kk] = a;
+      for (int kk = 0; kk < KT; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&us[kk][g * 8]);       // warp-wide broadcast loads
+        const float4 b = *reinterpret_cast<const float4*>(&us[kk][g * 8 + 4]);
+        float t = fmaf(wv[0], a.x, part[kk]);
+        t = fmaf(wv[1], a.y, t);
+        t = fmaf(wv[2], a.z, t);
+        t = fmaf(wv[3], a.w, t);
+        t = fmaf(wv[4], b.x, t);
+        t = fmaf(wv[5], b.y, t);
+        t = fmaf(wv[6], b.z, t);
+        part[kk] = fmaf(wv[7], b.w, t);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] += (double)part[i];
+    for (int i = 0; i < KT; ++i) acc[i] += (double)part[i];
   }
 #pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    const int k = kg * 16 + kk;
+  for (int kk = 0; kk < KT; ++kk) {
+    const int k = kg * KT + kk;
     if (k < K) floc[(long long)k * ncp + n] = acc[kk];
   }
 }
@@ -197,15 +204,13 @@ __global__ void k_phisum(const float* __restrict__ phi, int K, int V, float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per observation: marginal variance, reparameterised draw, the two Normal terms, topic softmax.
-//   var0 = clamp(variance - |W_n|^2, 0); f_var = var0 + q            (pyro conditional)
-//   mu = f_loc + f_var * eps   (guide Normal(f_loc, f_var): the variance is used as the scale,
-//                               sparse_gdrf.py:403-405)
-//   lq    += -log f_var - .5 log 2pi - .5 eps^2                                 (guide, :403-405)
-//   lp_mu += -log(f_var+noise) - .5 log 2pi - (f_var eps)^2 / (2 (f_var+noise)^2) (model, :354-357)
-//   theta = softmax_k(mu)  (abstract_gdrf.py:21-22);  s = sum_k theta_k * rowsum(phi)_k
+// Per observation, before the likelihood pass (sparse_gdrf.py:354-361, 403-405):
+//   f_var = var0 + q,  mu = f_loc + f_var * eps  (the variance is the Normal's scale),
+//   log q(mu), log p(mu) with scale f_var + noise,  theta = softmax_k(mu),  s = sum_k theta_k rowsum(phi)_k
+// 8 lanes per observation (lane j owns topics j, j + 8, ...; K <= 8 KQ), 256 threads = 32 observations.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_obs_prepare(int nc, int ncp, int K, long long n0, long long n_stride,
+template <int KQ>
+__global__ void __launch_bounds__(256) k_obs_prepare(int nc, int ncp, int K, long long n0, long long n_stride,
                                                      const double* __restrict__ floc, const double* __restrict__ q,
                                                      const double* __restrict__ wsq, const float* __restrict__ eps,
                                                      Hyper hp, const float* __restrict__ phisum,
@@ -214,45 +219,57 @@ __global__ void __launch_bounds__(128) k_obs_prepare(int nc, int ncp, int K, lon
   // fp64 throughout: mu carries f_var * eps with f_var = O(variance), and d ll / d mu = O(counts), so fp32
   // rounding of mu (1e-5 absolute) alone would cost 1e-4 ... 1e-3 relative in the gradients.
   __shared__ double scratch[32];
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x & 7;
+  const int n = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = n < nc;
   double lq = 0.0, lp = 0.0;
-  if (n < nc) {
-    const double var = hp.variance[0], noise = hp.noise[0];
-    const double var0 = fmax(var - wsq[n], 0.0);
-    const double HALF_LOG_2PI = 0.91893853320467274178;
-    double mx = -INFINITY;
-    for (int k = 0; k < K; ++k) {
+  double m[KQ];
+  const double var = hp.variance[0], noise = hp.noise[0];
+  const double var0 = live ? fmax(var - wsq[n], 0.0) : 0.0;
+  const double HALF_LOG_2PI = 0.91893853320467274178;
+  double mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) {
+    const int k = sub + 8 * i;
+    m[i] = -INFINITY;
+    if (live && k < K) {
       const long long o = (long long)k * ncp + n;
       const double fv = var0 + q[o];
       const double e = eps[(long long)k * n_stride + n0 + n];
       const double d = fv * e;
-      const double m = floc[o] + d;
+      m[i] = floc[o] + d;
       const double sp = fv + noise;
       lq += -log(fv) - HALF_LOG_2PI - 0.5 * e * e;
       const double z = d / sp;
       lp += -log(sp) - HALF_LOG_2PI - 0.5 * z * z;
       fvar[o] = (float)fv;
-      mx = fmax(mx, m);
+      mx = fmax(mx, m[i]);
     }
-    double den = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const long long o = (long long)k * ncp + n;
-      const double fv = var0 + q[o];
-      const double m = floc[o] + fv * (double)eps[(long long)k * n_stride + n0 + n];
-      den += exp(m - mx);
-    }
-    const double inv = 1.0 / den;
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const long long o = (long long)k * ncp + n;
-      const double fv = var0 + q[o];
-      const double m = floc[o] + fv * (double)eps[(long long)k * n_stride + n0 + n];
-      const double t = exp(m - mx) * inv;
-      theta[o] = (float)t;
-      s += t * (double)phisum[k];
-    }
-    srow[n] = (float)s;
   }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  double den = 0.0;
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) {
+    m[i] = (live && sub + 8 * i < K) ? exp(m[i] - mx) : 0.0;
+    den += m[i];
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const double inv = live ? 1.0 / den : 0.0;
+  double sr = 0.0;
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) {
+    const int k = sub + 8 * i;
+    if (live && k < K) {
+      const double t = m[i] * inv;
+      theta[(long long)k * ncp + n] = (float)t;
+      sr += t * (double)phisum[k];
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  if (live && sub == 0) srow[n] = (float)sr;
   lq = block_sum(lq, scratch);
   lp = block_sum(lp, scratch);
   if (threadIdx.x == 0) {
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
             const float4 r4 = *reinterpret_cast<const float4*>(rt + (lane + 32 * j) * LK_TS + n0);
 #pragma unroll
             for (int a = 0; a < KPW; ++a)
-              dacc[a][j] += t4[a].x * r4.x + t4[a].y * r4.y + t4[a].z * r4.z + t4[a].w * r4.w;
+              dacc[a][j] = fmaf(t4[a].x, r4.x, fmaf(t4[a].y, r4.y, fmaf(t4[a].z, r4.z, fmaf(t4[a].w, r4.w, dacc[a][j]))));
           }
         }
       }
@@ -475,8 +492,10 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
 //   dELBO/dnoise = -1/sp + eps^2 f_var^2 / sp^3
 //   gv0_n = sum_k dELBO/df_var  where the clamp var0 = max(variance - |W_n|^2, 0) is inactive
 // Outputs: g_loc = g_mu, g2 = 2 dELBO/df_var (row scale of R), gv0; padding rows are zeroed.
+// 8 lanes per observation (lane j owns topics j, j + 8, ...; K <= 8 KQ), 256 threads = 32 observations.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, long long n0, long long n_stride,
+template <int KQ>
+__global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, long long n0, long long n_stride,
                                                       const float* __restrict__ theta, const float* __restrict__ srow,
                                                       const float* __restrict__ g1, const float* __restrict__ arow,
                                                       const float* __restrict__ cnt, const float* __restrict__ fvar,
@@ -486,55 +505,69 @@ __global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, lo
                                                       float* __restrict__ gv0, double* __restrict__ ck,
                                                       double* __restrict__ acc, int npad) {
   __shared__ double scratch[32];
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  __shared__ float cks[8 * KQ];
+  const int sub = threadIdx.x & 7;
+  const int n = blockIdx.x * 32 + (threadIdx.x >> 3);
+  for (int t = threadIdx.x; t < 8 * KQ; t += 256) cks[t] = 0.f;
+  __syncthreads();
   double dnoise = 0.0, dvar = 0.0, llc = 0.0;
-  const bool live = n < nc;
-  float ratio = 0.f;
-  if (live) {
-    const float noise = hp.noise[0], var = hp.variance[0];
-    ratio = arow[n] / srow[n];
-    float dot = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float gt = g1[(long long)n * K + k] - ratio * phisum[k];
-      dot = fmaf(theta[(long long)k * ncp + n], gt, dot);
+  const bool live = n < nc;          // the 8 lanes of an observation agree; shuffles stay outside any branch
+  const float noise = hp.noise[0], var = hp.variance[0];
+  const float ratio = live ? arow[n] / srow[n] : 0.f;
+  float gt[KQ], th[KQ];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) {
+    const int k = sub + 8 * i;
+    gt[i] = th[i] = 0.f;
+    if (live && k < K) {
+      gt[i] = g1[(long long)n * K + k] - ratio * phisum[k];
+      th[i] = theta[(long long)k * ncp + n];
+      dot = fmaf(th[i], gt[i], dot);
     }
-    float gsum = 0.f, dn = 0.f;
-    for (int k = 0; k < K; ++k) {
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  float gsum = 0.f, dn = 0.f;
+#pragma unroll
+  for (int i = 0; i < KQ; ++i) {
+    const int k = sub + 8 * i;
+    if (k < K && n < npad) {
       const long long o = (long long)k * ncp + n;
-      const float gt = g1[(long long)n * K + k] - ratio * phisum[k];
-      const float gm = theta[o] * (gt - dot);
-      const float fv = fvar[o];
-      const float e = eps[(long long)k * n_stride + n0 + n];
-      const float sp = fv + noise;
-      const float isp = 1.f / sp;
-      const float e2 = e * e;
-      const float gv = -isp - e2 * fv * noise * isp * isp * isp + 1.f / fv + gm * e;
-      dn += -isp + e2 * fv * fv * isp * isp * isp;
-      g_loc[o] = gm;
+      float gm = 0.f, gv = 0.f;
+      if (live) {
+        gm = th[i] * (gt[i] - dot);
+        const float fv = fvar[o];
+        const float e = eps[(long long)k * n_stride + n0 + n];
+        const float sp = fv + noise;
+        const float isp = 1.f / sp;
+        const float e2 = e * e;
+        gv = -isp - e2 * fv * noise * isp * isp * isp + 1.f / fv + gm * e;
+        dn += -isp + e2 * fv * fv * isp * isp * isp;
+        gsum += gv;
+        // c_k = sum_n theta[n][k] A_n / s_n  (the renormalisation term of d ll / d phi)
+        atomicAdd(&cks[k], th[i] * ratio);
+      }
+      g_loc[o] = gm;            // padding rows are zeroed
       g2[o] = 2.f * gv;
-      gsum += gv;
     }
-    const bool clamp_open = ((double)var - wsq[n]) >= 0.0;
-    const float g0 = clamp_open ? gsum : 0.f;
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+  dnoise = dn;
+  if (sub == 0 && n < npad) {
+    float g0 = 0.f;
+    if (live) {
+      const bool clamp_open = ((double)var - wsq[n]) >= 0.0;
+      g0 = clamp_open ? gsum : 0.f;
+      dvar = g0;
+      llc = lgamma((double)cnt[n] + 1.0);
+    }
     gv0[n] = g0;
-    dnoise = dn;
-    dvar = g0;
-    llc = lgamma((double)cnt[n] + 1.0);
-  } else if (n < npad) {
-    for (int k = 0; k < K; ++k) {
-      const long long o = (long long)k * ncp + n;
-      g_loc[o] = 0.f;
-      g2[o] = 0.f;
-    }
-    gv0[n] = 0.f;
   }
-  // c_k = sum_n theta[n][k] A_n / s_n  (the renormalisation term of d ll / d phi)
-  for (int k = 0; k < K; ++k) {
-    float c = live ? theta[(long long)k * ncp + n] * ratio : 0.f;
-    c = warp_sum(c);
-    if (lane == 0 && c != 0.f) atomicAdd(&ck[k], (double)c);
-  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += 256)
+    if (cks[k] != 0.f) atomicAdd(&ck[k], (double)cks[k]);
   dnoise = block_sum(dnoise, scratch);
   dvar = block_sum(dvar, scratch);
   llc = block_sum(llc, scratch);
@@ -546,22 +579,28 @@ __global__ void __launch_bounds__(128) k_obs_finalize(int nc, int ncp, int K, lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// du_loc[k, m] += sum_n g_loc[k, n] W[n, m]          grid (MB, row splits), 256 threads.
-// Each 128 x 64 block of W is rebuilt from its planes into shared memory once; g_loc's [K][128] slab sits
-// beside it; thread (m, kq) owns topics kq, kq + 4, ...
+// du_loc[k, m] += sum_n g_loc[k, n] W[n, m]     (adjoint of f_loc = W u_loc^T)
+// One CTA per (64-column block, slab of row tiles).  Each 128-row tile of W is rebuilt from its planes into shared
+// memory; a thread owns a 4-column x 8-topic register tile and a slice of the rows (4 rows per step: one 16-byte
+// load of g per topic serves 4 rows).  256 threads = 16 column groups x KGP topic groups x (16 / KGP) row slices.
+// dynamic shared memory: W tile [128][68] | g tile [8 KGP][128]   (reused for the cross-slice reduction)
 // ---------------------------------------------------------------------------------------------
-template <int KQ>   // topics per thread = KQ (K <= 4 * KQ)
+template <int KGP>   // topic groups of 8 (power of two, K <= 8 KGP <= 128)
 __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict__ g_loc, int K, int M, int RT, int ncp,
                                             int tiles_per_cta, double* __restrict__ du_acc) {
-  extern __shared__ float du_smem[];
-  float* wsm = du_smem;                 // [128][65]
-  float* gsm = du_smem + 128 * 65;      // [4 * KQ][128]
+  constexpr int RS = 16 / KGP;            // row slices
+  constexpr int WS = 68;                  // W tile row stride (floats)
+  extern __shared__ __align__(16) float du_smem[];
+  float* wsm = du_smem;                   // [128][WS]
+  float* gsm = du_smem + 128 * WS;        // [8 * KGP][128]
   const int cb = blockIdx.x;
-  const int c = threadIdx.x & 63, kq = threadIdx.x >> 6;
-  const int m = cb * 64 + c;
-  float a[KQ];
+  const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4;
+  const int kq = tq % KGP, slice = tq / KGP;
+  float a[8][4];
 #pragma unroll
-  for (int i = 0; i < KQ; ++i) a[i] = 0.f;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
   const int rt0 = blockIdx.y * tiles_per_cta;
   const int rt1 = min(RT, rt0 + tiles_per_cta);
   for (int rt = rt0; rt < rt1; ++rt) {
@@ -573,26 +612,45 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
       for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, rt * 128 + r, cb * 64 + g * 8));
       float v[8];
       join8<3>(pk, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wsm[r * 65 + g * 8 + j] = v[j];
+      *reinterpret_cast<float4*>(wsm + r * WS + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(wsm + r * WS + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    for (int t = threadIdx.x; t < 4 * KQ * 128; t += 256) {
+    for (int t = threadIdx.x; t < 8 * KGP * 128; t += 256) {
       const int k = t >> 7, r = t & 127;
       gsm[t] = (k < K) ? g_loc[(long long)k * ncp + rt * 128 + r] : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < 128; ++r) {
-      const float wv = wsm[r * 65 + c];
+#pragma unroll 2
+    for (int r0 = 4 * slice; r0 < 128; r0 += 4 * RS) {
+      float4 wv[4];
 #pragma unroll
-      for (int i = 0; i < KQ; ++i) a[i] = fmaf(gsm[(kq + 4 * i) * 128 + r], wv, a[i]);
+      for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const float4*>(wsm + (r0 + q) * WS + cg * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 gv = *reinterpret_cast<const float4*>(gsm + (kq * 8 + i) * 128 + r0);
+        a[i][0] = fmaf(gv.x, wv[0].x, fmaf(gv.y, wv[1].x, fmaf(gv.z, wv[2].x, fmaf(gv.w, wv[3].x, a[i][0]))));
+        a[i][1] = fmaf(gv.x, wv[0].y, fmaf(gv.y, wv[1].y, fmaf(gv.z, wv[2].y, fmaf(gv.w, wv[3].y, a[i][1]))));
+        a[i][2] = fmaf(gv.x, wv[0].z, fmaf(gv.y, wv[1].z, fmaf(gv.z, wv[2].z, fmaf(gv.w, wv[3].z, a[i][2]))));
+        a[i][3] = fmaf(gv.x, wv[0].w, fmaf(gv.y, wv[1].w, fmaf(gv.z, wv[2].w, fmaf(gv.w, wv[3].w, a[i][3]))));
+      }
     }
   }
-  if (m < M) {
+  // cross-slice reduction through shared memory: red[slice][k][64]
+  __syncthreads();
+  float* red = du_smem;
 #pragma unroll
-    for (int i = 0; i < KQ; ++i) {
-      const int k = kq + 4 * i;
-      if (k < K) atomicAdd(&du_acc[(long long)k * M + m], (double)a[i]);
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(red + ((slice * 8 * KGP) + kq * 8 + i) * 64 + cg * 4) =
+        make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+  __syncthreads();
+  for (int t = threadIdx.x; t < 8 * KGP * 64; t += 256) {
+    const int k = t >> 6, c = t & 63;
+    const int m = cb * 64 + c;
+    if (k < K && m < M) {
+      float v = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < RS; ++sl) v += red[(sl * 8 * KGP + k) * 64 + c];
+      atomicAdd(&du_acc[(long long)k * M + m], (double)v);
     }
   }
 }
@@ -632,12 +690,14 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
 
 // ---------------------------------------------------------------------------------------------
 // dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 3 planes
-// grid (MB, RT), 256 threads.
+// grid (MB, RT), 256 threads: 8 lanes per 128-byte row, a thread owns 4 rows (r, r + 32, r + 64, r + 96) x 8 columns;
+// the rank-K update runs first on a 4 x 8 register tile (per topic: one 16-byte load of g for the 4 rows, two of u).
+// dynamic shared memory: u block [K][72] | g tile [K][128] with row r stored at (r & 31) * 4 + (r >> 5)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __restrict__ dw, int Mp,
                                                      const float* __restrict__ g_loc, const float* __restrict__ gv0,
                                                      const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt) {
-  extern __shared__ float dwf_smem[];
+  extern __shared__ __align__(16) float dwf_smem[];
   float* us = dwf_smem;            // [K][72]: 64 columns, the upper 32 shifted by 4 words (bank spread)
   float* gs = us + K * 72;         // [K][128]
   const int cb = blockIdx.x, rt = blockIdx.y;
@@ -647,15 +707,34 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     us[k * 72 + c + (c >> 5) * 4] = (m < M) ? u[(long long)k * M + m] : 0.f;
   }
   for (int t = threadIdx.x; t < K * 128; t += 256) {
-    const int k = t >> 7, r = t & 127;
+    const int k = t >> 7, pos = t & 127;
+    const int r = (pos >> 2) + 32 * (pos & 3);
     gs[t] = g_loc[(long long)k * ncp + rt * 128 + r];
   }
   __syncthreads();
-#pragma unroll 1
-  for (int wv = 0; wv < 4; ++wv) {
-    const int r = wv * 32 + (threadIdx.x >> 3), g = threadIdx.x & 7;   // 8 lanes per 128-byte row
-    const int n = rt * 128 + r;
-    const int col = cb * 64 + g * 8;
+  const int rr = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int col = cb * 64 + g * 8;
+  float v[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+  const float* up = us + g * 8 + (g >> 2) * 4;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 gk = *reinterpret_cast<const float4*>(gs + k * 128 + rr * 4);
+    const float4 u0 = *reinterpret_cast<const float4*>(up + k * 72);
+    const float4 u1 = *reinterpret_cast<const float4*>(up + k * 72 + 4);
+    const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    const float gq[4] = {gk.x, gk.y, gk.z, gk.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[q][j] = fmaf(gq[q], uu[j], v[q][j]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = rt * 128 + rr + 32 * q;
     uint4 pk[3];
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) pk[pl] = *reinterpret_cast<const uint4*>(w.elem(pl, n, col));
@@ -663,17 +742,13 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     join8<3>(pk, wj);
     const float4* src = reinterpret_cast<const float4*>(dw + (long long)n * Mp + col);
     const float4 d0 = src[0], d1 = src[1];
-    float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
     const float m2g = -2.f * gv0[n];
+    float o8[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(m2g, wj[j], v[j]);
-    for (int k = 0; k < K; ++k) {
-      const float gk = gs[k * 128 + r];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(gk, us[k * 72 + g * 8 + (g >> 2) * 4 + j], v[j]);
-    }
+    for (int j = 0; j < 8; ++j) o8[j] = fmaf(m2g, wj[j], dd[j]) + v[q][j];
     uint4 out[3];
-    split8<3>(v, out);
+    split8<3>(o8, out);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, n, col)) = out[pl];
   }
