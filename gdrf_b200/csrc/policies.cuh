@@ -250,7 +250,7 @@ struct G3 {
 struct G4 {
   static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
-  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr int PA = 2, PB = 2, BN = 128;   // 16-bit operands: see DESIGN.md (hyper-gradient probe)
   static constexpr bool A_MN = false, B_MN = true;
   struct Params {
     PlaneMat dwt, linv;
@@ -286,7 +286,7 @@ struct G4 {
 struct G5 {
   static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
-  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr int PA = 2, PB = 2, BN = 128;   // 16-bit operands, like G4
   static constexpr bool A_MN = true, B_MN = true;
   struct Params {
     PlaneMat dwt, w;

@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 3 planes
+// dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 2 planes
 // grid (MB, RT), 256 threads: 8 lanes per 128-byte row, a thread owns 4 rows (r, r + 32, r + 64, r + 96) x 8 columns;
 // the rank-K update runs first on a 4 x 8 register tile (per topic: one 16-byte load of g for the 4 rows, two of u).
 // dynamic shared memory: u block [K][72] | g tile [K][128] with row r stored at (r & 31) * 4 + (r >> 5)
@@ -747,10 +747,10 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     float o8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o8[j] = fmaf(m2g, wj[j], dd[j]) + v[q][j];
-    uint4 out[3];
-    split8<3>(o8, out);
+    uint4 out[2];      // G4 and G5 consume dWtot as two bf16 planes
+    split8<2>(o8, out);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, n, col)) = out[pl];
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, n, col)) = out[pl];
   }
 }
 
