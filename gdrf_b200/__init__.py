@@ -2,10 +2,10 @@
 from . import _lib
 from .elbo import (GDRFElbo, elbo_value_and_grads, elbo_value_and_grads_from_host, marginal_mean, marginal_moments,
                    perplexity_from_mean)
-from .kernels import KERNEL_DICT, RBF, Exponential, Matern32, Matern52
+from .kernels import KERNEL_DICT, RBF, Exponential, Matern32, Matern52, RationalQuadratic
 from .models import SparseMultinomialGDRF
 from .svi import SVI, FusedSVI, shard_bounds
 
 __all__ = ["GDRFElbo", "elbo_value_and_grads", "elbo_value_and_grads_from_host", "marginal_mean", "marginal_moments",
            "perplexity_from_mean", "RBF", "Matern32",
-           "Matern52", "Exponential", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "FusedSVI", "shard_bounds", "_lib"]
+           "Matern52", "Exponential", "RationalQuadratic", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "FusedSVI", "shard_bounds", "_lib"]

@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgdrf_b200.so")
 
-KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3}
+KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3, "rationalquadratic": 4}
 
 FLAG_WANT_GRAD = 1
 FLAG_INCLUDE_PRIOR = 2
@@ -34,7 +34,7 @@ class Shape(ctypes.Structure):
 
 class Inputs(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("xs", "ws", "eps", "z", "variance", "lengthscale", "u_loc",
-                                        "u_scale_tril", "noise", "phi", "beta")]
+                                        "u_scale_tril", "noise", "phi", "beta", "scale_mixture")]
 
 
 class Outputs(ctypes.Structure):

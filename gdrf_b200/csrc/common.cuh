@@ -144,13 +144,15 @@ __host__ __device__ __forceinline__ long long round_up_ll(long long a, long long
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // kernel ids shared with the host API (include/gdrf_b200.h)
-enum { KERNEL_RBF = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2, KERNEL_EXPONENTIAL = 3 };
+enum { KERNEL_RBF = 0, KERNEL_MATERN32 = 1, KERNEL_MATERN52 = 2, KERNEL_EXPONENTIAL = 3, KERNEL_RQ = 4 };
 constexpr int MAX_D = 8;
 
-// k(r2)/variance and d k / d r2 / variance for the three isotropic kernels
-// (pyro.contrib.gp.kernels.{RBF,Matern32,Matern52,Exponential}; r = sqrt(r2 + 1e-12) as in Isotropy._scaled_dist)
+// k(r2)/variance and d k / d r2 / variance for the isotropic kernels
+// (pyro.contrib.gp.kernels.{RBF,Matern32,Matern52,Exponential,RationalQuadratic}; r = sqrt(r2 + 1e-12) as in
+// Isotropy._scaled_dist).  RationalQuadratic: (1 + r2 / (2 alpha))^(-alpha); *dk_dalpha is written for it only.
 template <typename T>
-__host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_dr2) {
+__host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_dr2, T alpha = T(1),
+                                                     T* dk_dalpha = nullptr) {
   if (kid == KERNEL_RBF) {
     k = exp(T(-0.5) * r2);
     dk_dr2 = T(-0.5) * k;
@@ -164,10 +166,16 @@ __host__ __device__ __forceinline__ void kernel_eval(int kid, T r2, T& k, T& dk_
     T e = exp(-s);
     k = (T(1) + s + (T(5) / T(3)) * r2) * e;
     dk_dr2 = -(T(5) / T(6)) * (T(1) + s) * e;
-  } else {   // Exponential: exp(-r)
+  } else if (kid == KERNEL_EXPONENTIAL) {   // exp(-r)
     T r = sqrt(r2 + T(1e-12));
     k = exp(-r);
     dk_dr2 = T(-0.5) * k / r;
+  } else {                                  // RationalQuadratic
+    const T b = T(1) + (T(0.5) / alpha) * r2;
+    const T lb = log(b);
+    k = exp(-alpha * lb);
+    dk_dr2 = T(-0.5) * k / b;
+    if (dk_dalpha) *dk_dalpha = k * (r2 / (T(2) * alpha * b) - lb);
   }
 }
 

@@ -87,7 +87,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   if (s->v < 1) return fail(1, "v must be positive%s");
   if (s->n_local < 0) return fail(1, "n_local must be non-negative%s");
   if (s->ls_dim != 1 && s->ls_dim != s->d) return fail(1, "ls_dim must be 1 or d%s");
-  if (s->kernel_id < 0 || s->kernel_id > 3) return fail(1, "unknown kernel_id%s");
+  if (s->kernel_id < 0 || s->kernel_id > 4) return fail(1, "unknown kernel_id%s");
   if (s->chunk_rows < 0 || (s->chunk_rows % 256) != 0) return fail(1, "chunk_rows must be a multiple of 256%s");
   p.D = s->d; p.M = s->m; p.K = s->k; p.V = s->v;
   p.Mp = (int)round_up_ll(s->m, 256);
@@ -158,7 +158,7 @@ PlaneMat plane_mat(void* ws, size_t off, long long rows, long long cols) {
 
 Hyper make_hyper(const gdrf_shape* s, const gdrf_inputs* in) {
   Hyper hp;
-  hp.variance = in->variance; hp.lengthscale = in->lengthscale; hp.noise = in->noise;
+  hp.variance = in->variance; hp.lengthscale = in->lengthscale; hp.noise = in->noise; hp.alpha = in->scale_mixture;
   hp.ls_dim = s->ls_dim; hp.kid = s->kernel_id; hp.D = s->d;
   return hp;
 }
@@ -399,7 +399,7 @@ int gdrf_constrain(const gdrf_shape* s, const float* theta_u, float* theta_c, in
   if (int e = check_device()) return e;
   if (!theta_u || !theta_c) return fail(1, "null pointer argument%s");
   cudaStream_t st = (cudaStream_t)stream;
-  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim);
+  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim, s->kernel_id == KERNEL_RQ);
   long long blocks = (f.total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_constrain<<<(int)blocks, 256, 0, st>>>(f, theta_u, theta_c, learn_z);
@@ -418,7 +418,7 @@ int gdrf_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, co
   if (!theta_u || !theta_c || !grad || !m || !v || !row_scratch) return fail(1, "null pointer argument%s");
   if (step < 1) return fail(1, "step counts from 1%s");
   cudaStream_t st = (cudaStream_t)stream;
-  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim);
+  const FlatLayout f = make_layout(p.K, p.M, p.V, p.D, s->ls_dim, s->kernel_id == KERNEL_RQ);
   k_phi_rowdot<<<p.K, 256, 0, st>>>(theta_c + f.oP, grad + f.oP, p.V, row_scratch);
   LAUNCH_CHECK();
   AdamHyper h;
@@ -450,7 +450,7 @@ int gdrf_grad_elems(const gdrf_shape* s, int64_t* out_elems) {
   if (int e = make_plan(s, p)) return e;
   if (!out_elems) return fail(1, "null out pointer%s");
   *out_elems = (int64_t)s->k * s->m * s->m + (int64_t)s->k * s->m + (int64_t)s->k * s->v + (int64_t)s->m * s->d + 2 +
-               s->ls_dim;
+               s->ls_dim + (s->kernel_id == KERNEL_RQ ? 1 : 0);
   return 0;
 }
 
@@ -460,6 +460,7 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   if (int e = make_plan(s, p)) return e;
   if (int e = check_device()) return e;
   if (!in || !ws || !dev_status) return fail(1, "null pointer argument%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
   if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
   if (njitter < 0) return fail(1, "njitter must be >= 0%s");
   cudaStream_t st = (cudaStream_t)stream;
@@ -511,6 +512,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   if (int e = make_plan(s, p)) return e;
   if (int e = check_device()) return e;
   if (!in || !out || !ws || !out->terms) return fail(1, "null pointer argument%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
   if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
   const bool want_grad = (s->flags & GDRF_FLAG_WANT_GRAD) != 0;
   if (want_grad && !out->grad) return fail(1, "GDRF_FLAG_WANT_GRAD needs out->grad%s");
@@ -667,8 +669,9 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     LAUNCH_CHECK();
   }
   if (want_grad) {
-    const long long small = (long long)K * M + (long long)K * p.V + (long long)M * p.D + 2 + s->ls_dim;
-    k_assemble<<<(int)((small + 255) / 256), 256, 0, st>>>(K, M, p.V, p.D, s->ls_dim, include_prior, in->phi, in->beta,
+    const int has_alpha = s->kernel_id == KERNEL_RQ ? 1 : 0;
+    const long long small = (long long)K * M + (long long)K * p.V + (long long)M * p.D + 2 + s->ls_dim + has_alpha;
+    k_assemble<<<(int)((small + 255) / 256), 256, 0, st>>>(K, M, p.V, p.D, s->ls_dim, has_alpha, include_prior, in->phi, in->beta,
                                                            acc, at<double>(ws, p.ck), at<double>(ws, p.du),
                                                            at<double>(ws, p.dphi), at<double>(ws, p.dz), out->grad);
     LAUNCH_CHECK();
@@ -700,6 +703,7 @@ int gdrf_marginal_moments(const gdrf_shape* s, const gdrf_inputs* in, float* out
   if (int e = make_plan(s, p)) return e;
   if (int e = check_device()) return e;
   if (!in || !ws || !out_floc) return fail(1, "null pointer argument%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
   if (out_fvar && !in->u_scale_tril) return fail(1, "the marginal variance needs u_scale_tril%s");
   if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
   cudaStream_t st = (cudaStream_t)stream;

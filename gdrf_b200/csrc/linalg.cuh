@@ -48,7 +48,7 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
       r2 = r2 < T(0) ? T(0) : r2;
     }
     T k, dk;
-    kernel_eval<T>(hp.kid, r2, k, dk);
+    kernel_eval<T>(hp.kid, r2, k, dk, hp.kid == KERNEL_RQ ? (T)hp.alpha[0] : T(1));
     val = (T)hp.variance[0] * k;
     if (i == j) {
       if (sizeof(T) == 8) {
@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(128) k_kuu_backward(const double* __restrict__
   __shared__ double scratch[32];
   const int a = blockIdx.x;       // one block per row a; threads stride over j
   const int D = hp.D;
-  double dz[MAX_D], dl[MAX_D], dv = 0.0;
+  double dz[MAX_D], dl[MAX_D], dv = 0.0, da = 0.0;
+  const double alpha = hp.kid == KERNEL_RQ ? (double)hp.alpha[0] : 1.0;
   double za[MAX_D], il[MAX_D];
   for (int d = 0; d < D; ++d) {
     dz[d] = dl[d] = 0.0;
@@ -283,9 +284,10 @@ __global__ void __launch_bounds__(128) k_kuu_backward(const double* __restrict__
       diff[d] = (za[d] - (double)Z[j * D + d]) * il[d];
       r2 += diff[d] * diff[d];
     }
-    double k, dk;
-    kernel_eval<double>(hp.kid, r2, k, dk);
+    double k, dk, dka = 0.0;
+    kernel_eval<double>(hp.kid, r2, k, dk, alpha, &dka);
     dv += g * k;
+    da += g * var * dka;
     const double h = g * var * dk;
     for (int d = 0; d < D; ++d) {
       dz[d] += 4.0 * h * diff[d] * il[d];          // both arguments of k(z_a, z_j) move with z_a
@@ -298,6 +300,10 @@ __global__ void __launch_bounds__(128) k_kuu_backward(const double* __restrict__
   }
   dv = block_sum(dv, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dv);
+  if (hp.kid == KERNEL_RQ) {
+    da = block_sum(da, scratch);
+    if (threadIdx.x == 0) atomicAdd(&acc[ACC_DALPHA], da);
+  }
   if (hp.ls_dim == 1) {
     double t = 0.0;
     for (int d = 0; d < D; ++d) t += dl[d];

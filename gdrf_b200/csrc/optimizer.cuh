@@ -4,7 +4,7 @@
 // gdrf/models/sparse_gdrf.py:79-112 and abstract_gdrf.py:79-84).
 //
 // Flat layout (same order as the gradient of gdrf_elbo_step):
-//   [ u_scale_tril K*M*M | u_loc K*M | phi K*V | Z M*D | variance 1 | lengthscale ls_dim | noise 1 ]
+//   [ u_scale_tril K*M*M | u_loc K*M | phi K*V | Z M*D | variance 1 | lengthscale ls_dim | noise 1 | scale_mixture 0/1 ]
 // unconstrained -> constrained:  lower_cholesky (strict lower free, exp on the diagonal, zero above), identity,
 // row softmax (stacked simplex), sigmoid (interval(0,1) per dimension) and exp (positive).
 #pragma once
@@ -17,7 +17,7 @@ struct FlatLayout {
   int K, M, V, D, ls_dim;
 };
 
-__host__ __device__ inline FlatLayout make_layout(int K, int M, int V, int D, int ls_dim) {
+__host__ __device__ inline FlatLayout make_layout(int K, int M, int V, int D, int ls_dim, int has_alpha = 0) {
   FlatLayout f;
   f.K = K; f.M = M; f.V = V; f.D = D; f.ls_dim = ls_dim;
   f.oS = 0;
@@ -27,7 +27,7 @@ __host__ __device__ inline FlatLayout make_layout(int K, int M, int V, int D, in
   f.oV = f.oZ + (long long)M * D;
   f.oL = f.oV + 1;
   f.oN = f.oL + ls_dim;
-  f.total = f.oN + 1;
+  f.total = f.oN + 1 + has_alpha;   // RationalQuadratic's scale_mixture (positive, like the other kernel parameters)
   return f;
 }
 

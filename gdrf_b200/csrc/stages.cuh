@@ -9,24 +9,30 @@ struct Hyper {
   const float* variance;     // [1]
   const float* lengthscale;  // [ls_dim]
   const float* noise;        // [1]
+  const float* alpha;        // [1] RationalQuadratic scale_mixture (NULL otherwise)
   int ls_dim, kid, D;
 };
 
 // slots of the fp64 accumulator block (zeroed at the start of every step)
 enum { ACC_LP_MU = 0, ACC_LQ = 1, ACC_LL = 2, ACC_LP_PHI = 3, ACC_DNOISE = 4, ACC_DVAR = 5, ACC_DLS = 6,
-       ACC_HEAD = ACC_DLS + MAX_D + 2 };
+       ACC_DALPHA = ACC_DLS + MAX_D, ACC_HEAD = ACC_DLS + MAX_D + 2 };
 
 // compile-time (input dimension, kernel id) dispatch for the two kernels that evaluate k(x, z) element by element;
 // DT = 0 keeps the run-time dimension loop (D > 3)
-#define GDRF_DISPATCH_DK(D_, KID_, F_)                                                        \
-  switch ((KID_) * 4 + ((D_) <= 3 ? (D_) : 0)) {                                               \
-    case 0: F_(0, 0); break;  case 1: F_(1, 0); break;  case 2: F_(2, 0); break;  case 3: F_(3, 0); break;   \
-    case 4: F_(0, 1); break;  case 5: F_(1, 1); break;  case 6: F_(2, 1); break;  case 7: F_(3, 1); break;   \
-    case 8: F_(0, 2); break;  case 9: F_(1, 2); break;  case 10: F_(2, 2); break; case 11: F_(3, 2); break;  \
-    default:                                                                                   \
-      switch ((D_) <= 3 ? (D_) : 0) {                                                          \
-        case 0: F_(0, 3); break;  case 1: F_(1, 3); break;  case 2: F_(2, 3); break;  default: F_(3, 3); break; \
-      }                                                                                        \
+#define GDRF_DISPATCH_D_(D_, KID_, F_)                                                  \
+  switch ((D_) <= 3 ? (D_) : 0) {                                                          \
+    case 1: F_(1, KID_); break;                                                            \
+    case 2: F_(2, KID_); break;                                                            \
+    case 3: F_(3, KID_); break;                                                            \
+    default: F_(0, KID_); break;                                                           \
+  }
+#define GDRF_DISPATCH_DK(D_, KID_, F_)                                                     \
+  switch (KID_) {                                                                          \
+    case 0: GDRF_DISPATCH_D_(D_, 0, F_); break;                                            \
+    case 1: GDRF_DISPATCH_D_(D_, 1, F_); break;                                            \
+    case 2: GDRF_DISPATCH_D_(D_, 2, F_); break;                                            \
+    case 3: GDRF_DISPATCH_D_(D_, 3, F_); break;                                            \
+    default: GDRF_DISPATCH_D_(D_, 4, F_); break;                                           \
   }
 
 // ---------------------------------------------------------------------------------------------
@@ -54,6 +60,7 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
       if (d < D) zl[j][d] = (col < M) ? Z[col * D + d] : 0.f;
   }
   const float var = hp.variance[0];
+  const float alpha = (KID == KERNEL_RQ) ? hp.alpha[0] : 1.f;
   const int cvalid = min(8, M - (cb * 64 + g * 8));     // columns of this thread inside M (may be <= 0)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
           r2 = fmaf(t, t, r2);
         }
       float k, dk;
-      kernel_eval<float>(KID, r2, k, dk);
+      kernel_eval<float>(KID, r2, k, dk, alpha);
       v[j] = (n < nc && j < cvalid) ? var * k : 0.f;
     }
     uint4 pk[3];
@@ -783,7 +790,8 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
   float dz[DM], dl[DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d) dz[d] = dl[d] = 0.f;
-  float dv = 0.f;
+  float dv = 0.f, da = 0.f;
+  const float alpha = (KID == KERNEL_RQ) ? hp.alpha[0] : 1.f;
   const float* col = dkxz + i;
   for (int rb = r0; rb < r1; rb += 128) {
     __syncthreads();
@@ -805,9 +813,10 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
             t[d] = (xsh[r][d] - z[d]) * il[d];
             r2 = fmaf(t[d], t[d], r2);
           }
-        float k, dk;
-        kernel_eval<float>(KID, r2, k, dk);
+        float k, dk, dka = 0.f;
+        kernel_eval<float>(KID, r2, k, dk, alpha, &dka);
         dv = fmaf(g, k, dv);
+        if (KID == KERNEL_RQ) da = fmaf(g, dka, da);
         const float h = g * dk;
 #pragma unroll
         for (int d = 0; d < DM; ++d)
@@ -826,6 +835,10 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
       if (d < D) atomicAdd(&dz_acc[i * D + d], (double)(c * il[d] * dz[d]));
   double dvs = block_sum((double)dv, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dvs);
+  if (KID == KERNEL_RQ) {
+    double das = block_sum((double)(hp.variance[0] * da), scratch);
+    if (threadIdx.x == 0) atomicAdd(&acc[ACC_DALPHA], das);
+  }
   if (hp.ls_dim == 1) {
     float s = 0.f;
 #pragma unroll
@@ -861,14 +874,15 @@ __global__ void k_prior(const float* __restrict__ phi, const float* __restrict__
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_LP_PHI], lgamma(sb) + t);
 }
 
-__global__ void k_assemble(int K, int M, int V, int D, int ls_dim, int include_prior, const float* __restrict__ phi,
+__global__ void k_assemble(int K, int M, int V, int D, int ls_dim, int has_alpha, int include_prior,
+                           const float* __restrict__ phi,
                            const float* __restrict__ beta, const double* __restrict__ acc,
                            const double* __restrict__ ck, const double* __restrict__ du_acc,
                            const double* __restrict__ dphi_acc, const double* __restrict__ dz_acc,
                            float* __restrict__ grad) {
   const long long oS = 0, oU = oS + (long long)K * M * M, oP = oU + (long long)K * M, oZ = oP + (long long)K * V,
                   oV = oZ + (long long)M * D, oL = oV + 1, oN = oL + ls_dim;
-  const long long total = (long long)K * M + (long long)K * V + (long long)M * D + 2 + ls_dim;
+  const long long total = (long long)K * M + (long long)K * V + (long long)M * D + 2 + ls_dim + has_alpha;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     long long idx = t;
@@ -887,7 +901,9 @@ __global__ void k_assemble(int K, int M, int V, int D, int ls_dim, int include_p
     if (idx == 0) { grad[oV] = (float)acc[ACC_DVAR]; continue; }
     idx -= 1;
     if (idx < ls_dim) { grad[oL + idx] = (float)acc[ACC_DLS + idx]; continue; }
-    grad[oN] = (float)acc[ACC_DNOISE];
+    idx -= ls_dim;
+    if (idx == 0) { grad[oN] = (float)acc[ACC_DNOISE]; continue; }
+    grad[oN + 1] = (float)acc[ACC_DALPHA];
   }
 }
 

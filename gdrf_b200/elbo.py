@@ -61,7 +61,7 @@ class _Call:
     """Validated shapes + ctypes structs for one evaluation."""
 
     def __init__(self, xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
-                 kernel_id, n_offset, flags, chunk_rows):
+                 kernel_id, n_offset, flags, chunk_rows, scale_mixture=None):
         if not xs.is_cuda:
             raise RuntimeError("gdrf_b200 runs on an sm_100a CUDA device only; there is no CPU path")
         dev = xs.device
@@ -89,7 +89,10 @@ class _Call:
             z=_f32(Z, "Z", dev), variance=_f32(variance.reshape(1), "variance", dev),
             lengthscale=_f32(ls, "lengthscale", dev), u_loc=_f32(u_loc, "u_loc", dev),
             u_scale_tril=None if u_scale_tril is None else _f32(u_scale_tril, "u_scale_tril", dev), noise=_f32(noise.reshape(1), "noise", dev),
-            phi=_f32(phi, "phi", dev), beta=_f32(beta, "beta", dev))
+            phi=_f32(phi, "phi", dev), beta=_f32(beta, "beta", dev),
+            scale_mixture=None if scale_mixture is None else _f32(scale_mixture.reshape(1), "scale_mixture", dev))
+        if int(kernel_id) == _lib.KERNEL_IDS["rationalquadratic"] and scale_mixture is None:
+            raise ValueError("the RationalQuadratic kernel needs its scale_mixture parameter")
         if self.t["ws"].device != dev:
             raise ValueError("ws must live on the same device as xs")
         self.shape = _lib.Shape(n_local=N, n_offset=int(n_offset), n_eps=int(eps.shape[1]), d=D, m=M, k=K, v=V,
@@ -132,11 +135,16 @@ class _Call:
 
 
 def split_grad(flat: torch.Tensor, K: int, M: int, V: int, D: int, ls_dim: int):
-    """Views into the flat gradient of include/gdrf_b200.h:gdrf_outputs."""
+    """Views into the flat gradient of include/gdrf_b200.h:gdrf_outputs (``scale_mixture`` is present when the
+    buffer carries the RationalQuadratic kernel's extra entry)."""
     o = 0
     out = {}
-    for name, shape in (("u_scale_tril", (K, M, M)), ("u_loc", (K, M)), ("phi", (K, V)), ("Z", (M, D)),
-                        ("variance", ()), ("lengthscale", (ls_dim,)), ("noise", ())):
+    base = K * M * M + K * M + K * V + M * D + 2 + ls_dim
+    blocks = [("u_scale_tril", (K, M, M)), ("u_loc", (K, M)), ("phi", (K, V)), ("Z", (M, D)),
+              ("variance", ()), ("lengthscale", (ls_dim,)), ("noise", ())]
+    if flat.numel() > base:
+        blocks.append(("scale_mixture", ()))
+    for name, shape in blocks:
         n = 1
         for s in shape:
             n *= s
@@ -147,7 +155,7 @@ def split_grad(flat: torch.Tensor, K: int, M: int, V: int, D: int, ls_dim: int):
 
 class GDRFElbo(torch.autograd.Function):
     """elbo_over_n = GDRFElbo.apply(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta,
-    eps, kernel_id, jitter, maxjitter, n_global, n_offset, include_prior, flags, chunk_rows)"""
+    eps, kernel_id, jitter, maxjitter, n_global, n_offset, include_prior, flags, chunk_rows, scale_mixture)"""
 
     last_terms: Optional[torch.Tensor] = None   # [lp_mu, lq, ll, lp_phi] of the most recent call (device, fp64)
     last_njitter: int = 0
@@ -155,11 +163,14 @@ class GDRFElbo(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
                 kernel_id: int, jitter: float, maxjitter: int, n_global: int, n_offset: int = 0,
-                include_prior: bool = True, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+                include_prior: bool = True, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0,
+                scale_mixture=None):
         fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
         call = _Call(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
-                     kernel_id, n_offset, fl, chunk_rows)
-        want_grad = any(ctx.needs_input_grad[i] for i in (2, 3, 4, 5, 6, 7, 8))
+                     kernel_id, n_offset, fl, chunk_rows, scale_mixture)
+        want_grad = any(ctx.needs_input_grad[i] for i in (2, 3, 4, 5, 6, 7, 8)) or \
+            (scale_mixture is not None and ctx.needs_input_grad[19])
+        ctx.sm_shape = None if scale_mixture is None else scale_mixture.shape
         GDRFElbo.last_njitter = call.prologue(jitter, maxjitter)
         terms, grad = call.step(want_grad)
         GDRFElbo.last_terms = terms
@@ -190,18 +201,21 @@ class GDRFElbo(torch.autograd.Function):
                                                g["u_scale_tril"], g["noise"].reshape(ctx.noise_shape), g["phi"])
         outs = [dZ, dvar, dls, du, dS, dnoise, dphi]
         outs = [o.to(dt) if ctx.needs_input_grad[i + 2] else None for i, (o, dt) in enumerate(zip(outs, ctx.dtypes))]
-        return (None, None, *outs, None, None, None, None, None, None, None, None, None, None)
+        dsm = None
+        if ctx.sm_shape is not None and ctx.needs_input_grad[19]:
+            dsm = g["scale_mixture"].reshape(ctx.sm_shape)
+        return (None, None, *outs, None, None, None, None, None, None, None, None, None, None, dsm)
 
 
 def elbo_value_and_grads(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
                          kernel: str = "rbf", jitter: float = 1e-8, maxjitter: int = 5, n_global=None,
                          n_offset: int = 0, include_prior: bool = True,
-                         flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+                         flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0, scale_mixture=None):
     """Direct (no autograd graph) evaluation: returns (terms fp64[4] = lp_mu, lq, ll, lp_phi;
     dict of d ELBO_sum / d constrained parameter; njitter)."""
     fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
     call = _Call(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta, eps,
-                 _lib.KERNEL_IDS[kernel], n_offset, fl, chunk_rows)
+                 _lib.KERNEL_IDS[kernel], n_offset, fl, chunk_rows, scale_mixture)
     nj = call.prologue(jitter, maxjitter)
     terms, grad = call.step(True)
     g = split_grad(grad, u_loc.shape[0], Z.shape[0], ws.shape[1], xs.shape[1], call.shape.ls_dim)
@@ -211,7 +225,8 @@ def elbo_value_and_grads(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, 
 def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, lengthscale, u_loc, u_scale_tril, noise,
                                    phi, beta, kernel: str = "rbf", jitter: float = 1e-8, maxjitter: int = 5,
                                    n_global=None, n_offset: int = 0, include_prior: bool = True,
-                                   flags: int = _lib.FLAG_CHOL_FP32_STATUS, n_sub: int = 8, staging=None):
+                                   flags: int = _lib.FLAG_CHOL_FP32_STATUS, n_sub: int = 8, staging=None,
+                                   scale_mixture=None):
     """Same result as :func:`elbo_value_and_grads`, with the observations (``xs_host`` [N, D] fp32, ``ws_host``
     [N, V] int32, ``eps_host`` [K, >= n_offset + N] fp32) living in pinned HOST memory.  The shard is cut into
     ``n_sub`` sub-shards; while sub-shard i is being evaluated on the compute stream, sub-shard i+1 is copied
@@ -238,7 +253,7 @@ def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, leng
         st_ = staging[i % 2]
         n = hi - lo
         calls.append(_Call(st_["xs"][:n], st_["ws"][:n], Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta,
-                           st_["eps"], _lib.KERNEL_IDS[kernel], 0, fl, 0))
+                           st_["eps"], _lib.KERNEL_IDS[kernel], 0, fl, 0, scale_mixture))
     free_ev = [torch.cuda.Event(), torch.cuda.Event()]
     copied_ev = [torch.cuda.Event() for _ in bounds]
 
@@ -276,7 +291,8 @@ def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, leng
 
 
 def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitter: float = 1e-8,
-                  maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0) -> torch.Tensor:
+                  maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0,
+                  scale_mixture=None) -> torch.Tensor:
     """f_loc [K, N] of ``log_topic_probs`` (sparse_gdrf.py:161-186)."""
     K, M = u_loc.shape
     N = xs.shape[0]
@@ -285,7 +301,7 @@ def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitt
     call = _Call(xs, dummy_ws, Z, variance, lengthscale, u_loc,
                  None, torch.ones((), device=dev), torch.ones(K, 1, device=dev),
                  torch.ones(K, 1, device=dev), torch.zeros(K, N, device=dev), _lib.KERNEL_IDS[kernel], 0, flags,
-                 chunk_rows)
+                 chunk_rows, scale_mixture)
     call.prologue(jitter, maxjitter)
     out = torch.empty(K, N, dtype=torch.float32, device=dev)
     _lib.check(_lib.load().gdrf_marginal_mean(ctypes.byref(call.shape), ctypes.byref(call.inputs), out.data_ptr(),
@@ -294,7 +310,8 @@ def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitt
 
 
 def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: str = "rbf", jitter: float = 1e-8,
-                     maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0):
+                     maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0,
+                     scale_mixture=None):
     """(f_loc, f_var), each [K, N]: ``SparseGDRF.forward(Xnew, full_cov=False)`` (sparse_gdrf.py:277-319)."""
     K, M = u_loc.shape
     N = xs.shape[0]
@@ -302,7 +319,7 @@ def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: 
     dummy_ws = torch.zeros(N, 1, dtype=torch.int32, device=dev)
     call = _Call(xs, dummy_ws, Z, variance, lengthscale, u_loc, u_scale_tril, torch.ones((), device=dev),
                  torch.ones(K, 1, device=dev), torch.ones(K, 1, device=dev), torch.zeros(K, N, device=dev),
-                 _lib.KERNEL_IDS[kernel], 0, flags, chunk_rows)
+                 _lib.KERNEL_IDS[kernel], 0, flags, chunk_rows, scale_mixture)
     call.prologue(jitter, maxjitter)
     floc = torch.empty(K, N, dtype=torch.float32, device=dev)
     fvar = torch.empty(K, N, dtype=torch.float32, device=dev)

@@ -63,8 +63,10 @@ class Isotropy(nn.Module):
         if self.kind == "matern32":
             s = (3 ** 0.5) * r
             return self.variance * (1 + s) * torch.exp(-s)
-        s = (5 ** 0.5) * r
-        return self.variance * (1 + s + (5.0 / 3.0) * r2) * torch.exp(-s)
+        if self.kind == "matern52":
+            s = (5 ** 0.5) * r
+            return self.variance * (1 + s + (5.0 / 3.0) * r2) * torch.exp(-s)
+        return self.variance * (1 + (0.5 / self.scale_mixture) * r2).pow(-self.scale_mixture)
 
 
 class RBF(Isotropy):
@@ -83,8 +85,23 @@ class Exponential(Isotropy):
     kind = "exponential"
 
 
-# train_script.py:93-99 also lists "rationalquadratic" (an extra learnable scale_mixture parameter): not accelerated.
-KERNEL_DICT = {"rbf": RBF, "matern32": Matern32, "matern52": Matern52, "exponential": Exponential}
+class RationalQuadratic(Isotropy):
+    """variance * (1 + r2 / (2 scale_mixture))^(-scale_mixture); ``scale_mixture`` is a third positive parameter."""
+    kind = "rationalquadratic"
+
+    def __init__(self, input_dim: int, variance=None, lengthscale=None, scale_mixture=None, active_dims=None):
+        super().__init__(input_dim, variance, lengthscale, active_dims)
+        sm = torch.tensor(1.0) if scale_mixture is None else torch.as_tensor(scale_mixture, dtype=torch.float32)
+        self.scale_mixture_unconstrained = nn.Parameter(sm.detach().clone().float().log())
+
+    @property
+    def scale_mixture(self) -> torch.Tensor:
+        return self.scale_mixture_unconstrained.exp()
+
+
+# train_script.py:93-99
+KERNEL_DICT = {"rbf": RBF, "matern32": Matern32, "matern52": Matern52, "exponential": Exponential,
+               "rationalquadratic": RationalQuadratic}
 
 
 def kernel_kind(kernel) -> str:
@@ -93,4 +110,4 @@ def kernel_kind(kernel) -> str:
     if name in KERNEL_IDS:
         return name
     raise NotImplementedError(f"kernel {type(kernel).__name__} is not accelerated "
-                              "(rbf, matern32, matern52, exponential are)")
+                              "(rbf, matern32, matern52, exponential, rationalquadratic are)")

@@ -175,6 +175,11 @@ class SparseMultinomialGDRF(nn.Module):
     def word_topic_matrix(self): return self._word_topic_matrix_map
 
     @property
+    def _scale_mixture(self):
+        """RationalQuadratic's third hyper-parameter (None for the other kernels)."""
+        return getattr(self._kernel, "scale_mixture", None)
+
+    @property
     def kernel_lengthscale(self): return self._kernel.lengthscale.detach().cpu().numpy()
 
     @property
@@ -231,7 +236,8 @@ class SparseMultinomialGDRF(nn.Module):
             return GDRFElbo.apply(x, ws, self._inducing_points, self._kernel.variance, self._kernel.lengthscale,
                                   self.u_loc, self.u_scale_tril, self.noise, self._word_topic_matrix_map,
                                   self._dirichlet_param, e, _lib.KERNEL_IDS[self._kernel_kind], self._jitter,
-                                  self._maxjitter, n_global, n_offset, include_prior, flags, chunk_rows)
+                                  self._maxjitter, n_global, n_offset, include_prior, flags, chunk_rows,
+                                  self._scale_mixture)
 
         if eps.dim() == 3:      # [P, K, N]: Trace_ELBO(num_particles=P) averages the particles' ELBOs
             return torch.stack([one(e) for e in eps]).mean()
@@ -260,7 +266,8 @@ class SparseMultinomialGDRF(nn.Module):
         xs = xs.to(self.device)
         self._check_Xnew_shape(xs)
         return marginal_mean(self._scaled(xs), self._inducing_points, self._kernel.variance,
-                             self._kernel.lengthscale, self.u_loc, self._kernel_kind, self._jitter, self._maxjitter)
+                             self._kernel.lengthscale, self.u_loc, self._kernel_kind, self._jitter, self._maxjitter,
+                             scale_mixture=self._scale_mixture)
 
     def topic_probs(self, xs):
         return torch.softmax(self.log_topic_probs(xs), -2).T
@@ -286,7 +293,7 @@ class SparseMultinomialGDRF(nn.Module):
         with torch.no_grad():
             return marginal_moments(self._scaled(Xnew), self._inducing_points, self._kernel.variance,
                                     self._kernel.lengthscale, self.u_loc, self.u_scale_tril, self._kernel_kind,
-                                    self._jitter, self._maxjitter)
+                                    self._jitter, self._maxjitter, scale_mixture=self._scale_mixture)
 
     def artifacts(self, xs, ws, all: bool = False):
         ret = {"kernel variance": self.kernel_variance, "kernel lengthscale": self.kernel_lengthscale}

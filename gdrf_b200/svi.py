@@ -86,6 +86,8 @@ class FusedSVI:
                      module._word_topic_matrix_map_unconstrained.reshape(-1), z_u.reshape(-1),
                      module._kernel.variance_unconstrained.reshape(-1), module._kernel.lengthscale_unconstrained.reshape(-1),
                      module.noise_unconstrained.reshape(-1)]
+            if module._kernel_kind == "rationalquadratic":
+                parts.append(module._kernel.scale_mixture_unconstrained.reshape(-1))
             self.theta_u = torch.cat([p.detach().float() for p in parts]).contiguous().to(dev)
         self.theta_c = torch.empty_like(self.theta_u)
         self.mom1 = torch.zeros_like(self.theta_u)
@@ -118,7 +120,8 @@ class FusedSVI:
         terms, g, _ = elbo_value_and_grads(x, ws.to(m.device), c["Z"], c["variance"], c["lengthscale"], c["u_loc"],
                                            c["u_scale_tril"], c["noise"], c["phi"], m._dirichlet_param, eps,
                                            kernel=m._kernel_kind, jitter=m._jitter, maxjitter=m._maxjitter,
-                                           n_global=n_global, n_offset=n_offset, include_prior=(rank == 0))
+                                           n_global=n_global, n_offset=n_offset, include_prior=(rank == 0),
+                                           scale_mixture=c.get("scale_mixture"))
         flat = g["u_scale_tril"].reshape(-1).as_strided((self.theta_u.numel(),), (1,))
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -143,6 +146,8 @@ class FusedSVI:
                        (m._inducing_points_unconstrained if self.learn_z else None, M * D),
                        (m._kernel.variance_unconstrained, 1), (m._kernel.lengthscale_unconstrained, self.ls_dim),
                        (m.noise_unconstrained, 1)]
+            if m._kernel_kind == "rationalquadratic":
+                targets.append((m._kernel.scale_mixture_unconstrained, 1))
             for p, n in targets:
                 if p is not None:
                     p.copy_(self.theta_u[o:o + n].view_as(p))

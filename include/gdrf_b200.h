@@ -27,7 +27,8 @@ extern "C" {
 
 typedef struct CUstream_st* gdrf_stream_t; /* == cudaStream_t */
 
-enum { GDRF_KERNEL_RBF = 0, GDRF_KERNEL_MATERN32 = 1, GDRF_KERNEL_MATERN52 = 2, GDRF_KERNEL_EXPONENTIAL = 3 };
+enum { GDRF_KERNEL_RBF = 0, GDRF_KERNEL_MATERN32 = 1, GDRF_KERNEL_MATERN52 = 2, GDRF_KERNEL_EXPONENTIAL = 3,
+       GDRF_KERNEL_RATIONALQUADRATIC = 4 };
 
 enum {
   GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
@@ -56,7 +57,7 @@ typedef struct gdrf_shape {
   int32_t m;          /* inducing points (<= 4096)                                                            */
   int32_t k;          /* topics (<= 128)                                                                      */
   int32_t v;          /* observation categories                                                               */
-  int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT rbf/matern32/matern52/exponential)  */
+  int32_t kernel_id;  /* GDRF_KERNEL_*   (train_script.py:93-99 KERNEL_DICT, all five)                           */
   int32_t ls_dim;     /* 1 (isotropic lengthscale) or d                                                       */
   int32_t chunk_rows; /* observations streamed per pass, multiple of 256; 0 = library default                 */
   int32_t flags;      /* GDRF_FLAG_*                                                                          */
@@ -75,13 +76,15 @@ typedef struct gdrf_inputs {
   const float* noise;        /* [1]                                                                           */
   const float* phi;          /* [k, v]         word-topic matrix, rows on the simplex                         */
   const float* beta;         /* [k, v]         Dirichlet concentration                                        */
+  const float* scale_mixture;/* [1]            RationalQuadratic's third hyper-parameter; NULL for the other kernels  */
 } gdrf_inputs;
 
 /* terms[0..3] = { log p(mu), log q(mu), log p(w | mu, phi), log p(phi) } summed over this shard (fp64);
  *   ELBO = terms[0] + terms[3] + terms[2] - terms[1];  the reference's loss is -ELBO / N (train_script.py:365).
  * grad  = d ELBO / d (constrained parameter), fp32, laid out
- *   [ u_scale_tril k*m*m | u_loc k*m | phi k*v | z m*d | variance 1 | lengthscale ls_dim | noise 1 ]
- *   (gdrf_grad_elems() floats); u_scale_tril's entries above the diagonal are 0.                            */
+ *   [ u_scale_tril k*m*m | u_loc k*m | phi k*v | z m*d | variance 1 | lengthscale ls_dim | noise 1 | scale_mixture 1 ]
+ *   (gdrf_grad_elems() floats; the last entry exists for GDRF_KERNEL_RATIONALQUADRATIC only); u_scale_tril's
+ *   entries above the diagonal are 0.                                                                       */
 typedef struct gdrf_outputs {
   double* terms; /* [4]                      */
   float* grad;   /* [gdrf_grad_elems(shape)] or NULL when GDRF_FLAG_WANT_GRAD is clear                        */

@@ -29,7 +29,7 @@ This file restates, op for op in plain PyTorch,
   * ``gdrf/models/abstract_gdrf.py:17-22``  zero mean, softmax link over the topic axis
   * ``gdrf/models/abstract_gdrf.py:113-139`` topic_probs / word_probs / perplexity
   * ``gdrf/train_script.py:365-371``        poutine.scale(1/N) around model and guide
-  * pyro.contrib.gp.kernels.{Isotropy,RBF,Matern32,Matern52,Exponential}  (published algorithm)
+  * pyro.contrib.gp.kernels.{Isotropy,RBF,Matern32,Matern52,Exponential,RationalQuadratic}  (published algorithm)
   * pyro.contrib.gp.util.conditional(whiten=True, full_cov=False) (published algorithm)
   * pyro.infer.Trace_ELBO with fully reparameterised guide sites: loss = -(log p - log q)
 """
@@ -41,7 +41,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3}
+KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3, "rationalquadratic": 4}
 
 
 # --------------------------------------------------------------------------------------
@@ -58,8 +58,10 @@ def square_scaled_dist(X: torch.Tensor, Z: torch.Tensor, lengthscale: torch.Tens
 
 
 def kernel_matrix(kind: str, X: torch.Tensor, Z: torch.Tensor, variance: torch.Tensor,
-                  lengthscale: torch.Tensor) -> torch.Tensor:
+                  lengthscale: torch.Tensor, scale_mixture: Optional[torch.Tensor] = None) -> torch.Tensor:
     r2 = square_scaled_dist(X, Z, lengthscale)
+    if kind == "rationalquadratic":      # pyro.contrib.gp.kernels.RationalQuadratic
+        return variance * (1 + (0.5 / scale_mixture) * r2).pow(-scale_mixture)
     if kind == "rbf":
         return variance * torch.exp(-0.5 * r2)
     r = (r2 + 1e-12).sqrt()
@@ -106,11 +108,11 @@ def effective_jitter(jitter: float, njitter: int) -> float:
 # --------------------------------------------------------------------------------------
 # pyro.contrib.gp.util.conditional, whiten=True, full_cov=False, Lff given
 # --------------------------------------------------------------------------------------
-def conditional_whitened(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff):
+def conditional_whitened(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff, scale_mixture=None):
     N = X.size(0)
     M = Xnew.size(0)
     latent_shape = f_loc.shape[:-1]
-    Kfs = kernel_matrix(kind, X, Xnew, variance, lengthscale)          # [N_ind, N_obs]
+    Kfs = kernel_matrix(kind, X, Xnew, variance, lengthscale, scale_mixture)          # [N_ind, N_obs]
     f_loc_2D = f_loc.permute(-1, *range(len(latent_shape))).reshape(N, -1)
     S = f_scale_tril.permute(-2, -1, *range(len(latent_shape)))
     S_2D = S.reshape(N, -1)
@@ -159,20 +161,26 @@ class OracleInputs:
     jitter: float = 1e-8
     maxjitter: int = 5
     n_global: Optional[int] = None   # the 1/N of poutine.scale; defaults to len(xs)
+    scale_mixture: Optional[torch.Tensor] = None   # RationalQuadratic only
 
     def to(self, dtype: torch.dtype) -> "OracleInputs":
         f = lambda t: t.detach().to(dtype)
         return OracleInputs(f(self.xs), self.ws, f(self.Z), f(self.variance), f(self.lengthscale),
                             f(self.u_loc), f(self.u_scale_tril), f(self.noise), f(self.phi),
                             f(self.beta), f(self.eps), self.kernel, self.jitter, self.maxjitter,
-                            self.n_global)
+                            self.n_global, None if self.scale_mixture is None else f(self.scale_mixture))
 
 
 GRAD_NAMES = ("Z", "variance", "lengthscale", "u_loc", "u_scale_tril", "noise", "phi")
 
 
+def param_names(inp: "OracleInputs"):
+    return GRAD_NAMES + (("scale_mixture",) if inp.scale_mixture is not None else ())
+
+
 def _one_conditional(inp: OracleInputs, p: Dict[str, torch.Tensor], force_njitter=None):
-    Kuu = kernel_matrix(inp.kernel, p["Z"], p["Z"], p["variance"], p["lengthscale"]).contiguous()
+    sm = p.get("scale_mixture", inp.scale_mixture)
+    Kuu = kernel_matrix(inp.kernel, p["Z"], p["Z"], p["variance"], p["lengthscale"], sm).contiguous()
     M = Kuu.size(0)
     if force_njitter is None:
         Luu, nj = jittercholesky(Kuu, M, inp.jitter, inp.maxjitter)
@@ -181,7 +189,7 @@ def _one_conditional(inp: OracleInputs, p: Dict[str, torch.Tensor], force_njitte
         Kj = Kuu + effective_jitter(inp.jitter, nj) * torch.eye(M, dtype=Kuu.dtype)
         Luu = torch.linalg.cholesky(Kj)
     f_loc, f_var = conditional_whitened(inp.kernel, inp.xs, p["Z"], p["variance"], p["lengthscale"],
-                                        p["u_loc"], p["u_scale_tril"], Luu)
+                                        p["u_loc"], p["u_scale_tril"], Luu, **({} if sm is None else {"scale_mixture": sm}))
     # zero mean function (abstract_gdrf.py:17-18) broadcast-added
     f_loc = f_loc + torch.zeros(inp.xs.shape[:-1], dtype=f_loc.dtype)
     return f_loc, f_var, nj
@@ -195,7 +203,7 @@ def elbo_terms(inp: OracleInputs, params: Optional[Dict[str, torch.Tensor]] = No
     does (sparse_gdrf.py:334-344 and :384-394); the numbers are identical either way.
     ``force_njitter`` pins the escalation level (used to compare fp64 against an fp32 run that
     needed more escalations)."""
-    p = params if params is not None else {k: getattr(inp, k) for k in GRAD_NAMES}
+    p = params if params is not None else {k: getattr(inp, k) for k in param_names(inp)}
     N = inp.xs.size(0)
     # ---- guide (sparse_gdrf.py:375-409) ----
     f_loc_g, f_var_g, nj = _one_conditional(inp, p, force_njitter)
@@ -224,14 +232,15 @@ def elbo_terms(inp: OracleInputs, params: Optional[Dict[str, torch.Tensor]] = No
 def loss_and_grads(inp: OracleInputs, twice: bool = True, force_njitter: Optional[int] = None,
                    include_prior: bool = True):
     """loss = -ELBO/N and d loss / d (constrained parameter) for every name in GRAD_NAMES."""
-    params = {k: getattr(inp, k).detach().clone().requires_grad_(True) for k in GRAD_NAMES}
+    names = param_names(inp)
+    params = {k: getattr(inp, k).detach().clone().requires_grad_(True) for k in names}
     out = elbo_terms(inp, params, twice=twice, force_njitter=force_njitter)
     loss = out["loss"]
     if not include_prior:
         n_scale = inp.n_global if inp.n_global is not None else inp.xs.size(0)
         loss = loss + out["lp_phi"] / n_scale
-    grads = torch.autograd.grad(loss, [params[k] for k in GRAD_NAMES], allow_unused=True)
-    g = {k: (torch.zeros_like(params[k]) if gi is None else gi.detach()) for k, gi in zip(GRAD_NAMES, grads)}
+    grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
+    g = {k: (torch.zeros_like(params[k]) if gi is None else gi.detach()) for k, gi in zip(names, grads)}
     g["u_scale_tril"] = g["u_scale_tril"].tril()
     return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}, g
 
@@ -240,7 +249,7 @@ def loss_and_grads(inp: OracleInputs, twice: bool = True, force_njitter: Optiona
 # evaluation path (abstract_gdrf.py:113-139, sparse_gdrf.py:161-186)
 # --------------------------------------------------------------------------------------
 def log_topic_probs(inp: OracleInputs) -> torch.Tensor:
-    p = {k: getattr(inp, k) for k in GRAD_NAMES}
+    p = {k: getattr(inp, k) for k in param_names(inp)}
     f_loc, _, _ = _one_conditional(inp, p)
     return f_loc
 
@@ -307,7 +316,8 @@ def make_problem(N: int, D: int, K: int, V: int, grid, kernel: str = "rbf", seed
     mask = torch.arange(idx.size(1))[None, :] < counts[:, None]
     ws.scatter_add_(1, idx, mask.to(torch.int32))
     u_loc = 0.5 * torch.randn(K, M, generator=torch.Generator().manual_seed(7 + seed))
-    Kuu = kernel_matrix(kernel, Z.double(), Z.double(), var.double(), ls.double())
+    sm = torch.tensor(1.7) if kernel == "rationalquadratic" else None
+    Kuu = kernel_matrix(kernel, Z.double(), Z.double(), var.double(), ls.double(), None if sm is None else sm.double())
     L0 = torch.linalg.cholesky(Kuu + jitter * torch.eye(M, dtype=torch.float64)).float()
     S = L0.expand(K, M, M) + 0.05 * torch.randn(K, M, M, generator=torch.Generator().manual_seed(8 + seed)).tril()
     S = S.tril().contiguous()
@@ -318,7 +328,7 @@ def make_problem(N: int, D: int, K: int, V: int, grid, kernel: str = "rbf", seed
     eps = torch.randn(K, N, generator=torch.Generator().manual_seed(2024 + seed))
     return OracleInputs(xs=xs, ws=ws, Z=Z, variance=var, lengthscale=ls, u_loc=u_loc, u_scale_tril=S,
                         noise=torch.tensor(1.0), phi=phi, beta=beta, eps=eps, kernel=kernel,
-                        jitter=jitter, maxjitter=maxjitter)
+                        jitter=jitter, maxjitter=maxjitter, scale_mixture=sm)
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:

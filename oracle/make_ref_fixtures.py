@@ -57,6 +57,7 @@ CASES = {
     "ref_m32_1d_fixed": ("Matern32", 1, 14, 4, 9, 200, True, False, 1e-5, 15),
     "ref_m52_3d_ard": ("Matern52", 3, 3, 2, 15, 160, False, True, 1e-4, 15),
     "ref_exp2d": ("Exponential", 2, 4, 3, 10, 150, False, False, 1e-6, 5),
+    "ref_rq2d": ("RationalQuadratic", 2, 4, 3, 11, 180, False, False, 1e-5, 15),
 }
 
 

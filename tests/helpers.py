@@ -30,8 +30,9 @@ def load_golden(name):
     return inp, d
 
 
-REF_CASES = ["ref_rbf2d", "ref_m32_1d_fixed", "ref_m52_3d_ard", "ref_exp2d"]
-REF_KERNELS = {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52", "Exponential": "exponential"}
+REF_CASES = ["ref_rbf2d", "ref_m32_1d_fixed", "ref_m52_3d_ard", "ref_exp2d", "ref_rq2d"]
+REF_KERNELS = {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52", "Exponential": "exponential",
+               "RationalQuadratic": "rationalquadratic"}
 
 
 def load_ref_fixture(name):
@@ -56,6 +57,8 @@ def ref_constrained(spec, u, d, dtype=torch.float64):
               "u_loc": leaves["u_loc_unconstrained"], "u_scale_tril": O.lower_cholesky(leaves["u_scale_tril_unconstrained"]),
               "noise": O.positive(leaves["noise_unconstrained"]),
               "phi": O.simplex_rows(leaves["_word_topic_matrix_map_unconstrained"])}
+    if "_kernel.scale_mixture_unconstrained" in leaves:
+        params["scale_mixture"] = O.positive(leaves["_kernel.scale_mixture_unconstrained"])
     return leaves, params
 
 
@@ -65,4 +68,5 @@ def ref_oracle_inputs(spec, params, d, eps, dtype=torch.float64):
                         variance=det["variance"], lengthscale=det["lengthscale"], u_loc=det["u_loc"],
                         u_scale_tril=det["u_scale_tril"], noise=det["noise"], phi=det["phi"],
                         beta=torch.from_numpy(d["beta"]).to(dtype), eps=torch.as_tensor(eps).to(dtype),
-                        kernel=spec["kernel"], jitter=spec["jitter"], maxjitter=spec["maxjitter"])
+                        kernel=spec["kernel"], jitter=spec["jitter"], maxjitter=spec["maxjitter"],
+                        scale_mixture=det.get("scale_mixture"))

@@ -41,7 +41,8 @@ def _run(inp, flags=None, chunk_rows=0, n_global=None, n_offset=0, include_prior
                                         c(inp.u_loc), c(inp.u_scale_tril), c(inp.noise), c(inp.phi), c(inp.beta),
                                         c(e), kernel=inp.kernel, jitter=inp.jitter, maxjitter=inp.maxjitter,
                                         n_global=n_global, n_offset=n_offset, include_prior=include_prior,
-                                        flags=fl, chunk_rows=chunk_rows)
+                                        flags=fl, chunk_rows=chunk_rows,
+                                        scale_mixture=None if inp.scale_mixture is None else c(inp.scale_mixture))
     torch.cuda.synchronize()
     return terms.cpu(), {k: v.cpu().double() for k, v in g.items()}, nj
 
@@ -359,6 +360,8 @@ SWEEP = [
     (1000, 3, 17, 65, [5, 3, 3], "exponential"),
     (513, 2, 40, 300, [9, 9], "rbf"),           # K > 32 (two topics per lane), V > 256
     (2049, 1, 6, 31, [300], "matern52"),        # M = 300 -> padded to 512, N = 16 tiles + 1 row
+    (700, 2, 4, 23, [6, 6], "rationalquadratic"),   # third kernel hyper-parameter (scale_mixture)
+    (400, 3, 3, 12, [4, 3, 3], "rationalquadratic"),
 ]
 
 
@@ -382,7 +385,8 @@ def test_shape_sweep_against_fp64_oracle(N, D, K, V, grid, kernel):
             continue
         err, err32 = O.rel_err(-g[k] / N, ref), O.rel_err(g32[k], ref)
         assert err <= max(2 * GRAD_TOL, 2.0 * err32), (k, err, err32)
-    rep = {k: (O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k]), g64[k].norm().item()) for k in HYPER}
+    hyper = HYPER + (("scale_mixture",) if kernel == "rationalquadratic" else ())
+    rep = {k: (O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k]), g64[k].norm().item()) for k in hyper}
     print("sweep", (N, D, K, V, grid, kernel), {k: (f"{a:.1e}", f"fp32 {b:.1e}", f"|g| {c:.1e}") for k, (a, b, c) in rep.items()})
     for k, (err, err32, nrm) in rep.items():
         if nrm > 1e-12:

@@ -13,7 +13,8 @@ from tests.helpers import REF_CASES, load_ref_fixture, ref_constrained, ref_orac
 
 TERM_TOL = 2e-5          # each ELBO term, relative (reference = fp32 sums over N*K or N*V elements)
 GRAD_TOL = 3e-4          # well-conditioned gradients; else 3x the oracle's own fp32-vs-fp64 distance
-HYPER = ("_kernel.variance_unconstrained", "_kernel.lengthscale_unconstrained", "_inducing_points_unconstrained")
+HYPER = ("_kernel.variance_unconstrained", "_kernel.lengthscale_unconstrained", "_inducing_points_unconstrained",
+         "_kernel.scale_mixture_unconstrained")
 
 
 def _oracle_loss_and_grads(spec, u, d, eps, dtype):
@@ -70,6 +71,8 @@ def test_oracle_follows_reference_svi_trajectory(name):
                   "u_loc": cur["u_loc_unconstrained"], "u_scale_tril": O.lower_cholesky(cur["u_scale_tril_unconstrained"]),
                   "noise": O.positive(cur["noise_unconstrained"]),
                   "phi": O.simplex_rows(cur["_word_topic_matrix_map_unconstrained"])}
+        if "_kernel.scale_mixture_unconstrained" in cur:
+            params["scale_mixture"] = O.positive(cur["_kernel.scale_mixture_unconstrained"])
         inp = ref_oracle_inputs(spec, params, d, d["svi_eps"][step])
         opt.zero_grad()
         out = O.elbo_terms(inp, params, twice=False)

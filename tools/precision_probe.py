@@ -48,7 +48,7 @@ class RowNormTS(torch.autograd.Function):
         return dW, dS
 
 
-def conditional(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff):
+def conditional(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff, **kw):
     Kfs = O.kernel_matrix(kind, X, Xnew, variance, lengthscale)
     W = torch.linalg.solve_triangular(Lff, Kfs, upper=False).t()
     loc = (W @ f_loc.t()).t()

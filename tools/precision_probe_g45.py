@@ -29,7 +29,7 @@ class Whiten(torch.autograd.Function):
         return dKxz, dLinv
 
 
-def conditional(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff):
+def conditional(kind, Xnew, X, variance, lengthscale, f_loc, f_scale_tril, Lff, **kw):
     Kfs = O.kernel_matrix(kind, X, Xnew, variance, lengthscale)
     Linv = torch.linalg.solve_triangular(Lff, torch.eye(Lff.size(0), dtype=Lff.dtype), upper=False)
     W = Whiten.apply(Kfs.t(), Linv)
