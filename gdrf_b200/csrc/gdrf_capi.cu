@@ -256,9 +256,19 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
 #undef GDRF_KXZ_PLANES
   LAUNCH_CHECK();
   {
-    G1::Params g{};
-    g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq); g.RT = RT; g.MB = p.MB;
-    { ProfScope ps(PK_G1, st); ++g_launches; CU(launch_gemm<G1>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st)); }
+    auto fill = [&](auto& g) {
+      g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq);
+      g.RT = RT; g.MB = p.MB;
+    };
+    ProfScope ps(PK_G1, st);
+    ++g_launches;
+    if ((s->flags & (GDRF_FLAG_REF_G1 | GDRF_FLAG_SINGLE_CTA)) != 0) {
+      G1T<128>::Params g{}; fill(g);
+      CU(launch_gemm<G1T<128>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G1) != 0, st));
+    } else {
+      G1T<256>::Params g{}; fill(g);
+      CU(launch_gemm2<G1T<256>>(g, RT, sms, st));
+    }
   }
   k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
@@ -616,9 +626,16 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
-      G4::Params g{};
-      g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
-      { ProfScope ps(PK_G4, st); ++g_launches; CU(launch_gemm<G4>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st)); }
+      auto fill = [&](auto& g) { g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp; };
+      ProfScope ps(PK_G4, st);
+      ++g_launches;
+      if ((s->flags & (GDRF_FLAG_REF_G4 | GDRF_FLAG_SINGLE_CTA)) != 0) {
+        G4T<128>::Params g{}; fill(g);
+        CU(launch_gemm<G4T<128>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st));
+      } else {
+        G4T<256>::Params g{}; fill(g);
+        CU(launch_gemm2<G4T<256>>(g, RT, sms, st));
+      }
     }
     {
       const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
@@ -630,16 +647,27 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       LAUNCH_CHECK();
     }
     {
-      G5::Params g{};
-      g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
-      const int base = p.MT * p.MT;
-      int splits = base >= 2 * sms ? 1 : (2 * sms + base - 1) / base;
       const int NBt = 2 * RT;
-      if (splits > NBt) splits = NBt;
-      int per = (NBt + splits - 1) / splits;
-      splits = (NBt + per - 1) / per;
-      g.splits = splits; g.nb_per_split = per;
-      { ProfScope ps(PK_G5, st); ++g_launches; CU(launch_gemm<G5>(g, base * splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st)); }
+      auto fill = [&](auto& g, int splits) {
+        g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+        if (splits > NBt) splits = NBt;
+        if (splits < 1) splits = 1;
+        const int per = (NBt + splits - 1) / splits;
+        g.splits = (NBt + per - 1) / per;
+        g.nb_per_split = per;
+      };
+      ProfScope ps(PK_G5, st);
+      ++g_launches;
+      if ((s->flags & (GDRF_FLAG_REF_G5 | GDRF_FLAG_SINGLE_CTA)) != 0) {
+        const int base = p.MT * p.MT;
+        G5T<128>::Params g{}; fill(g, base >= 2 * sms ? 1 : (2 * sms + base - 1) / base);
+        CU(launch_gemm<G5T<128>>(g, base * g.splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
+      } else {
+        // 256 x 256 pair tiles: as many splits of the observation range as fill the sms / 2 CTA pairs once
+        const int base = p.MT * (Mp / 256), pairs = base / 2, clusters = sms / 2;
+        G5T<256>::Params g{}; fill(g, pairs >= clusters ? 1 : clusters / pairs);
+        CU(launch_gemm2<G5T<256>>(g, base * g.splits, sms, st));
+      }
     }
   }
 

@@ -60,24 +60,26 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------
 // G1:  W[n, m] = sum_{i <= m} Kxz[n, i] Linv[m, i]      epilogue: W planes + wsq[n] = sum_m W^2
 // ---------------------------------------------------------------------------------------------
-struct G1 {
+template <int BN_>
+struct G1T {
   static constexpr int EPI_WARPS = 4;
-  static constexpr int PA = 3, PB = 3, BN = 128;
+  static constexpr int PA = 3, PB = 3, BN = BN_;     // 128: one CTA per tile; 256: CTA pair (gemm_tc2_kernel)
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
+  static constexpr int CB = BN / 64, PCS = BN / 128;
   struct Params {
     PlaneMat kxz, linv, w, w16;   // w16: fp16 2-plane copy of W for the forward row-norm contraction
     double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients)
     int RT, MB;
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
-  __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
-  __device__ static int k_iters(const Params& p, int, int sub) { return min(p.MB, 2 * (sub + 1)); }
+  __device__ static int num_subs(const Params& p, int) { return p.MB / CB; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return min(p.MB, CB * (sub + 1)); }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int) {
     return p.kxz.base + pl * p.kxz.plane_stride + p.kxz.block_off(item, kit);
   }
-  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int) {
-    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(sub, kit);
+  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
+    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(sub * PCS + pc, kit);
   }
   struct Epi {
     double acc;
@@ -90,7 +92,7 @@ struct G1 {
         uint4 pa[3], pb[3];
         split8<3>(&v[g * 8], pa);
         split8<3>(&v[g * 8 + 8], pb);
-        const int col = sub * 128 + c0 + g * 8;
+        const int col = sub * BN + c0 + g * 8;
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) store16(p.w, pl, r, col, pa[pl], pb[pl]);
         uint4 ha[2], hb[2];
@@ -105,6 +107,7 @@ struct G1 {
     __device__ void item_end(const Params& p, int item, int row) { p.wsq[item * 128 + row] = acc; }
   };
 };
+using G1 = G1T<128>;
 
 // ---------------------------------------------------------------------------------------------
 // G2:  T[n, (k, j)] = sum_{i >= j} W[n, i] S_k[i, j]
@@ -247,31 +250,33 @@ struct G3 {
 // ---------------------------------------------------------------------------------------------
 // G4:  dKxz[n, i] = sum_{m >= i} dWtot[n, m] Linv[m, i]          (B = LINV read MN-major)
 // ---------------------------------------------------------------------------------------------
-struct G4 {
+template <int BN_>
+struct G4T {
   static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
-  static constexpr int PA = 2, PB = 2, BN = 128;   // 16-bit operands: see DESIGN.md (hyper-gradient probe)
+  static constexpr int PA = 2, PB = 2, BN = BN_;   // 16-bit operands: see DESIGN.md (hyper-gradient probe)
   static constexpr bool A_MN = false, B_MN = true;
+  static constexpr int CB = BN / 64;
   struct Params {
     PlaneMat dwt, linv;
     float* dkxz;   // [ncp][Mp] fp32
     int RT, MB, Mp;
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
-  __device__ static int num_subs(const Params& p, int) { return p.MB / 2; }
-  __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - 2 * sub; }
+  __device__ static int num_subs(const Params& p, int) { return p.MB / CB; }
+  __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - CB * sub; }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
-    return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(item, 2 * sub + kit);
+    return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(item, CB * sub + kit);
   }
   __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
-    const int mb = 2 * sub + kit;
-    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(mb >> 1, sub * 2 + pc) + (mb & 1) * 4096;
+    const int mb = CB * sub + kit;
+    return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(mb >> 1, sub * CB + pc) + (mb & 1) * 4096;
   }
   struct Epi {
     __device__ void item_begin(const Params&, int, int) {}
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
-      float4* dst = reinterpret_cast<float4*>(p.dkxz + (long long)(item * 128 + row) * p.Mp + sub * 128 + c0);
+      float4* dst = reinterpret_cast<float4*>(p.dkxz + (long long)(item * 128 + row) * p.Mp + sub * BN + c0);
 #pragma unroll
       for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     }
@@ -279,42 +284,48 @@ struct G4 {
     __device__ void item_end(const Params&, int, int) {}
   };
 };
+using G4 = G4T<128>;
 
 // ---------------------------------------------------------------------------------------------
 // G5:  C5[a, b] += sum_n dWtot[n, a] W[n, b]        (both operands MN-major; split over n; fp64 atomics)
 // ---------------------------------------------------------------------------------------------
-struct G5 {
+template <int BN_>
+struct G5T {
   static constexpr int EPI_WARPS = 4;
   static constexpr int FMT = FMT_BF16;
-  static constexpr int PA = 2, PB = 2, BN = 128;   // 16-bit operands, like G4
+  static constexpr int PA = 2, PB = 2, BN = BN_;   // 16-bit operands, like G4
   static constexpr bool A_MN = true, B_MN = true;
+  static constexpr int CB = BN / 64;
   struct Params {
     PlaneMat dwt, w;
     double* c5;   // [Mp][Mp]
     int RT, MB, Mp, MT, splits, nb_per_split;
   };
-  __device__ static int num_items(const Params& p) { return p.MT * p.MT * p.splits; }
+  // item = (split, column tile bt of BN columns, 128-row tile at), at fastest: with BN = 256 the items 2t, 2t + 1 are
+  // the two row halves of one 256 x 256 pair tile
+  __device__ static int per_split(const Params& p) { return p.MT * (p.Mp / BN); }
+  __device__ static int num_items(const Params& p) { return per_split(p) * p.splits; }
   __device__ static int num_subs(const Params&, int) { return 1; }
   __device__ static int k_iters(const Params& p, int item, int) {
-    const int s = item / (p.MT * p.MT);
+    const int s = item / per_split(p);
     return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
   }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / (p.MT * p.MT), t = item - s * p.MT * p.MT, at = t / p.MT;
+    const int s = item / per_split(p), t = item - s * per_split(p), at = t % p.MT;
     const int nb = s * p.nb_per_split + kit;
     return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(nb >> 1, at * 2 + pc) + (nb & 1) * 4096;
   }
   __device__ static const bf16* b_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / (p.MT * p.MT), t = item - s * p.MT * p.MT, bt = t % p.MT;
+    const int s = item / per_split(p), t = item - s * per_split(p), bt = t / p.MT;
     const int nb = s * p.nb_per_split + kit;
-    return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, bt * 2 + pc) + (nb & 1) * 4096;
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, bt * CB + pc) + (nb & 1) * 4096;
   }
   struct Epi {
     __device__ void item_begin(const Params&, int, int) {}
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
-      const int t = item % (p.MT * p.MT), at = t / p.MT, bt = t % p.MT;
-      double* dst = p.c5 + (long long)(at * 128 + row) * p.Mp + bt * 128 + c0;
+      const int t = item % per_split(p), at = t % p.MT, bt = t / p.MT;
+      double* dst = p.c5 + (long long)(at * 128 + row) * p.Mp + bt * BN + c0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) atomicAdd(dst + j, (double)v[j]);
     }
@@ -322,6 +333,7 @@ struct G5 {
     __device__ void item_end(const Params&, int, int) {}
   };
 };
+using G5 = G5T<128>;
 
 // ---------------------------------------------------------------------------------------------
 // G6:  dS_k[i, j] += sum_n WG[n, (k, i)] T[n, (k, j)]   for j <= i   (both MN-major; tiles on/below the diagonal)
