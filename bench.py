@@ -381,7 +381,14 @@ def main():
         per_launch_ms = dom_ms / dom_n
         obs_per_launch = n_local * steps / dom_n
         achieved = alg[dom] * obs_per_launch / (per_launch_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
+        # what the tensor pipe is actually asked to do: 3 16-bit MMAs per logical product, and whole 64-row k-blocks
+        # of 256-wide tiles where the triangular operand is half empty (Mp / 64 blocks per side)
+        MBk = (M + 255) // 256 * 4
+        pad = sum((MBk - 4 * j) * 4 for j in range(MBk // 4)) / (MBk * MBk / 2.0) if dom in ("G2_fwd", "G3", "G6") else 1.0
+        issued = achieved * 3.0 * pad * (float(MBk * 64) / M) ** 2
+        roofline = {"bound": "tensor", "kernel": f"gemm_tc2_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
+                    "issued": {"tflops": issued, "frac": issued / peak_tf, "mma_per_product": 3, "tile_padding": pad,
+                               "note": "issued 16-bit MMA flops / peak: the tensor-pipe utilisation this kernel runs at"},
                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                     "traffic_note": "dram__bytes_read+write per launch, ncu --set full, one 18 944-observation chunk (profiles/)",
                     "peak_source": peak_src,
@@ -399,7 +406,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": "observations/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (error-compensated 16-bit-plane tcgen05 products: fp16x3 forward, bf16x3 backward, bf16x6 whitening; f32 accumulate; f64 per-observation chain and MxM prologue)",
+            "vs_baseline": None, "dtype": "f32 (error-compensated 16-bit-plane tcgen05 products: fp16x3 forward, bf16x3 backward, bf16x6 whitening W = Kxz L^-T; f32 accumulate; f64 per-observation chain and MxM prologue)",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: N={N} D={D} K={K} V={V} M={M} {cfg['kernel']}, sharded by "
                                    f"observation over {world} GPU(s)", "l2": "inputs (ws) exceed L2 every step",
