@@ -64,7 +64,7 @@ struct Plan {
   int chunk_rows;
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, status_pad;
-  size_t L64, Linv64, tmpA, tmpB, dinv;
+  size_t L64, Linv64, tmpA, tmpB, dinv, dinv32;
   size_t linv_pl, st_pl, st16_pl, w16_pl;
   // per chunk
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
@@ -117,6 +117,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tmpA = bump(off, sizeof(double) * Mp2);
   p.tmpB = bump(off, sizeof(double) * Mp2);
   p.dinv = bump(off, sizeof(double) * (size_t)p.Mp * NB);
+  p.dinv32 = bump(off, sizeof(float) * (size_t)p.Mp * NB);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
   p.st16_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
@@ -477,22 +478,22 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   const Hyper hp = make_hyper(s, in);
   CU(cudaMemsetAsync(dev_status, 0, sizeof(int), st));
   const dim3 g2d(ceil_div(p.Mp, 256), p.Mp);
-  if (s->flags & GDRF_FLAG_CHOL_FP32_STATUS) {
-    // the reference's own fp32 arithmetic decides whether this jitter level "fails" (utils.py:31-37)
-    float* k32 = at<float>(ws, p.tmpA);
-    float* l32 = at<float>(ws, p.tmpB);
-    k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
-    LAUNCH_CHECK();
-    cholesky<float>(k32, l32, at<float>(ws, p.dinv), p.Mp, dev_status, st);
-    g_launches += 2 * (p.Mp / NB);
-    LAUNCH_CHECK();
-  }
   double* L = at<double>(ws, p.L64);
   double* Linv = at<double>(ws, p.Linv64);
   double* kuu = at<double>(ws, p.tmpA);
   k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, kuu);
   LAUNCH_CHECK();
-  cholesky<double>(kuu, L, at<double>(ws, p.dinv), p.Mp, dev_status, st);
+  if (s->flags & GDRF_FLAG_CHOL_FP32_STATUS) {
+    // the reference's own fp32 arithmetic decides whether this jitter level "fails" (utils.py:31-37); its
+    // factorisation runs in the same launches as the fp64 one (values), in the two halves of tmpB
+    float* k32 = at<float>(ws, p.tmpB);
+    float* l32 = k32 + (size_t)p.Mp * p.Mp;
+    k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
+    LAUNCH_CHECK();
+    cholesky_both(kuu, L, at<double>(ws, p.dinv), k32, l32, at<float>(ws, p.dinv32), p.Mp, dev_status, st);
+  } else {
+    cholesky<double>(kuu, L, at<double>(ws, p.dinv), p.Mp, dev_status, st);
+  }
   g_launches += 2 * (p.Mp / NB);
   LAUNCH_CHECK();
   tri_inverse(L, at<double>(ws, p.dinv), Linv, p.Mp, st);
@@ -680,12 +681,13 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     double* tA = at<double>(ws, p.tmpA);
     double* tB = at<double>(ws, p.tmpB);
     const dim3 g2d(ceil_div(Mp, 256), Mp);
-    dgemm<true, false>(Linv, at<double>(ws, p.c5), tA, Mp, st);
+    // every factor is triangular: (L^-T X)[i, j] sums over k >= i, a lower X over k >= j, X L^-1 over k >= j
+    dgemm<true, false, 1, true>(Linv, at<double>(ws, p.c5), tA, Mp, st);     // lower part of L^-T C5
     k_tril_op<<<g2d, 256, 0, st>>>(tA, Mp, 0);
-    dgemm<true, false>(L, tA, tB, Mp, st);
+    dgemm<true, false, 1, true>(L, tA, tB, Mp, st);                          // lower part of L^T G_L
     k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
-    dgemm<true, false>(Linv, tB, tA, Mp, st);
-    dgemm<false, false>(tA, Linv, tB, Mp, st);
+    dgemm<true, false, 3, false>(Linv, tB, tA, Mp, st);                      // L^-T Phi, Phi lower
+    dgemm<false, false, 2, false>(tA, Linv, tB, Mp, st);                     // (...) L^-1
     g_launches += 5;
     LAUNCH_CHECK();
     k_kuu_backward<<<M, 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);

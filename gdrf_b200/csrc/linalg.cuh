@@ -74,8 +74,8 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 //                 A[ib][jb] -= P_i P_j^T; the jb == kb+1 blocks also store L[ib][kb] = P_i.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(32) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
-                                                  int Mp, int kb, int* __restrict__ status) {
+__device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+                                               int Mp, int kb, int* __restrict__ status) {
   const int lane = threadIdx.x;
   const T* blk = A + ((long long)kb * NB + lane) * Mp + kb * NB;
   T a[NB];
@@ -123,8 +123,24 @@ __global__ void __launch_bounds__(32) k_chol_diag(const T* __restrict__ A, T* __
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NB * NB) k_chol_trail(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
-                                                        int Mp, int kb) {
+__global__ void __launch_bounds__(32) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+                                                  int Mp, int kb, int* __restrict__ status) {
+  chol_diag_body<T>(A, L, Dinv, Mp, kb, status);
+}
+
+// the fp64 factorisation (values) and the fp32 one (the reference's "did it fail" decision) side by side:
+// block 0 = double, block 1 = float
+__global__ void __launch_bounds__(32) k_chol_diag_both(const double* __restrict__ A, double* __restrict__ L,
+                                                       double* __restrict__ Dinv, const float* __restrict__ Af,
+                                                       float* __restrict__ Lf, float* __restrict__ Dinvf, int Mp, int kb,
+                                                       int* __restrict__ status) {
+  if (blockIdx.x == 0) chol_diag_body<double>(A, L, Dinv, Mp, kb, status);
+  else chol_diag_body<float>(Af, Lf, Dinvf, Mp, kb, status);
+}
+
+template <typename T>
+__device__ __forceinline__ void chol_trail_body(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
+                                                int Mp, int kb) {
   const int ib = kb + 1 + blockIdx.y, jb = kb + 1 + blockIdx.x;
   if (jb > ib) return;
   __shared__ T ai[NB][NB + 1], aj[NB][NB + 1], dd[NB][NB + 1];
@@ -150,6 +166,20 @@ __global__ void __launch_bounds__(NB * NB) k_chol_trail(T* __restrict__ A, T* __
   A[((long long)ib * NB + r) * Mp + jb * NB + c] -= s;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(NB * NB) k_chol_trail(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
+                                                        int Mp, int kb) {
+  chol_trail_body<T>(A, L, Dinv, Mp, kb);
+}
+
+__global__ void __launch_bounds__(NB * NB) k_chol_trail_both(double* __restrict__ A, double* __restrict__ L,
+                                                             const double* __restrict__ Dinv, float* __restrict__ Af,
+                                                             float* __restrict__ Lf, const float* __restrict__ Dinvf,
+                                                             int Mp, int kb) {
+  if (blockIdx.z == 0) chol_trail_body<double>(A, L, Dinv, Mp, kb);
+  else chol_trail_body<float>(Af, Lf, Dinvf, Mp, kb);
+}
+
 // A: Kuu (destroyed), L: factor (zero above the diagonal), Dinv: [Mp/32][32][32]
 template <typename T>
 inline void cholesky(T* A, T* L, T* Dinv, int Mp, int* status, cudaStream_t st) {
@@ -159,6 +189,18 @@ inline void cholesky(T* A, T* L, T* Dinv, int Mp, int* status, cudaStream_t st) 
     k_chol_diag<T><<<1, NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
     const int rem = nblk - kb - 1;
     if (rem > 0) k_chol_trail<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb);
+  }
+}
+
+inline void cholesky_both(double* A, double* L, double* Dinv, float* Af, float* Lf, float* Dinvf, int Mp, int* status,
+                          cudaStream_t st) {
+  cudaMemsetAsync(L, 0, sizeof(double) * (size_t)Mp * Mp, st);
+  cudaMemsetAsync(Lf, 0, sizeof(float) * (size_t)Mp * Mp, st);
+  const int nblk = Mp / NB;
+  for (int kb = 0; kb < nblk; ++kb) {
+    k_chol_diag_both<<<2, NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb, status);
+    const int rem = nblk - kb - 1;
+    if (rem > 0) k_chol_trail_both<<<dim3(rem, rem, 2), NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb);
   }
 }
 
@@ -205,15 +247,25 @@ inline void tri_inverse(const double* L, const double* Dinv, double* X, int Mp, 
 
 // ---------------------------------------------------------------------------------------------
 // C = op(A) * op(B), square [Mp][Mp] fp64, 64 x 64 tile per CTA, 4 x 4 per thread.
+// The Cholesky adjoint only multiplies triangular matrices: KSTART says where the contraction index can start for
+// a tile (0: 0, 1: the tile's first row, 2: its first column, 3: the larger of the two) and LOWER_ONLY skips the
+// tiles strictly above the diagonal (their values are discarded by the caller's tril).  The contraction range of a
+// tile is cut into gridDim.z pieces that add into a zeroed C (a single CTA walking all of it is a 64-step chain of
+// load -> barrier -> 256 dependent fp64 FMAs per thread, which is what the kernel's duration used to be).
 // ---------------------------------------------------------------------------------------------
-template <bool TA, bool TB>
+template <bool TA, bool TB, int KSTART, bool LOWER_ONLY>
 __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
                                                double* __restrict__ C, int Mp) {
   __shared__ double as[16][65], bs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  if (LOWER_ONLY && j0 > i0) return;
+  const int kfirst = KSTART == 0 ? 0 : (KSTART == 1 ? i0 : (KSTART == 2 ? j0 : max(i0, j0)));
+  const int steps = (Mp - kfirst) / 16, per = (steps + gridDim.z - 1) / gridDim.z;
+  const int kbeg = kfirst + 16 * per * blockIdx.z, kend = min(Mp, kbeg + 16 * per);
+  if (kbeg >= kend) return;
   double acc[4][4] = {};
-  for (int k0 = 0; k0 < Mp; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
     __syncthreads();
     for (int t = threadIdx.x; t < 16 * 64; t += 256) {
       const int kk = t >> 6, e = t & 63;
@@ -238,12 +290,13 @@ __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, con
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) C[(long long)(i0 + ty * 4 + u) * Mp + j0 + tx * 4 + v] = acc[u][v];
+    for (int v = 0; v < 4; ++v) atomicAdd(&C[(long long)(i0 + ty * 4 + u) * Mp + j0 + tx * 4 + v], acc[u][v]);
 }
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int KSTART = 0, bool LOWER_ONLY = false>
 inline void dgemm(const double* A, const double* B, double* C, int Mp, cudaStream_t st) {
-  k_dgemm<TA, TB><<<dim3(Mp / 64, Mp / 64), 256, 0, st>>>(A, B, C, Mp);
+  cudaMemsetAsync(C, 0, sizeof(double) * (size_t)Mp * Mp, st);
+  k_dgemm<TA, TB, KSTART, LOWER_ONLY><<<dim3(Mp / 64, Mp / 64, 4), 256, 0, st>>>(A, B, C, Mp);
 }
 
 // mode 0: X <- -tril(X)      mode 1: X <- tril(X) with the diagonal halved  (the Phi of the Cholesky adjoint)
