@@ -89,8 +89,12 @@ __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __res
       if (bad == 0) bad = kb * NB + j + 1;
       d = T(1);
     }
-    const T inv = T(1) / sqrt(d);
-    if (lane == j) a[j] = sqrt(d);
+    // one reciprocal square root per column instead of two square roots and a division (each a long dependent
+    // chain in fp64); a Newton step puts sqrt(d) = d * inv back within an ulp
+    const T inv = rsqrt(d);
+    T sq = d * inv;
+    sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
+    if (lane == j) a[j] = sq;
     if (lane > j) a[j] *= inv;
 #pragma unroll
     for (int c = j + 1; c < NB; ++c) {
