@@ -617,14 +617,21 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
     {
       g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
-      const int base = K * g6.ntile;
-      int splits = base >= sms ? 1 : (sms + base - 1) / base;
-      const int NBt = 2 * RT;
-      if (splits > NBt) splits = NBt;
-      int per = (NBt + splits - 1) / splits;
-      splits = (NBt + per - 1) / per;
-      g6.splits = splits; g6.nb_per_split = per;
-      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, base * splits, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+      // (topic, tile) items in units of CTA pairs: as many whole rounds of the sms / 2 pairs as fit run unsplit; the
+      // items of the last, partial round are cut along the observations so that this round is full as well
+      const int base = K * g6.ntile, pairs = base / 2, clusters = sms / 2, NBt = 2 * RT;
+      int whole_pairs = (pairs / clusters) * clusters, sp;
+      if (pairs - whole_pairs == 0) sp = 1;
+      else sp = clusters / (pairs - whole_pairs);
+      if (sp < 1) sp = 1;
+      if (sp > 8 && whole_pairs > 0) sp = 8;
+      if (sp > NBt) sp = NBt;
+      const int per = (NBt + sp - 1) / sp;
+      sp = (NBt + per - 1) / per;
+      if (sp == 1) whole_pairs = pairs;
+      g6.n_whole = 2 * whole_pairs; g6.tail_sp = sp; g6.tail_per = per;
+      const int n_items6 = g6.n_whole + (base - g6.n_whole) * sp;
+      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, n_items6, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
       auto fill = [&](auto& g) { g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp; };

@@ -12,6 +12,7 @@
 // same policy drives `gemm_ref_kernel`, a plain-FMA CUDA kernel used by the tests to check the tensor
 // path element for element (it is a device-side checker, not a fallback: the product never selects it).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace gdrf {
@@ -136,6 +137,32 @@ template <class P>
 constexpr int gemm_threads() { return 64 + 32 * P::EPI_WARPS; }
 constexpr int GEMM_SMEM_BUDGET = 216 * 1024;
 
+// Operand addresses in the producer loops.  A policy whose (item -> operand block) map is expensive declares
+// `Item`, `decode(prm, item)` and `a_at / b_at(prm, Item, kit, plane, piece)`; the producer then decodes once per
+// item instead of once per bulk copy (a single thread issues 8-12 copies per k-block).
+template <class P, class = void>
+struct OperandCtx {
+  struct type { int item, sub; };
+  __device__ static type make(const typename P::Params&, int item, int sub) { return type{item, sub}; }
+  __device__ static const bf16* a(const typename P::Params& p, const type& c, int kit, int pl, int pc) {
+    return P::a_src(p, c.item, c.sub, kit, pl, pc);
+  }
+  __device__ static const bf16* b(const typename P::Params& p, const type& c, int kit, int pl, int pc) {
+    return P::b_src(p, c.item, c.sub, kit, pl, pc);
+  }
+};
+template <class P>
+struct OperandCtx<P, std::void_t<typename P::Item>> {
+  using type = typename P::Item;
+  __device__ static type make(const typename P::Params& p, int item, int) { return P::decode(p, item); }
+  __device__ static const bf16* a(const typename P::Params& p, const type& c, int kit, int pl, int pc) {
+    return P::a_at(p, c, kit, pl, pc);
+  }
+  __device__ static const bf16* b(const typename P::Params& p, const type& c, int kit, int pl, int pc) {
+    return P::b_at(p, c, kit, pl, pc);
+  }
+};
+
 template <class P>
 struct GemmCfg {
   static constexpr int A_BYTES = 16384;                       // one plane of a 128 x 64 A stage
@@ -194,6 +221,7 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
         const int nsub = P::num_subs(prm, item);
         for (int sub = 0; sub < nsub; ++sub) {
           const int kn = P::k_iters(prm, item, sub);
+          const auto octx = OperandCtx<P>::make(prm, item, sub);
           for (int kit = 0; kit < kn; ++kit, ++it) {
             const int s = it % NST;
             const uint32_t ph = (it / NST) & 1;
@@ -204,11 +232,11 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
             for (int pl = 0; pl < P::PA; ++pl) {
               uint8_t* dst = st + pl * Cfg::A_BYTES;
               if (!P::A_MN) {
-                bulk_g2s(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s]);
+                bulk_g2s(dst, OperandCtx<P>::a(prm, octx, kit, pl, 0), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < 2; ++pc)
-                  bulk_g2s(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+                  bulk_g2s(dst + pc * 8192, OperandCtx<P>::a(prm, octx, kit, pl, pc), 8192, &full_bar[s]);
               }
             }
 #pragma unroll
@@ -217,11 +245,11 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
               if (!P::B_MN) {
 #pragma unroll
                 for (int pc = 0; pc < P::BN / 128; ++pc)
-                  bulk_g2s(dst + pc * 16384, P::b_src(prm, item, sub, kit, pl, pc), 16384, &full_bar[s]);
+                  bulk_g2s(dst + pc * 16384, OperandCtx<P>::b(prm, octx, kit, pl, pc), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < P::BN / 64; ++pc)
-                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+                  bulk_g2s(dst + pc * 8192, OperandCtx<P>::b(prm, octx, kit, pl, pc), 8192, &full_bar[s]);
               }
             }
           }
@@ -435,6 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
         const int nsub = P::num_subs(prm, item);
         for (int sub = 0; sub < nsub; ++sub) {
           const int kn = P::k_iters(prm, item, sub);
+          const auto octx = OperandCtx<P>::make(prm, item, sub);
           for (int kit = 0; kit < kn; ++kit, ++it) {
             const int s = it % NST;
             const uint32_t ph = (it / NST) & 1;
@@ -445,22 +474,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
             for (int pl = 0; pl < P::PA; ++pl) {
               uint8_t* dst = st + pl * Cfg::A_BYTES;
               if (!P::A_MN) {
-                bulk_g2s(dst, P::a_src(prm, item, sub, kit, pl, 0), 16384, &full_bar[s]);
+                bulk_g2s(dst, OperandCtx<P>::a(prm, octx, kit, pl, 0), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < 2; ++pc)
-                  bulk_g2s(dst + pc * 8192, P::a_src(prm, item, sub, kit, pl, pc), 8192, &full_bar[s]);
+                  bulk_g2s(dst + pc * 8192, OperandCtx<P>::a(prm, octx, kit, pl, pc), 8192, &full_bar[s]);
               }
             }
 #pragma unroll
             for (int pl = 0; pl < P::PB; ++pl) {
               uint8_t* dst = st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES;
               if (!P::B_MN) {
-                bulk_g2s(dst, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s]);
+                bulk_g2s(dst, OperandCtx<P>::b(prm, octx, kit, pl, (int)rank * B_HALF_K), 16384, &full_bar[s]);
               } else {
 #pragma unroll
                 for (int pc = 0; pc < B_HALF_MN; ++pc)
-                  bulk_g2s(dst + pc * 8192, P::b_src(prm, item, sub, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
+                  bulk_g2s(dst + pc * 8192, OperandCtx<P>::b(prm, octx, kit, pl, (int)rank * B_HALF_MN + pc), 8192,
                            &full_bar[s]);
               }
             }

@@ -347,35 +347,62 @@ struct G6 {
   struct Params {
     PlaneMat wg, tp;
     float* ds;   // [K][M][M] fp32, unpadded gradient accumulator
-    int RT, MB, K, M, ntile, splits, nb_per_split;
+    // items [0, n_whole) contract the whole observation range of the chunk and own their tile (plain += on dS);
+    // each of the remaining (topic, tile) pairs is cut into tail_sp pieces of tail_per 64-observation blocks that add
+    // atomically -- sized by the host so that the last round of the persistent CTAs / CTA pairs is full
+    int RT, MB, K, M, ntile, n_whole, tail_sp, tail_per;
     unsigned char ta[MAX_TILES], tb[MAX_TILES];
   };
-  __device__ static int num_items(const Params& p) { return p.K * p.ntile * p.splits; }
+  struct Item {
+    int k, t, nb0, cnt;
+    bool whole;
+  };
+  __device__ static Item decode(const Params& p, int item) {
+    Item it;
+    int rem;
+    if (item < p.n_whole) {
+      rem = item; it.nb0 = 0; it.cnt = 2 * p.RT; it.whole = true;
+    } else {
+      const int q = item - p.n_whole, pi = q >> 1, h = q & 1;     // 2 t, 2 t + 1: the row halves of one pair tile
+      const int sp = pi % p.tail_sp, bp = pi / p.tail_sp;
+      rem = p.n_whole + 2 * bp + h;
+      it.nb0 = sp * p.tail_per;
+      it.cnt = min(p.tail_per, 2 * p.RT - it.nb0);
+      it.whole = false;
+    }
+    it.k = rem / p.ntile;
+    it.t = rem - it.k * p.ntile;
+    return it;
+  }
+  __device__ static int num_items(const Params& p) { return p.n_whole + (p.K * p.ntile - p.n_whole) * p.tail_sp; }
   __device__ static int num_subs(const Params&, int) { return 1; }
-  __device__ static int k_iters(const Params& p, int item, int) {
-    const int s = item / (p.K * p.ntile);
-    return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
+  __device__ static int k_iters(const Params& p, int item, int) { return decode(p, item).cnt; }
+  __device__ static const bf16* a_at(const Params& p, const Item& it, int kit, int pl, int pc) {
+    const int nb = it.nb0 + kit;
+    return p.wg.base + pl * p.wg.plane_stride + p.wg.block_off(nb >> 1, it.k * p.MB + p.ta[it.t] * 2 + pc) +
+           (nb & 1) * 4096;
+  }
+  __device__ static const bf16* b_at(const Params& p, const Item& it, int kit, int pl, int pc) {
+    const int nb = it.nb0 + kit;
+    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(nb >> 1, it.k * p.MB + p.tb[it.t] * 4 + pc) +
+           (nb & 1) * 4096;
   }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
-    const int nb = s * p.nb_per_split + kit;
-    return p.wg.base + pl * p.wg.plane_stride + p.wg.block_off(nb >> 1, k * p.MB + p.ta[t] * 2 + pc) + (nb & 1) * 4096;
+    return a_at(p, decode(p, item), kit, pl, pc);
   }
   __device__ static const bf16* b_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / (p.K * p.ntile), rem = item - s * p.K * p.ntile, k = rem / p.ntile, t = rem % p.ntile;
-    const int nb = s * p.nb_per_split + kit;
-    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(nb >> 1, k * p.MB + p.tb[t] * 4 + pc) + (nb & 1) * 4096;
+    return b_at(p, decode(p, item), kit, pl, pc);
   }
   struct Epi {
     __device__ void item_begin(const Params&, int, int) {}
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
-      const int rem = item % (p.K * p.ntile), k = rem / p.ntile, t = rem % p.ntile;
-      const int i = p.ta[t] * 128 + row;
-      const int j0 = p.tb[t] * 256 + c0;
+      const Item it = decode(p, item);
+      const int i = p.ta[it.t] * 128 + row;
+      const int j0 = p.tb[it.t] * 256 + c0;
       if (i >= p.M) return;
-      float* dst = p.ds + ((long long)k * p.M + i) * p.M;
-      if (p.splits == 1) {
+      float* dst = p.ds + ((long long)it.k * p.M + i) * p.M;
+      if (it.whole) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j0 + j <= i) dst[j0 + j] += v[j];
