@@ -4,7 +4,7 @@ import sys
 import torch
 sys.path.insert(0, ".")
 from oracle import gdrf_oracle as O
-from tools.precision_probe import planes
+from oracle.precision_probe import planes
 
 CFG = {}
 

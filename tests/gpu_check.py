@@ -1,7 +1,7 @@
 """Exploratory GPU parity runner (development tool; the asserting version is tests/test_gpu_parity.py).
 
-    python tools/gpu_check.py            # runs every case in its own subprocess (a trap cannot poison the rest)
-    python tools/gpu_check.py case NAME FLAGS
+    python tests/gpu_check.py            # runs every case in its own subprocess (a trap cannot poison the rest)
+    python tests/gpu_check.py case NAME FLAGS
 """
 import json
 import os
