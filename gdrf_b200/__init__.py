@@ -4,8 +4,11 @@ from .elbo import (GDRFElbo, elbo_value_and_grads, elbo_value_and_grads_from_hos
                    perplexity_from_mean)
 from .kernels import KERNEL_DICT, RBF, Exponential, Matern32, Matern52, RationalQuadratic
 from .models import SparseMultinomialGDRF
-from .svi import SVI, FusedSVI, shard_bounds
+from .streaming import (StreamingData, streaming_epoch, streaming_probabilities, streaming_selection,
+                        streaming_window)
+from .svi import SVI, ClippedAdam, FusedSVI, shard_bounds
 
 __all__ = ["GDRFElbo", "elbo_value_and_grads", "elbo_value_and_grads_from_host", "marginal_mean", "marginal_moments",
            "perplexity_from_mean", "RBF", "Matern32",
-           "Matern52", "Exponential", "RationalQuadratic", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "FusedSVI", "shard_bounds", "_lib"]
+           "Matern52", "Exponential", "RationalQuadratic", "KERNEL_DICT", "SparseMultinomialGDRF", "SVI", "FusedSVI", "ClippedAdam", "shard_bounds",
+           "StreamingData", "streaming_epoch", "streaming_probabilities", "streaming_selection", "streaming_window", "_lib"]

@@ -43,7 +43,7 @@ class Outputs(ctypes.Structure):
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
            "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_marginal_moments", "gdrf_perplexity_terms",
-           "gdrf_constrain", "gdrf_adam_step", "gdrf_last_error",
+           "gdrf_constrain", "gdrf_adam_step", "gdrf_clipped_adam_step", "gdrf_gather_rows", "gdrf_last_error",
            "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
 _lib = None
@@ -69,7 +69,11 @@ def load() -> ctypes.CDLL:
     lib.gdrf_constrain.argtypes = [P(Shape), c_void_p, c_void_p, c_int, c_void_p]
     lib.gdrf_adam_step.argtypes = [P(Shape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                    c_float, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]
-    for n in EXPORTS[:10]:
+    lib.gdrf_clipped_adam_step.argtypes = [P(Shape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                           c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]
+    lib.gdrf_gather_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.c_int32, ctypes.c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]
+    for n in EXPORTS[:12]:
         getattr(lib, n).restype = c_int
     lib.gdrf_launch_count.restype = ctypes.c_longlong
     lib.gdrf_profile_enable.argtypes = [c_int]

@@ -11,6 +11,7 @@
 #include "optimizer.cuh"
 #include "policies.cuh"
 #include "stages.cuh"
+#include "streaming.cuh"
 
 using namespace gdrf;
 
@@ -420,9 +421,9 @@ int gdrf_constrain(const gdrf_shape* s, const float* theta_u, float* theta_c, in
   return 0;
 }
 
-int gdrf_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, const float* grad, float* m, float* v,
-                   float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                   float grad_scale, int learn_z, gdrf_stream_t stream) {
+static int adam_common(const gdrf_shape* s, float* theta_u, const float* theta_c, const float* grad, float* m, float* v,
+                       float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay, float clip,
+                       int step, float grad_scale, int learn_z, gdrf_stream_t stream) {
   Plan p;
   if (int e = make_plan(s, p)) return e;
   if (int e = check_device()) return e;
@@ -437,9 +438,48 @@ int gdrf_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, co
   h.bc1 = 1.f - powf(beta1, (float)step);
   h.bc2 = 1.f - powf(beta2, (float)step);
   h.grad_scale = grad_scale;
+  h.clip = clip;
   long long blocks = (f.total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_adam<<<(int)blocks, 256, 0, st>>>(f, theta_u, theta_c, grad, row_scratch, m, v, h, learn_z);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int gdrf_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, const float* grad, float* m, float* v,
+                   float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, int learn_z, gdrf_stream_t stream) {
+  return adam_common(s, theta_u, theta_c, grad, m, v, row_scratch, lr, beta1, beta2, eps, weight_decay, 0.f, step,
+                     grad_scale, learn_z, stream);
+}
+
+int gdrf_clipped_adam_step(const gdrf_shape* s, float* theta_u, const float* theta_c, const float* grad, float* m,
+                           float* v, float* row_scratch, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float clip_norm, int step, float grad_scale, int learn_z,
+                           gdrf_stream_t stream) {
+  if (!(clip_norm > 0.f)) return fail(1, "clip_norm must be positive%s");
+  return adam_common(s, theta_u, theta_c, grad, m, v, row_scratch, lr, beta1, beta2, eps, weight_decay, clip_norm, step,
+                     grad_scale, learn_z, stream);
+}
+
+int gdrf_gather_rows(const float* xs, const int32_t* ws, const int64_t* index, int64_t n_sel, int64_t n_rows, int32_t d,
+                     int32_t v, float* xs_out, int32_t* ws_out, int* dev_status, gdrf_stream_t stream) {
+  if (int e = check_device()) return e;
+  if (n_sel < 0 || n_rows < 1) return fail(1, "n_sel must be >= 0 and n_rows >= 1%s");
+  if (d < 1 || d > MAX_D) return fail(1, "d must be in [1, 8]%s");
+  if (v < 1) return fail(1, "v must be positive%s");
+  if (n_sel == 0) return 0;
+  if (!xs || !ws || !index || !xs_out || !ws_out) return fail(1, "null pointer argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blocks = (n_sel + 7) / 8;                       // one warp per selected row, 8 warps per block
+  if (blocks > DEFAULT_SMS * 8) blocks = DEFAULT_SMS * 8;
+  const bool vec = (v % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(ws_out)) % 16 == 0);
+  if (vec)
+    k_gather_rows<true><<<(int)blocks, 256, 0, st>>>(xs, ws, (const long long*)index, n_sel, n_rows, d, v, xs_out, ws_out,
+                                                     dev_status);
+  else
+    k_gather_rows<false><<<(int)blocks, 256, 0, st>>>(xs, ws, (const long long*)index, n_sel, n_rows, d, v, xs_out, ws_out,
+                                                      dev_status);
   LAUNCH_CHECK();
   return 0;
 }

@@ -91,6 +91,8 @@ struct AdamHyper {
   float lr, beta1, beta2, eps, weight_decay;   // weight_decay > 0: decoupled (AdamW)
   float bc1, bc2;                               // 1 - beta1^t, 1 - beta2^t
   float grad_scale;                             // d loss / d ELBO  (= -1 / N for the reference's loss)
+  float clip;                                   // > 0: pyro.optim.ClippedAdam (element-wise clamp, L2 weight decay,
+                                                //      denom = sqrt(v) + eps, step = lr sqrt(bc2) / bc1); 0: Adam / AdamW
 };
 
 // grad is d ELBO / d constrained (the flat output of gdrf_elbo_step); one fused pass: chain rule to the
@@ -118,6 +120,17 @@ __global__ void k_adam(FlatLayout f, float* __restrict__ u, const float* __restr
       g *= c[t];
     }
     float x = u[t];
+    if (h.clip > 0.f) {
+      // pyro.optim.ClippedAdam (scripts/mvco.py:135): clamp, then L2 decay folded into the gradient
+      g = fminf(fmaxf(g, -h.clip), h.clip);
+      if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, x, g);
+      const float mc = h.beta1 * m[t] + (1.f - h.beta1) * g;
+      const float vc = h.beta2 * v[t] + (1.f - h.beta2) * g * g;
+      m[t] = mc;
+      v[t] = vc;
+      u[t] = x - (h.lr * sqrtf(h.bc2) / h.bc1) * mc / (sqrtf(vc) + h.eps);
+      continue;
+    }
     if (h.weight_decay > 0.f) x -= h.lr * h.weight_decay * x;
     const float mm = h.beta1 * m[t] + (1.f - h.beta1) * g;
     const float vv = h.beta2 * v[t] + (1.f - h.beta2) * g * g;

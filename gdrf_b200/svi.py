@@ -32,6 +32,43 @@ def shard_bounds(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class ClippedAdam(torch.optim.Optimizer):
+    """``pyro.optim.ClippedAdam`` (pyro-ppl 1.8.0 ``pyro/optim/clipped_adam.py``; the optimiser of
+    ``scripts/mvco.py:135`` and OPTIMIZER_DICT["clippedadam"], ``train_script.py:75``) for the un-fused path: the
+    gradient is clamped element-wise to ``[-clip_norm, clip_norm]``, weight decay is L2, the learning rate decays by
+    ``lrd`` every step, ``denom = sqrt(v) + eps`` and ``step = lr sqrt(1 - beta2^t) / (1 - beta1^t)``."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, clip_norm=10.0, lrd=1.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_norm=clip_norm,
+                                      lrd=lrd))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            group["lr"] *= group["lrd"]
+            beta1, beta2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                grad = p.grad.clamp_(-group["clip_norm"], group["clip_norm"])
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(grad)
+                    state["exp_avg_sq"] = torch.zeros_like(grad)
+                state["step"] += 1
+                if group["weight_decay"] != 0:
+                    grad = grad.add(p, alpha=group["weight_decay"])
+                state["exp_avg"].mul_(beta1).add_(grad, alpha=1 - beta1)
+                state["exp_avg_sq"].mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                denom = state["exp_avg_sq"].sqrt().add_(group["eps"])
+                bc1 = 1 - beta1 ** state["step"]
+                bc2 = 1 - beta2 ** state["step"]
+                p.addcdiv_(state["exp_avg"], denom, value=-group["lr"] * (bc2 ** 0.5) / bc1)
+        return loss
+
+
 class SVI:
     def __init__(self, model, guide=None, optim: Optional[torch.optim.Optimizer] = None, loss=None, group=None):
         self.module = getattr(model, "__self__", model)
@@ -68,7 +105,10 @@ class FusedSVI:
     """
 
     def __init__(self, module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 group=None):
+                 group=None, clip_norm: float = 0.0, lrd: float = 1.0):
+        """``clip_norm > 0`` selects pyro's ClippedAdam (with its ``lrd`` decay and L2 ``weight_decay``) instead of
+        Adam / AdamW."""
+        self.clip_norm, self.lrd = float(clip_norm), float(lrd)
         import ctypes
         from . import _lib
         self._ct, self._lib = ctypes, _lib
@@ -128,10 +168,17 @@ class FusedSVI:
             dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=self.group)
         self.t += 1
         st = torch.cuda.current_stream(self.theta_u.device).cuda_stream
-        self._lib.check(self._lib.load().gdrf_adam_step(
-            self._ct.byref(self.shape), self.theta_u.data_ptr(), self.theta_c.data_ptr(), flat.data_ptr(),
-            self.mom1.data_ptr(), self.mom2.data_ptr(), self.row_scratch.data_ptr(), self.lr, self.betas[0],
-            self.betas[1], self.eps, self.weight_decay, self.t, -1.0 / n_global, self.learn_z, st))
+        if self.clip_norm > 0.0:
+            self.lr *= self.lrd       # ClippedAdam decays before the update
+            self._lib.check(self._lib.load().gdrf_clipped_adam_step(
+                self._ct.byref(self.shape), self.theta_u.data_ptr(), self.theta_c.data_ptr(), flat.data_ptr(),
+                self.mom1.data_ptr(), self.mom2.data_ptr(), self.row_scratch.data_ptr(), self.lr, self.betas[0],
+                self.betas[1], self.eps, self.weight_decay, self.clip_norm, self.t, -1.0 / n_global, self.learn_z, st))
+        else:
+            self._lib.check(self._lib.load().gdrf_adam_step(
+                self._ct.byref(self.shape), self.theta_u.data_ptr(), self.theta_c.data_ptr(), flat.data_ptr(),
+                self.mom1.data_ptr(), self.mom2.data_ptr(), self.row_scratch.data_ptr(), self.lr, self.betas[0],
+                self.betas[1], self.eps, self.weight_decay, self.t, -1.0 / n_global, self.learn_z, st))
         elbo = terms[0] + terms[3] + terms[2] - terms[1]
         return float((-elbo / n_global).item())
 

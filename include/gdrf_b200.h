@@ -143,6 +143,23 @@ int gdrf_adam_step(const gdrf_shape* shape, float* theta_u, const float* theta_c
                    float* v, float* row_scratch, float lr, float beta1, float beta2, float eps, float weight_decay,
                    int step, float grad_scale, int learn_z, gdrf_stream_t stream);
 
+/* pyro.optim.ClippedAdam on the same flat buffers (scripts/mvco.py:135; OPTIMIZER_DICT "clippedadam",
+ * train_script.py:75): the chained gradient is clamped to [-clip_norm, clip_norm] element-wise, weight_decay is L2
+ * (added to the clamped gradient), denom = sqrt(v) + eps and step size = lr sqrt(1 - beta2^t) / (1 - beta1^t).  ClippedAdam's
+ * learning-rate decay (lr *= lrd before every step) is applied by the caller: pass lr = lr0 * lrd^step.                */
+int gdrf_clipped_adam_step(const gdrf_shape* shape, float* theta_u, const float* theta_c, const float* grad, float* m,
+                           float* v, float* row_scratch, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float clip_norm, int step, float grad_scale, int learn_z,
+                           gdrf_stream_t stream);
+
+/* Streaming / mini-batch inference (train_script.py:442-460: `xs[selection, ...]`, `ws[selection, ...]` with a multiset
+ * `selection` drawn on the host every sub-epoch): xs_out[i] = xs[index[i]], ws_out[i] = ws[index[i]] for i < n_sel, with
+ * the data set [n_rows, d] / [n_rows, v] resident on the device.  index: DEVICE int64, negative values count from the end
+ * like numpy.  An out-of-range index zero-fills its row and, when dev_status (DEVICE int, caller-zeroed, may be NULL) is
+ * given, records 1 + the first offending position there (the reference raises IndexError).                           */
+int gdrf_gather_rows(const float* xs, const int32_t* ws, const int64_t* index, int64_t n_sel, int64_t n_rows, int32_t d,
+                     int32_t v, float* xs_out, int32_t* ws_out, int* dev_status, gdrf_stream_t stream);
+
 /* Instrumentation for bench.py: kernels launched by this process so far; CUDA-event timing of the six
  * contractions (ms[7] / launches[7] in the order G1, G2, k_scale_w, G3, G4, G5, G6, summed since
  * the previous read; the read synchronises the device).  Off by default.                                   */

@@ -1,0 +1,124 @@
+"""Streaming / mini-batch inference and the ClippedAdam tail on the B200: the gather kernel
+is bit-exact against torch indexing, a streamed step equals the oracle's ELBO of the gathered rows under the full data
+set's 1/N, and the fused ClippedAdam follows autograd + the host ClippedAdam."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gdrf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,D,V,n_sel", [(1000, 2, 24, 333), (4096, 3, 512, 10000), (77, 1, 17, 5), (300, 8, 6, 1)])
+def test_gather_rows_is_bit_exact(N, D, V, n_sel):
+    from gdrf_b200.streaming import StreamingData
+    g = torch.Generator().manual_seed(N + V)
+    xs = torch.rand(N, D, generator=g)
+    ws = torch.randint(0, 1 << 20, (N, V), generator=g, dtype=torch.int32)
+    data = StreamingData(xs, ws, device="cuda:0")
+    sel = torch.randint(-N, N, (n_sel,), generator=g)           # multiset, negative indices count from the end
+    for s in (sel.numpy(), sel.tolist(), sel, sel.cuda()):
+        xo, wo = data.gather(s)
+        assert torch.equal(xo.cpu(), xs[sel]) and torch.equal(wo.cpu(), ws[sel])
+    xo, wo = data.gather(np.zeros(0, dtype=np.int64))
+    assert xo.shape == (0, D) and wo.shape == (0, V)
+    with pytest.raises(IndexError):
+        data.gather([0, N])
+    with pytest.raises(IndexError):
+        data.gather(torch.tensor([1, 2, -N - 1], device="cuda:0"))
+
+
+def _model(src, K, V, grid, fixed=False):
+    from gdrf_b200 import RBF, SparseMultinomialGDRF
+    m = SparseMultinomialGDRF(num_observation_categories=V, num_topic_categories=K, world=[(0.0, 1.0)] * 2,
+                              kernel=RBF(2, variance=src.variance, lengthscale=src.lengthscale), dirichlet_param=0.01,
+                              n_points=grid, inducing_init="grid", device="cuda:0", jitter=1e-4, maxjitter=15,
+                              fixed_inducing_points=fixed)
+    with torch.no_grad():
+        m.u_loc_unconstrained.copy_(src.u_loc.cuda())
+        m._word_topic_matrix_map_unconstrained.copy_(src.phi.log().cuda())
+    return m
+
+
+def test_streamed_step_is_the_oracle_elbo_of_the_gathered_rows_under_the_full_scale():
+    """train_script.py:365 fixes the scale at 1 / len(xs); a streamed step evaluates the selected multiset of rows
+    under it (the Dirichlet prior is not rescaled)."""
+    from gdrf_b200 import SVI
+    from gdrf_b200.streaming import StreamingData, streaming_epoch, streaming_selection
+    src = O.make_problem(N=600, D=2, K=3, V=20, grid=[5, 5], seed=77)
+    m = _model(src, 3, 20, 5)
+    data = StreamingData(src.xs, src.ws, device="cuda:0")
+    rng = np.random.RandomState(3)
+    sel = streaming_selection(epoch=400, n_data=600, epochs=600, streaming_inference="uniform_exp", streaming_size=64,
+                              streaming_exp=0.01, streaming_weight=0.3, rng=np.random.RandomState(3))
+    eps = torch.randn(3, 64, generator=torch.Generator().manual_seed(11))
+    svi = SVI(m.model, m.guide, None, loss=None)
+    loss = streaming_epoch(svi, data, epoch=400, epochs=600, streaming_inference="uniform_exp", streaming_size=64,
+                           streaming_exp=0.01, streaming_weight=0.3, rng=rng, eps_fn=lambda n: eps.cuda())
+    # oracle on the same rows with the model's current (constrained) parameters, loss scaled by the FULL N
+    sub = copy.copy(src)
+    sub.xs, sub.ws, sub.eps = src.xs[sel], src.ws[sel], eps
+    sub.Z = m._inducing_points.detach().cpu()
+    sub.u_scale_tril = m.u_scale_tril.detach().cpu()
+    sub.noise = m.noise.detach().cpu()
+    sub.phi = m._word_topic_matrix_map.detach().cpu()
+    sub.beta = m._dirichlet_param.cpu()
+    sub.variance = m._kernel.variance.detach().cpu()
+    sub.lengthscale = m._kernel.lengthscale.detach().cpu()
+    sub.n_global = 600
+    o64, g64 = O.loss_and_grads(sub.to(torch.float64), twice=False)
+    want = o64["loss"].item()
+    assert abs(loss - want) <= 1e-5 * abs(want), (loss, want)
+    got = m.u_loc_unconstrained.grad.cpu().double()           # u_loc is unconstrained: d loss / d u_loc directly
+    assert O.rel_err(got, g64["u_loc"]) <= 3e-4, O.rel_err(got, g64["u_loc"])
+
+
+@pytest.mark.parametrize("wd,fixed", [(0.0, False), (0.02, True)])
+def test_fused_clipped_adam_matches_autograd_plus_host_clipped_adam(wd, fixed):
+    from gdrf_b200 import SVI, ClippedAdam, FusedSVI
+    src = O.make_problem(N=800, D=2, K=3, V=17, grid=[5, 5], seed=131)
+    m1 = _model(src, 3, 17, 5, fixed)
+    m2 = copy.deepcopy(m1)
+    kw = dict(lr=1e-2, betas=(0.95, 0.999), weight_decay=wd, clip_norm=0.05, lrd=0.97)
+    ref = SVI(m1.model, m1.guide, ClippedAdam(m1.parameters(), **kw), loss=None)
+    fused = FusedSVI(m2, **kw)
+    xs, ws = src.xs.cuda(), src.ws.cuda()
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    for it in range(4):
+        eps = torch.randn(3, 800, device="cuda:0", generator=gen)
+        l1 = ref.step(xs=xs, ws=ws, eps=eps)
+        l2 = fused.step(xs, ws, eps=eps)
+        assert abs(l1 - l2) <= 2e-5 * abs(l1), (it, l1, l2)
+    fused.write_back()
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert n1 == n2
+        if n1 == "u_scale_tril_unconstrained":
+            p1, p2 = p1.tril(), p2.tril()
+        diff = (p1 - p2).abs()
+        assert diff.mean().item() <= 2e-4 and diff.max().item() <= 4.1e-2, (n1, diff.mean().item(), diff.max().item())
+
+
+def test_streaming_training_loop_fused_equals_unfused():
+    """A few epochs of the reference's streaming loop (sliding truncated window, several sub-epochs) through FusedSVI
+    and through SVI + torch Adam draw the same rows and follow the same losses."""
+    from gdrf_b200 import SVI, FusedSVI
+    from gdrf_b200.streaming import StreamingData, streaming_epoch
+    src = O.make_problem(N=500, D=2, K=3, V=20, grid=[5, 5], seed=9)
+    m1 = _model(src, 3, 20, 5)
+    m2 = copy.deepcopy(m1)
+    data = StreamingData(src.xs, src.ws, device="cuda:0")
+    a = SVI(m1.model, m1.guide, torch.optim.Adam(m1.parameters(), lr=5e-3), loss=None)
+    b = FusedSVI(m2, lr=5e-3)
+    kw = dict(epochs=500, streaming_inference="exp_now", streaming_size=48, streaming_subepochs=2,
+              streaming_truncate=100, streaming_exp=0.05, streaming_weight=0.2)
+    for epoch in (150, 151, 152):
+        ga = torch.Generator(device="cuda:0").manual_seed(epoch)
+        gb = torch.Generator(device="cuda:0").manual_seed(epoch)
+        la = streaming_epoch(a, data, epoch, rng=np.random.RandomState(epoch),
+                             eps_fn=lambda n: torch.randn(3, n, device="cuda:0", generator=ga), **kw)
+        lb = streaming_epoch(b, data, epoch, rng=np.random.RandomState(epoch),
+                             eps_fn=lambda n: torch.randn(3, n, device="cuda:0", generator=gb), **kw)
+        assert abs(la - lb) <= 5e-5 * abs(la), (epoch, la, lb)

@@ -182,3 +182,63 @@ def test_csv_ingest_matches_reference_recipe(tmp_path):
     p1.write_text("t,a,b\n10,1,0\n20,0,5\n40,2,2\n")
     xs1, ws1, world1 = load_counts_csv(str(p1), 1)
     assert xs1.shape == (3, 1) and torch.allclose(xs1[:, 0], torch.tensor([0.0, 1.0 / 3.0, 1.0]))
+
+
+def test_streaming_sampler_reproduces_the_reference_source_lines():
+    """tests/golden/ref_streaming.json was produced by executing train_script.py:396-452 itself
+    (oracle/make_streaming_fixtures.py): same probabilities bit for bit, same rows from the seeded numpy generator."""
+    import json
+    import numpy as np
+    from gdrf_b200.streaming import streaming_probabilities, streaming_selection, streaming_window
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_streaming.json")))
+    assert {c["inference"] for c in cases} == {"uniform", "now", "exp", "uniform_now", "exp_now", "uniform_exp"}
+    for c in cases:
+        n_stream = streaming_window(c["epoch"], c["n_data"], c["epochs"], c["truncate"], c["batch"])
+        assert n_stream == c["n_stream"], c
+        p = streaming_probabilities(c["inference"], n_stream, c["exp"], c["weight"])
+        assert [float(q) for q in p] == c["p"], c["inference"]
+        np.random.seed(c["seed"])
+        sel = streaming_selection(c["epoch"], c["n_data"], c["epochs"], c["inference"], c["size"], c["truncate"],
+                                  c["exp"], c["weight"], c["batch"])
+        assert sel.dtype == np.int64 and sel.tolist() == c["selection"], c
+        # with streaming_batch_splits AND streaming_truncate the reference offsets by `epoch`, not the effective epoch
+        # (train_script.py:447-451), so rows wrap around from the end like any negative numpy index: kept as is
+        assert sel.min() >= -c["n_data"] and sel.max() < c["n_data"]
+    with pytest.raises(ValueError):
+        streaming_probabilities("latest", 3)
+
+
+def test_clipped_adam_follows_the_published_update():
+    """gdrf_b200.svi.ClippedAdam against the update written out by hand (pyro-ppl 1.8.0 clipped_adam.py): clamp, L2
+    decay, lr decay before the step, denom = sqrt(v) + eps."""
+    import math
+    from gdrf_b200.svi import ClippedAdam
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(7, dtype=torch.float64))
+    x = p.detach().clone()
+    opt = ClippedAdam([p], lr=0.05, betas=(0.95, 0.999), eps=1e-8, weight_decay=0.01, clip_norm=0.3, lrd=0.9)
+    m = torch.zeros_like(x)
+    v = torch.zeros_like(x)
+    lr = 0.05
+    for t in range(1, 6):
+        g = torch.randn(7, dtype=torch.float64) * (2.0 if t % 2 else 0.1)
+        p.grad = g.clone()
+        opt.step()
+        lr *= 0.9
+        gc = g.clamp(-0.3, 0.3) + 0.01 * x
+        m = 0.95 * m + 0.05 * gc
+        v = 0.999 * v + 0.001 * gc * gc
+        x = x - lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.95 ** t) * m / (v.sqrt() + 1e-8)
+        assert torch.allclose(p.detach(), x, rtol=1e-12, atol=1e-14), t
+
+
+def test_streaming_data_refuses_cpu_and_bad_indices():
+    from gdrf_b200.streaming import StreamingData
+    d = StreamingData(torch.rand(5, 2), torch.ones(5, 3, dtype=torch.int32), device="cpu")
+    with pytest.raises(IndexError):
+        d.gather([0, 5])
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            d.gather([0, 1])
+    with pytest.raises(ValueError):
+        StreamingData(torch.rand(5, 2), torch.ones(4, 3, dtype=torch.int32), device="cpu")
