@@ -286,6 +286,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp);
       g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
+      g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
   }
@@ -645,6 +646,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       G3::Params g{};
       g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
       g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
+      g.varn = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_FULL_WIDTH)) ? 0 : 1;
       { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {

@@ -398,6 +398,17 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on 
                : "memory");
 }
 
+// Triangular operands inside a diagonal tile: a policy with `VARN != 0` tells the pair kernel, per k-block, how many
+// of the 256 accumulator columns can be non-zero (`ncols`, a multiple of 64).  The issuer then runs a narrower MMA on
+// the column window [128 - N/2, 128 + N/2) of the accumulator -- each CTA of the pair supplies the N/2 B rows that
+// sit next to the centre, so the policy orders its columns with the most-needed groups in the middle -- and the
+// producer stages only those rows (`load_b`).  `kblock` lets the policy walk the k-blocks so that the first one is
+// full width (it initialises the whole accumulator).
+template <class P, class = void>
+struct VarN { static constexpr int value = 0; };
+template <class P>
+struct VarN<P, std::void_t<decltype(P::VARN)>> { static constexpr int value = P::VARN; };
+
 template <class P>
 struct Gemm2Cfg {
   static_assert(P::BN == 256, "pair kernel computes 256 x 256 tiles");
@@ -469,6 +480,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
             const uint32_t ph = (it / NST) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            if constexpr (VarN<P>::value != 0) {
+              const int kb = P::kblock(kit, kn);
+              const int ncols = P::ncols(prm, kb, kn);
+              mbar_arrive_expect_tx(&full_bar[s], P::PA * Cfg::A_BYTES + P::PB * (ncols >> 1) * 128);
+#pragma unroll
+              for (int pl = 0; pl < P::PA; ++pl)
+                bulk_g2s(st + pl * Cfg::A_BYTES, P::a_src(prm, item, sub, kb, pl, 0), 16384, &full_bar[s]);
+#pragma unroll
+              for (int pl = 0; pl < P::PB; ++pl)
+                P::load_b(prm, item, sub, kb, pl, (int)rank, ncols, st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES,
+                          &full_bar[s]);
+              continue;
+            }
             mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
 #pragma unroll
             for (int pl = 0; pl < P::PA; ++pl) {
@@ -524,6 +548,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
               const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
               const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
               bool first = (kit == 0);
+              uint32_t idesc_k = idesc, d_k = d_tmem;
+              if constexpr (VarN<P>::value != 0) {
+                const int ncols = P::ncols(prm, P::kblock(kit, kn), kn);   // first k-block is full width by contract
+                idesc_k = make_idesc(256, ncols, P::A_MN, P::B_MN, P::FMT);
+                d_k = d_tmem + (128 - (ncols >> 1));
+              }
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -535,7 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
                     const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
                     const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
                     const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
-                    umma2_f16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                    umma2_f16(d_k, da, db, idesc_k, first ? 0u : 1u);
                     first = false;
                   }
                 }

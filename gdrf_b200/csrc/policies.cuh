@@ -131,6 +131,7 @@ struct G2 {
                        //           halves of a row add their partial sums
     int store_t;       // write TP (gradient pass)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
+    int varn;          // CTA pairs: 1 = narrow MMAs in the diagonal blocks, 0 = full width (GDRF_FLAG_FULL_WIDTH, A/B)
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.K * p.NT; }
@@ -143,6 +144,28 @@ struct G2 {
     const int jt = sub % p.NT;
     return p.st.base + pl * p.st.plane_stride + p.st.block_off(sub * PCS + pc, CB * jt + kit);
   }
+  // MODE 2, CTA pairs: the first four k-blocks of a column tile are its diagonal 256 x 256 block of S_k, where
+  // k-block b only reaches the columns j < 64 (b + 1).  The fp16 ST planes are stored with the rows of every 256-row
+  // tile in the order [g3a g2a g1a g0a | g0b g1b g2b g3b] (gXa / gXb: first / second 32 rows of 64-row group X,
+  // k_pack_st), so the needed rows are the ones next to the middle: rank 0 stages the last N/2 rows of its block,
+  // rank 1 the first N/2 of its, and the MMA covers accumulator columns [128 - N/2, 128 + N/2).  The k-blocks are
+  // walked last-to-first so that the first MMA is full width; 15 % fewer MMA columns per tile row.
+  static constexpr int VARN = (MODE == 2) ? 1 : 0;
+  __device__ static int kblock(int kit, int kn) { return kn - 1 - kit; }
+  __device__ static int ncols(const Params& p, int kb, int) {
+    return (kb >= 4 || p.varn == 0) ? 256 : 64 * (kb + 1);
+  }
+  __device__ static void load_b(const Params& p, int item, int sub, int kb, int pl, int rank, int ncols, uint8_t* dst,
+                                uint64_t* bar) {
+    const bf16* blk = b_src(p, item, sub, kb, pl, rank);
+    const int rows = ncols >> 1;
+    bulk_g2s(dst, rank == 0 ? blk + (128 - rows) * 64 : blk, rows * 128, bar);
+  }
+  // accumulator column -> column of the tile under that row order (identity for the other modes)
+  __device__ static int tile_col(int c) {
+    if (MODE != 2) return c;
+    return c < 128 ? 64 * (3 - (c >> 5)) + (c & 31) : 64 * ((c - 128) >> 5) + 32 + (c & 31);
+  }
   struct Epi {
     double qacc;
     __device__ void item_begin(const Params&, int, int) { qacc = 0.0; }
@@ -153,7 +176,7 @@ struct G2 {
       qacc += sumsq32(v);
       if (p.store_t) {
         const int r = item * 128 + row;
-        const int col0 = sub * BN + c0;     // (k * NT + jt) * BN == k * Mp + jt * BN
+        const int col0 = sub * BN + tile_col(c0);     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
         for (int g = 0; g < 4; g += 2) {
           uint4 pa[2], pb[2];
@@ -187,6 +210,7 @@ struct G3 {
     const float* g2;   // [K][ncp]
     float* dw;         // [ncp][Mp] fp32
     int RT, MB, K, JT, Mp, ncp;
+    int varn;          // CTA pairs only: narrow MMAs in the diagonal block + the column order that goes with them
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.JT * p.K; }   // sub = it * K + k
@@ -199,6 +223,22 @@ struct G3 {
     const int it = sub / p.K, k = sub - it * p.K;
     return p.st.base + pl * p.st.plane_stride + p.st.block_off(k * 2 * p.JT + (kit >> 1), it * 4 + pc) +
            (kit & 1) * 4096;
+  }
+  // CTA pairs (Params::varn): the LAST four k-blocks of a column tile are its diagonal block, where k-block b only
+  // reaches the columns i >= 64 b.  The accumulator holds the four 64-column groups in the order [g0 g2 | g3 g1], so
+  // the last two k-blocks run 128-wide MMAs on the middle of it (rank 0 stages g2, rank 1 g3); 10 % fewer MMA columns.
+  static constexpr int VARN = 2;
+  __device__ static int kblock(int kit, int) { return kit; }
+  __device__ static int ncols(const Params& p, int kb, int kn) { return (p.varn && kb >= kn - 2) ? 128 : 256; }
+  __device__ static void load_b(const Params& p, int item, int sub, int kb, int pl, int rank, int ncols, uint8_t* dst,
+                                uint64_t* bar) {
+    if (ncols == 256) {
+      const int p0 = p.varn ? (rank == 0 ? 0 : 3) : 2 * rank, p1 = p.varn ? (rank == 0 ? 2 : 1) : 2 * rank + 1;
+      bulk_g2s(dst, b_src(p, item, sub, kb, pl, p0), 8192, bar);
+      bulk_g2s(dst + 8192, b_src(p, item, sub, kb, pl, p1), 8192, bar);
+    } else {
+      bulk_g2s(dst, b_src(p, item, sub, kb, pl, rank == 0 ? 2 : 3), 8192, bar);
+    }
   }
   struct Epi {
     float acc[128];
@@ -239,9 +279,15 @@ struct G3 {
       if (sub % p.K != p.K - 1) return;
       const int it = sub / p.K;
       const int half = last_c0 >> 7;
-      float4* dst = reinterpret_cast<float4*>(p.dw + (long long)(item * 128 + row) * p.Mp + it * 256 + half * 128);
+      float* base = p.dw + (long long)(item * 128 + row) * p.Mp + it * 256;
+      // 64-column groups held by this thread: natural order, or [g0 g2 | g3 g1] under varn
+      float4* d0 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 192 : 0) : half * 128));
+      float4* d1 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 64 : 128) : half * 128 + 64));
 #pragma unroll
-      for (int g = 0; g < 32; ++g) dst[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+      for (int g = 0; g < 16; ++g) d0[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+#pragma unroll
+      for (int g = 0; g < 16; ++g)
+        d1[g] = make_float4(acc[64 + 4 * g], acc[65 + 4 * g], acc[66 + 4 * g], acc[67 + 4 * g]);
     }
     __device__ void item_end(const Params&, int, int) {}
   };

@@ -123,7 +123,12 @@ __global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, in
     uint4 hk[2];
     split8h<2>(v, hk);
 #pragma unroll
-    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st16.elem(pl, row, it * 64 + g * 8)) = hk[pl];
+    // fp16 planes: rows of every 256-row tile in the order [g3a g2a g1a g0a | g0b g1b g2b g3b] (policies.cuh, G2)
+    const int jl = (jt * 64 + jj) & 255, X = jl >> 6, w32 = jl & 31;
+    const int pos = (jl & 32) ? 128 + 32 * X + w32 : 32 * (3 - X) + w32;
+    const int row16 = row - jl + pos;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st16.elem(pl, row16, it * 64 + g * 8)) = hk[pl];
   }
 }
 

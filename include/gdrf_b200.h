@@ -43,6 +43,9 @@ enum {
                                      adjoint, prior, gradient assembly, terms)                                 */
   GDRF_FLAG_SINGLE_CTA = 32,      /* run the four large contractions on single CTAs (cta_group::1) instead of
                                      CTA pairs (cta_group::2); same results, used for A/B measurement         */
+  GDRF_FLAG_FULL_WIDTH = 1 << 14, /* issue full 256-column MMAs in the diagonal blocks of the triangular operands too
+                                     (default: narrower MMAs there, 10-15 % fewer MMA columns); same results up to
+                                     fp32 summation order, used for A/B measurement                           */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
   GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
   GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,

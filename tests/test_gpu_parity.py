@@ -111,6 +111,20 @@ def test_tensor_path_matches_plain_fma_checker():
         assert O.rel_err(g_tc[k], g_rf[k]) < (2 * HYPER_TOL if k in HYPER else 1e-3), k
 
 
+def test_narrow_diagonal_mmas_agree_with_full_width():
+    """The CTA-pair kernels shrink the MMA to the non-zero columns inside the diagonal blocks of S_k (column windows
+    of 64 ... 256 around the middle of a permuted accumulator); GDRF_FLAG_FULL_WIDTH issues full 256-column MMAs over
+    the same operands.  Only the fp32 summation order may differ."""
+    from gdrf_b200 import _lib
+    for grid, K in (([20, 20], 3), ([31, 31], 2)):       # Mp = 512 (two column tiles) and Mp = 1024 (four)
+        inp = O.make_problem(N=1500, D=2, K=K, V=24, grid=grid, kernel="matern32", seed=grid[0])
+        t_n, g_n, _ = _run(inp)
+        t_f, g_f, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_FULL_WIDTH)
+        assert torch.allclose(t_n, t_f, rtol=1e-7, atol=1e-3)
+        for k in g_n:
+            assert O.rel_err(g_n[k], g_f[k]) < (1e-3 if k in HYPER else 2e-5), (grid, k, O.rel_err(g_n[k], g_f[k]))
+
+
 def test_fp16_forward_agrees_with_24bit_forward_and_falls_back_out_of_range():
     """The default forward row-norm contraction uses 2 fp16 planes (22-bit operands, 3 MMAs per product); the
     24-bit bf16 path (6 MMAs) is selected by flag and automatically when u_scale_tril leaves the fp16 range."""
