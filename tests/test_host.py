@@ -242,3 +242,33 @@ def test_streaming_data_refuses_cpu_and_bad_indices():
             d.gather([0, 1])
     with pytest.raises(ValueError):
         StreamingData(torch.rand(5, 2), torch.ones(4, 3, dtype=torch.int32), device="cpu")
+
+
+def test_checkpoint_interchange_follows_the_reference_resume_logic(tmp_path):
+    """make_checkpoint / load_checkpoint: fp16 state dict out, fp32 intersection on key + shape in, strict=False
+    (train_script.py:338-357, 490-499; general.py:455-461)."""
+    from gdrf_b200.checkpoint import intersect_dicts, load_checkpoint, make_checkpoint, strip_optimizer
+    a = _cpu_model()
+    with torch.no_grad():
+        for p in a.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    ck = make_checkpoint(a, epoch=6, best_fitness=-12.5, optimizer_state={"t": 6})
+    assert all(v.dtype == torch.float16 for v in ck["model"].values() if v.is_floating_point())
+    torch.save(ck, tmp_path / "last.pt")
+    ck2 = torch.load(tmp_path / "last.pt", weights_only=False)
+    b = _cpu_model()
+    n, start_epoch, best = load_checkpoint(b, ck2)
+    assert n == len(b.state_dict()) and start_epoch == 7 and best == -12.5
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pb.detach(), pa.detach().half().float()), k
+    # a model of another shape only takes what matches (the kernel's scalars, noise), like intersect_dicts
+    c = _cpu_model(n_points=5)
+    n_c, _, _ = load_checkpoint(c, ck2)
+    assert 0 < n_c < n
+    assert set(intersect_dicts(ck2["model"], c.state_dict())) == {
+        k for k, v in ck2["model"].items() if v.shape == c.state_dict()[k].shape}
+    # a module in ckpt["model"] (what the reference pickles) is read through its state_dict()
+    n_m, _, best_m = load_checkpoint(_cpu_model(), {"model": a, "epoch": -1, "best_fitness": 0.0, "optimizer": None})
+    assert n_m == n and best_m == float("-inf")
+    s = strip_optimizer(ck2)
+    assert s["optimizer"] is None and s["epoch"] == -1
