@@ -372,7 +372,7 @@ def main():
     roofline = None
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r01h_gemm_ncu_summary.json")))
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r01i_gemm_ncu_summary.json")))
         tag = {"G2_fwd": "G2<2>", "G3": "<G3>", "G6": "<G6>", "G1": "<G1T", "G4": "<G4T", "G5": "<G5T"}[dom]
         traffic = next(v["dram_bytes"] for k, v in summ.items() if tag in k)
     except Exception:
@@ -384,7 +384,10 @@ def main():
         # what the tensor pipe is actually asked to do: 3 16-bit MMAs per logical product, and whole 64-row k-blocks
         # of 256-wide tiles where the triangular operand is half empty (Mp / 64 blocks per side)
         MBk = (M + 255) // 256 * 4
-        pad = sum((MBk - 4 * j) * 4 for j in range(MBk // 4)) / (MBk * MBk / 2.0) if dom in ("G2_fwd", "G3", "G6") else 1.0
+        # ... minus the 64-column groups the narrow diagonal-block MMAs leave out (6 of 16 per tile in G2, 4 in G3)
+        narrow = 0 if (flags & _lib.FLAG_FULL_WIDTH) else {"G2_fwd": 6, "G3": 4}.get(dom, 0)
+        pad = (sum((MBk - 4 * j) * 4 - narrow for j in range(MBk // 4)) / (MBk * MBk / 2.0)
+               if dom in ("G2_fwd", "G3", "G6") else 1.0)
         issued = achieved * 3.0 * pad * (float(MBk * 64) / M) ** 2
         roofline = {"bound": "tensor", "kernel": f"gemm_tc2_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
                     "issued": {"tflops": issued, "frac": issued / peak_tf, "mma_per_product": 3, "tile_padding": pad,
