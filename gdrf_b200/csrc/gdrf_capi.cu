@@ -96,10 +96,9 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   long long chunk = s->chunk_rows ? s->chunk_rows : (long long)DEFAULT_SMS * 128;
   const long long nneed = round_up_ll(s->n_local > 0 ? s->n_local : 1, 256);
   if (chunk > nneed) chunk = nneed;
-  if (!s->chunk_rows && s->n_local > chunk) {      // equal chunks: no short last wave (matters when N / ranks is small)
-    const long long nchunks = (s->n_local + chunk - 1) / chunk;
-    chunk = round_up_ll((s->n_local + nchunks - 1) / nchunks, 256);
-  }
+  // full chunks of one 256-row tile per CTA pair plus one short last chunk: G2 / G3 / G6 / G5 cut the items of a short
+  // chunk so that it still fills the machine (policies.cuh: ksplit, isplit, G6's tail pieces), so its cost is
+  // proportional to its rows -- equalised chunks would instead run every round with idle pairs
   p.chunk_rows = (int)chunk;
   p.ncp = chunk;
   const size_t Mp2 = (size_t)p.Mp * p.Mp;
@@ -237,6 +236,19 @@ int launch_du(const Plan& p, PlaneMat w, int RT, void* ws, int sms, cudaStream_t
   return 0;
 }
 
+// G2 on CTA pairs: how many topic groups to cut a pair tile's work into so that `tiles` pair tiles fill `pairs` CTA
+// pairs best: smallest ceil(tiles * s / pairs) / s over the divisors s <= 8 of K (ties: fewer, longer items)
+int topic_split(int K, int tiles, int pairs) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= 8 && sp <= K; ++sp) {
+    if (K % sp) continue;
+    const double cost = (double)((tiles * sp + pairs - 1) / pairs) / sp;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
+
 // the four large contractions run on CTA pairs (cta_group::2) unless the checker or the single-CTA kernel is asked for
 template <class P>
 cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool use_ref, bool single_cta, cudaStream_t st) {
@@ -287,7 +299,10 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
       g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
-      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+      const bool pairs = (s->flags & (GDRF_FLAG_REF_G2 | GDRF_FLAG_SINGLE_CTA)) == 0;
+      g.ksplit = pairs ? topic_split(p.K, (RT + 1) / 2, sms / 2) : 0;
+      const int n_items = pairs ? ((RT + 1) / 2) * 2 * g.ksplit : RT;
+      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
   }
   return 0;
@@ -647,7 +662,9 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
       g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
       g.varn = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_FULL_WIDTH)) ? 0 : 1;
-      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+      g.isplit = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA)) ? 0 : 1;
+      const int n_items = g.isplit ? ((RT + 1) / 2) * 2 * p.JT : RT;
+      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
       const size_t smem = sizeof(float) * (size_t)K * (72 + 128);

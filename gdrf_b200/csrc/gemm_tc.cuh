@@ -409,6 +409,17 @@ struct VarN { static constexpr int value = 0; };
 template <class P>
 struct VarN<P, std::void_t<decltype(P::VARN)>> { static constexpr int value = P::VARN; };
 
+template <class P, bool = (VarN<P>::value != 0)>
+struct VarCtx {
+  struct type {};
+  __device__ static type make(const typename P::Params&, int, int) { return type{}; }
+};
+template <class P>
+struct VarCtx<P, true> {
+  using type = typename P::Ctx;
+  __device__ static type make(const typename P::Params& p, int item, int sub) { return P::make_ctx(p, item, sub); }
+};
+
 template <class P>
 struct Gemm2Cfg {
   static_assert(P::BN == 256, "pair kernel computes 256 x 256 tiles");
@@ -475,6 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
         for (int sub = 0; sub < nsub; ++sub) {
           const int kn = P::k_iters(prm, item, sub);
           const auto octx = OperandCtx<P>::make(prm, item, sub);
+          const auto vctx = VarCtx<P>::make(prm, item, sub);   // operand base addresses of this (item, sub), decoded once
           for (int kit = 0; kit < kn; ++kit, ++it) {
             const int s = it % NST;
             const uint32_t ph = (it / NST) & 1;
@@ -486,10 +498,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
               mbar_arrive_expect_tx(&full_bar[s], P::PA * Cfg::A_BYTES + P::PB * (ncols >> 1) * 128);
 #pragma unroll
               for (int pl = 0; pl < P::PA; ++pl)
-                bulk_g2s(st + pl * Cfg::A_BYTES, P::a_src(prm, item, sub, kb, pl, 0), 16384, &full_bar[s]);
+                bulk_g2s(st + pl * Cfg::A_BYTES, P::a_at(prm, vctx, kb, pl), 16384, &full_bar[s]);
 #pragma unroll
               for (int pl = 0; pl < P::PB; ++pl)
-                P::load_b(prm, item, sub, kb, pl, (int)rank, ncols, st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES,
+                P::load_b(prm, vctx, kb, pl, (int)rank, ncols, st + P::PA * Cfg::A_BYTES + pl * Cfg::B_BYTES,
                           &full_bar[s]);
               continue;
             }

@@ -132,17 +132,29 @@ struct G2 {
     int store_t;       // write TP (gradient pass)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
     int varn;          // CTA pairs: 1 = narrow MMAs in the diagonal blocks, 0 = full width (GDRF_FLAG_FULL_WIDTH, A/B)
+    // CTA pairs: items are (256-row pair tile, group of K / ksplit topics), two consecutive items = the two 128-row
+    // halves of one pair tile.  A chunk with fewer than 74 pair tiles (the last chunk of a shard) then still fills
+    // the machine: ksplit is chosen by the host so that ceil(pair tiles * ksplit / 74) / ksplit is smallest.
+    // 0: one item per 128-row tile with all topics (single-CTA kernel and the checker).
+    int ksplit;
   };
-  __device__ static int num_items(const Params& p) { return p.RT; }
-  __device__ static int num_subs(const Params& p, int) { return p.K * p.NT; }
+  __device__ static int num_items(const Params& p) { return p.ksplit ? ((p.RT + 1) >> 1) * 2 * p.ksplit : p.RT; }
+  __device__ static int row_tile(const Params& p, int item) {
+    return p.ksplit ? ((item >> 1) / p.ksplit) * 2 + (item & 1) : item;
+  }
+  // first (topic, column tile) index of the item
+  __device__ static int sub0(const Params& p, int item) {
+    return p.ksplit ? ((item >> 1) % p.ksplit) * (p.K / p.ksplit) * p.NT : 0;
+  }
+  __device__ static int num_subs(const Params& p, int) { return (p.ksplit ? p.K / p.ksplit : p.K) * p.NT; }
   __device__ static int k_iters(const Params& p, int, int sub) { return p.MB - CB * (sub % p.NT); }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
     const int jt = sub % p.NT;
-    return p.w.base + pl * p.w.plane_stride + p.w.block_off(item, CB * jt + kit);
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(row_tile(p, item), CB * jt + kit);
   }
-  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
+  __device__ static const bf16* b_src(const Params& p, int item, int sub, int kit, int pl, int pc) {
     const int jt = sub % p.NT;
-    return p.st.base + pl * p.st.plane_stride + p.st.block_off(sub * PCS + pc, CB * jt + kit);
+    return p.st.base + pl * p.st.plane_stride + p.st.block_off((sub0(p, item) + sub) * PCS + pc, CB * jt + kit);
   }
   // MODE 2, CTA pairs: the first four k-blocks of a column tile are its diagonal 256 x 256 block of S_k, where
   // k-block b only reaches the columns j < 64 (b + 1).  The fp16 ST planes are stored with the rows of every 256-row
@@ -155,9 +167,23 @@ struct G2 {
   __device__ static int ncols(const Params& p, int kb, int) {
     return (kb >= 4 || p.varn == 0) ? 256 : 64 * (kb + 1);
   }
-  __device__ static void load_b(const Params& p, int item, int sub, int kb, int pl, int rank, int ncols, uint8_t* dst,
+  // operand bases of one (item, sub), decoded once by the producer (a single thread issues every copy of a k-block:
+  // integer divisions per copy would make it the bottleneck)
+  struct Ctx { const bf16 *a0, *b0; };
+  __device__ static Ctx make_ctx(const Params& p, int item, int sub) {
+    const int jt = sub % p.NT;
+    Ctx c;
+    c.a0 = p.w.base + p.w.block_off(row_tile(p, item), CB * jt);
+    c.b0 = p.st.base + p.st.block_off((sub0(p, item) + sub) * PCS, CB * jt);
+    return c;
+  }
+  __device__ static const bf16* a_at(const Params& p, const Ctx& c, int kb, int pl) {
+    return c.a0 + pl * p.w.plane_stride + (long long)kb * TILE_ELEMS;
+  }
+  __device__ static void load_b(const Params& p, const Ctx& c, int kb, int pl, int rank, int ncols, uint8_t* dst,
                                 uint64_t* bar) {
-    const bf16* blk = b_src(p, item, sub, kb, pl, rank);
+    // this CTA's 128-row block of ST (rows already permuted, k_pack_st): row block `rank` of the tile's two
+    const bf16* blk = c.b0 + pl * p.st.plane_stride + ((long long)rank * p.st.col_blocks + kb) * TILE_ELEMS;
     const int rows = ncols >> 1;
     bulk_g2s(dst, rank == 0 ? blk + (128 - rows) * 64 : blk, rows * 128, bar);
   }
@@ -168,15 +194,20 @@ struct G2 {
   }
   struct Epi {
     double qacc;
-    __device__ void item_begin(const Params&, int, int) { qacc = 0.0; }
+    int rt, s0;
+    __device__ void item_begin(const Params& p, int item, int) {
+      qacc = 0.0;
+      rt = row_tile(p, item);
+      s0 = sub0(p, item);
+    }
     __device__ void sub_begin(const Params& p, int, int sub, int) {
       if (sub % p.NT == 0) qacc = 0.0;
     }
-    __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
+    __device__ void chunk(const Params& p, int, int sub, int row, int c0, const float (&v)[32]) {
       qacc += sumsq32(v);
-      if (p.store_t) {
-        const int r = item * 128 + row;
-        const int col0 = sub * BN + tile_col(c0);     // (k * NT + jt) * BN == k * Mp + jt * BN
+      if (p.store_t && rt < p.RT) {
+        const int r = rt * 128 + row;
+        const int col0 = (s0 + sub) * BN + tile_col(c0);     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
         for (int g = 0; g < 4; g += 2) {
           uint4 pa[2], pb[2];
@@ -187,8 +218,9 @@ struct G2 {
         }
       }
     }
-    __device__ void sub_end(const Params& p, int item, int sub, int row) {
-      if ((sub % p.NT) == p.NT - 1) atomicAdd(&p.q[(long long)(sub / p.NT) * p.ncp + item * 128 + row], qacc);
+    __device__ void sub_end(const Params& p, int, int sub, int row) {
+      if ((sub % p.NT) == p.NT - 1 && rt < p.RT)
+        atomicAdd(&p.q[(long long)((s0 + sub) / p.NT) * p.ncp + rt * 128 + row], qacc);
     }
     __device__ void item_end(const Params&, int, int) {}
   };
@@ -211,16 +243,28 @@ struct G3 {
     float* dw;         // [ncp][Mp] fp32
     int RT, MB, K, JT, Mp, ncp;
     int varn;          // CTA pairs only: narrow MMAs in the diagonal block + the column order that goes with them
+    // CTA pairs: items are (column tile, 256-row pair tile), widest column tile first, two consecutive items = the two
+    // 128-row halves of a pair tile; round-robin over the CTA pairs this is the same schedule as one item per row
+    // tile when the chunk has 74 pair tiles, and it spreads a shorter chunk (the last one of a shard) over all SMs.
+    // 0: one item per 128-row tile with all column tiles (single-CTA kernel and the checker).
+    int isplit;
   };
-  __device__ static int num_items(const Params& p) { return p.RT; }
-  __device__ static int num_subs(const Params& p, int) { return p.JT * p.K; }   // sub = it * K + k
-  __device__ static int k_iters(const Params& p, int, int sub) { return 4 * (sub / p.K + 1); }
+  __device__ static int rt2(const Params& p) { return (p.RT + 1) >> 1; }
+  __device__ static int num_items(const Params& p) { return p.isplit ? 2 * rt2(p) * p.JT : p.RT; }
+  __device__ static int row_tile(const Params& p, int item) {
+    return p.isplit ? ((item >> 1) % rt2(p)) * 2 + (item & 1) : item;
+  }
+  __device__ static int col_tile(const Params& p, int item, int sub) {
+    return p.isplit ? p.JT - 1 - (item >> 1) / rt2(p) : sub / p.K;
+  }
+  __device__ static int num_subs(const Params& p, int) { return p.isplit ? p.K : p.JT * p.K; }   // sub = [it * K +] k
+  __device__ static int k_iters(const Params& p, int item, int sub) { return 4 * (col_tile(p, item, sub) + 1); }
   __device__ static const bf16* a_src(const Params& p, int item, int sub, int kit, int pl, int) {
     const int k = sub % p.K;
-    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(item, k * p.MB + kit);
+    return p.tp.base + pl * p.tp.plane_stride + p.tp.block_off(row_tile(p, item), k * p.MB + kit);
   }
-  __device__ static const bf16* b_src(const Params& p, int, int sub, int kit, int pl, int pc) {
-    const int it = sub / p.K, k = sub - it * p.K;
+  __device__ static const bf16* b_src(const Params& p, int item, int sub, int kit, int pl, int pc) {
+    const int it = col_tile(p, item, sub), k = sub % p.K;
     return p.st.base + pl * p.st.plane_stride + p.st.block_off(k * 2 * p.JT + (kit >> 1), it * 4 + pc) +
            (kit & 1) * 4096;
   }
@@ -230,14 +274,27 @@ struct G3 {
   static constexpr int VARN = 2;
   __device__ static int kblock(int kit, int) { return kit; }
   __device__ static int ncols(const Params& p, int kb, int kn) { return (p.varn && kb >= kn - 2) ? 128 : 256; }
-  __device__ static void load_b(const Params& p, int item, int sub, int kb, int pl, int rank, int ncols, uint8_t* dst,
+  struct Ctx { const bf16 *a0, *b0; };
+  __device__ static Ctx make_ctx(const Params& p, int item, int sub) {
+    const int k = sub % p.K;
+    Ctx c;
+    c.a0 = p.tp.base + p.tp.block_off(row_tile(p, item), k * p.MB);
+    c.b0 = p.st.base + p.st.block_off(k * 2 * p.JT, col_tile(p, item, sub) * 4);
+    return c;
+  }
+  __device__ static const bf16* a_at(const Params& p, const Ctx& c, int kb, int pl) {
+    return c.a0 + pl * p.tp.plane_stride + (long long)kb * TILE_ELEMS;
+  }
+  __device__ static void load_b(const Params& p, const Ctx& c, int kb, int pl, int rank, int ncols, uint8_t* dst,
                                 uint64_t* bar) {
+    // 64 (j) x 64 (i) pieces of ST: row block kb >> 1, half (kb & 1), column block = piece
+    const bf16* row = c.b0 + pl * p.st.plane_stride + (long long)(kb >> 1) * p.st.col_blocks * TILE_ELEMS + (kb & 1) * 4096;
     if (ncols == 256) {
       const int p0 = p.varn ? (rank == 0 ? 0 : 3) : 2 * rank, p1 = p.varn ? (rank == 0 ? 2 : 1) : 2 * rank + 1;
-      bulk_g2s(dst, b_src(p, item, sub, kb, pl, p0), 8192, bar);
-      bulk_g2s(dst + 8192, b_src(p, item, sub, kb, pl, p1), 8192, bar);
+      bulk_g2s(dst, row + p0 * TILE_ELEMS, 8192, bar);
+      bulk_g2s(dst + 8192, row + p1 * TILE_ELEMS, 8192, bar);
     } else {
-      bulk_g2s(dst, b_src(p, item, sub, kb, pl, rank == 0 ? 2 : 3), 8192, bar);
+      bulk_g2s(dst, row + (rank == 0 ? 2 : 3) * TILE_ELEMS, 8192, bar);
     }
   }
   struct Epi {
@@ -250,8 +307,8 @@ struct G3 {
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.f;
       }
-      scale = p.g2[(long long)k * p.ncp + item * 128 + row];
-    }
+      scale = p.g2[(long long)k * p.ncp + row_tile(p, item) * 128 + row];   // no state beyond acc[]: the kernel is at
+    }                                                                          // its register limit
     __device__ void chunk(const Params&, int, int, int, int c0, const float (&v)[32]) {
       // c0 is 0/32/64/96 (+128 for the upper-half warps); the unrolled switch keeps acc[] in registers
       switch ((c0 & 127) >> 5) {
@@ -276,10 +333,11 @@ struct G3 {
     }
     int last_c0;
     __device__ void sub_end(const Params& p, int item, int sub, int row) {
-      if (sub % p.K != p.K - 1) return;
-      const int it = sub / p.K;
+      const int rt = row_tile(p, item);
+      if (sub % p.K != p.K - 1 || rt >= p.RT) return;
+      const int it = col_tile(p, item, sub);
       const int half = last_c0 >> 7;
-      float* base = p.dw + (long long)(item * 128 + row) * p.Mp + it * 256;
+      float* base = p.dw + (long long)(rt * 128 + row) * p.Mp + it * 256;
       // 64-column groups held by this thread: natural order, or [g0 g2 | g3 g1] under varn
       float4* d0 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 192 : 0) : half * 128));
       float4* d1 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 64 : 128) : half * 128 + 64));
