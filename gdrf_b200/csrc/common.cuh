@@ -43,51 +43,60 @@ struct PlaneMat {
 };
 
 // error-compensated split of fp32 values into up to three bf16 planes:
-// 8 consecutive fp32 values -> one 16-byte packet per plane
+// 8 consecutive fp32 values -> one 16-byte packet per plane.
+// Two values are converted at a time with the packed cvt.rn.bf16x2.f32 (F2FP.PACK_AB, full ALU rate); the scalar
+// cvt.rn.bf16.f32 is an F2F on the quarter-rate conversion pipe and made the plane-writing epilogues XU-bound.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 template <int P>
 __device__ __forceinline__ void split8(const float* v, uint4 (&pk)[P]) {
-  unsigned short h[P][8];
+  uint32_t w[P][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float r = v[i];
+  for (int i = 0; i < 4; ++i) {
+    float r0 = v[2 * i], r1 = v[2 * i + 1];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      bf16 b = __float2bfloat16_rn(r);
-      r -= __bfloat162float(b);
-      h[p][i] = __bfloat16_as_ushort(b);
+      const uint32_t d = pack_bf16x2(r0, r1);
+      w[p][i] = d;
+      if (p + 1 < P) {
+        r0 -= __uint_as_float(d << 16);
+        r1 -= __uint_as_float(d & 0xffff0000u);
+      }
     }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    pk[p].x = h[p][0] | ((uint32_t)h[p][1] << 16);
-    pk[p].y = h[p][2] | ((uint32_t)h[p][3] << 16);
-    pk[p].z = h[p][4] | ((uint32_t)h[p][5] << 16);
-    pk[p].w = h[p][6] | ((uint32_t)h[p][7] << 16);
-  }
+  for (int p = 0; p < P; ++p) pk[p] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
 }
 
 // 8 consecutive fp32 values -> one 16-byte packet per fp16 plane (x ~= h0 + h1, 22 significant bits for
 // |x| in the normal fp16 range; the caller guarantees |x| < 65504)
 template <int P>
 __device__ __forceinline__ void split8h(const float* v, uint4 (&pk)[P]) {
-  unsigned short h[P][8];
+  uint32_t w[P][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float r = v[i];
+  for (int i = 0; i < 4; ++i) {
+    float r0 = v[2 * i], r1 = v[2 * i + 1];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      __half b = __float2half_rn(r);
-      r -= __half2float(b);
-      h[p][i] = __half_as_ushort(b);
+      const uint32_t d = pack_f16x2(r0, r1);
+      w[p][i] = d;
+      if (p + 1 < P) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&d));
+        r0 -= f.x;
+        r1 -= f.y;
+      }
     }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    pk[p].x = h[p][0] | ((uint32_t)h[p][1] << 16);
-    pk[p].y = h[p][2] | ((uint32_t)h[p][3] << 16);
-    pk[p].z = h[p][4] | ((uint32_t)h[p][5] << 16);
-    pk[p].w = h[p][6] | ((uint32_t)h[p][7] << 16);
-  }
+  for (int p = 0; p < P; ++p) pk[p] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
 }
 
 enum { FMT_F16 = 0, FMT_BF16 = 1 };   // tcgen05 kind::f16 operand formats (instruction descriptor encoding)
