@@ -372,7 +372,7 @@ def main():
     roofline = None
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r01i_gemm_ncu_summary.json")))
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r01j_gemm_ncu_summary.json")))
         tag = {"G2_fwd": "G2<2>", "G3": "<G3>", "G6": "<G6>", "G1": "<G1T", "G4": "<G4T", "G5": "<G5T"}[dom]
         traffic = next(v["dram_bytes"] for k, v in summ.items() if tag in k)
     except Exception:
