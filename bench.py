@@ -263,7 +263,8 @@ def main():
 
     def one_step(x, w, e):
         call = _Call(x, w, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],
-                     prm["noise"], prm["phi"], prm["beta"], e, _lib.KERNEL_IDS[cfg["kernel"]], 0, flags, 0)
+                     prm["noise"], prm["phi"], prm["beta"], e, _lib.KERNEL_IDS[cfg["kernel"]], 0, flags,
+                     int(os.environ.get("GDRF_BENCH_CHUNK_ROWS", "0")))
         call.prologue(jitter, maxjitter)
         terms, grad = call.step(True)
         if world > 1:                      # the one collective of the step: small parameter gradients + ELBO terms
