@@ -9,9 +9,10 @@ Same constructor keywords, parameter names (``u_loc``, ``u_scale_tril``, ``noise
 ``scale``, ``artifacts``) and error behaviour.  Only ``whiten=True`` with the default zero mean and
 softmax link is accelerated; anything else raises ``NotImplementedError`` (there is no fallback path).
 
-When Pyro is importable, ``model`` contributes the whole ELBO as one ``pyro.factor`` and ``guide``
-registers nothing to sample, so ``pyro.infer.SVI(model=scale(m.model), guide=scale(m.guide), ...)``
-(``train_script.py:365-371``) sees the identical loss and gradients.  Without Pyro,
+When Pyro is importable, ``model`` registers the module's parameters (``pyro.module``) and contributes the whole
+ELBO as one ``pyro.factor``; ``guide`` has nothing to sample, so ``pyro.infer.SVI(model=scale(m.model),
+guide=scale(m.guide), ...)`` (``train_script.py:365-371``) sees the identical loss and steps the same parameters
+(``tests/test_gpu_streaming.py::test_pyro_adapter_path_under_the_shim`` drives exactly that wiring).  Without Pyro,
 :class:`gdrf_b200.svi.SVI` provides the same ``step(xs=, ws=, subsample=)`` call.
 """
 from __future__ import annotations
@@ -251,6 +252,7 @@ class SparseMultinomialGDRF(nn.Module):
         """sparse_gdrf.py:322-373.  Under Pyro: one factor carrying N * (ELBO / N); the enclosing
         ``poutine.scale(1/N)`` (train_script.py:365) restores the reference's loss."""
         if _HAVE_PYRO:
+            pyro.module("gdrf_b200", self)     # param sites: SVI's optimiser only steps what the trace registered
             e = self.elbo(xs, ws)
             pyro.factor("gdrf_elbo", e * xs.shape[0])
             return ws

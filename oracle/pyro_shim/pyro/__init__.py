@@ -72,6 +72,30 @@ def param(name, *args, **kwargs):
     return torch.distributions.transform_to(constraint)(unconstrained)
 
 
+class _Unit:
+    """pyro.distributions.Unit(log_factor): an empty-valued site whose log-density is the given factor."""
+    has_rsample = True
+
+    def __init__(self, log_factor):
+        self.log_factor = log_factor
+
+    def log_prob(self, value):
+        return self.log_factor
+
+
+def factor(name, log_factor):
+    """pyro.factor: adds ``log_factor`` to the model's log-density (observed Unit site)."""
+    return sample(name, _Unit(log_factor), obs=torch.empty(0))
+
+
+def module(name, nn_module, update_module_params=False):
+    """pyro.module: registers every parameter of a torch module with the param store (unconstrained = the parameter
+    itself, constraint real), so that SVI's optimiser steps it."""
+    for pname, p in nn_module.named_parameters():
+        _PARAM_STORE.setdefault(f"{name}$$${pname}", (p, torch.distributions.constraints.real))
+    return nn_module
+
+
 def clear_param_store():
     _PARAM_STORE.clear()
 

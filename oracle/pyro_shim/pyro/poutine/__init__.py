@@ -35,6 +35,9 @@ class _ScaleHandler(pyro._Handler):
     def process(self, msg):
         msg["scale"] = msg["scale"] * self.scale
 
+    def __call__(self, fn):      # handler used as a decorator: scale = poutine.scale(scale=1/N); scale(model)  (train_script.py:365)
+        return _Wrapped(fn, lambda: _ScaleHandler(self.scale))
+
 
 class _Wrapped:
     def __init__(self, fn, make_handler):
