@@ -76,22 +76,32 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 template <typename T>
 __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
                                                int Mp, int kb, int* __restrict__ status) {
-  // The block lives in shared memory and the loops stay rolled: a first version kept the row in registers with every
-  // loop unrolled (32 x 32 shuffles, twice) -- ~100 KB of straight-line code that ran at instruction-fetch speed,
-  // 35 us per block column.  Arithmetic and its order are unchanged (right-looking column updates; one accumulator,
-  // ascending t, in the inverse), so the fp32 status mirror takes the same pivots as before.
-  __shared__ T sm[NB][NB + 1];     // the diagonal block, then L (zero above the diagonal)
-  __shared__ T sx[NB][NB + 1];     // its inverse, row by row
-  __shared__ T sinv[NB];           // 1 / L[j][j] (the reciprocal square roots of the pivots)
+  // One warp, lane = row.  The row lives in registers (statically indexed: the column loops are unrolled and
+  // predicated, the loop over the pivot column j stays rolled), a finished column is broadcast through shared memory.
+  // Two earlier versions took 31-35 us per block column: all-shuffle with every loop unrolled (~100 KB of straight-line
+  // code) and all-shared-memory with read-modify-write inner loops (one shared-memory round trip per element).
+  // Arithmetic and its order are those of the first version (right-looking column updates; one accumulator,
+  // ascending t, in the inverse), except that the inverse multiplies by the pivots' reciprocal square roots.
+  __shared__ T sl[NB][NB + 1];     // the block on entry, L (zero above the diagonal) on exit
+  __shared__ T sx[NB][NB + 1];     // the inverse, for the coalesced store
+  __shared__ T scol[NB];           // the column being eliminated
+  __shared__ T sinv[NB];           // 1 / L[j][j]
   const int lane = threadIdx.x;
   const T* blk = A + ((long long)kb * NB) * Mp + kb * NB;
 #pragma unroll 4
-  for (int r = 0; r < NB; ++r) sm[r][lane] = blk[(long long)r * Mp + lane];
+  for (int r = 0; r < NB; ++r) sl[r][lane] = blk[(long long)r * Mp + lane];
   __syncwarp();
+  T a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = sl[lane][c];
   int bad = 0;
 #pragma unroll 1
   for (int j = 0; j < NB; ++j) {
-    T d = sm[j][j];
+    T aj = T(0);
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c == j) aj = a[c];
+    T d = __shfl_sync(0xffffffffu, aj, j);
     if (!(d > T(0))) {
       if (bad == 0) bad = kb * NB + j + 1;
       d = T(1);
@@ -103,30 +113,43 @@ __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __res
     sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
     T lj = T(0);
     if (lane == j) lj = sq;
-    else if (lane > j) lj = sm[lane][j] * inv;
-    __syncwarp();
-    sm[lane][j] = lj;
+    else if (lane > j) lj = aj * inv;
+    scol[lane] = lj;
+    sl[lane][j] = lj;
     if (lane == j) sinv[j] = inv;
     __syncwarp();
-#pragma unroll 4
-    for (int c = j + 1; c < NB; ++c)
-      if (lane >= c) sm[lane][c] -= lj * sm[c][j];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      const T lc = scol[c];
+      if (c > j && lane >= c) a[c] -= lj * lc;
+    }
     __syncwarp();
   }
   // row `lane` of the inverse: x L = e_lane, back-substituted over the columns from the right
+  T x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) x[c] = T(0);
 #pragma unroll 1
   for (int j = NB - 1; j >= 0; --j) {
     T sacc = (lane == j) ? T(1) : T(0);
-#pragma unroll 4
-    for (int t = j + 1; t < NB; ++t) sacc -= sx[lane][t] * sm[t][j];
-    sx[lane][j] = (j <= lane) ? sacc * sinv[j] : T(0);     // a multiply instead of a 30-step fp64 division chain
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      const T l = sl[t][j];
+      if (t > j) sacc -= x[t] * l;
+    }
+    const T xj = (j <= lane) ? sacc * sinv[j] : T(0);
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c == j) x[c] = xj;
   }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) sx[lane][c] = x[c];
   __syncwarp();
   T* lb = L + ((long long)kb * NB) * Mp + kb * NB;
   T* db = Dinv + ((long long)kb * NB) * NB;
 #pragma unroll 4
   for (int r = 0; r < NB; ++r) {
-    lb[(long long)r * Mp + lane] = (lane <= r) ? sm[r][lane] : T(0);
+    lb[(long long)r * Mp + lane] = (lane <= r) ? sl[r][lane] : T(0);
     db[r * NB + lane] = sx[r][lane];
   }
   if (lane == 0 && bad != 0) atomicCAS(status, 0, bad);
