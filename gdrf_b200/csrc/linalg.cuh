@@ -67,7 +67,7 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 // ---------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky (lower), out of place: A holds Kuu and receives the trailing updates, L the
 // factor, Dinv the inverses of L's 32 x 32 diagonal blocks.  Two launches per block column:
-//   k_chol_diag : one warp, lane = row, the block lives in registers, columns exchanged by shuffles; also
+//   k_chol_diag : 32 warps, one thread per element of the block, columns exchanged through shared memory; also
 //                 inverts the triangular block.  status: 0 ok, c+1 = pivot of column c not > 0 (the
 //                 RuntimeError of torch.linalg.cholesky that gdrf/models/utils.py:31-37 catches).
 //   k_chol_trail: block (ib, jb), ib >= jb > kb: panel tiles P_i = A[ib][kb] Dinv^T, P_j likewise, then
@@ -76,32 +76,24 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 template <typename T>
 __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
                                                int Mp, int kb, int* __restrict__ status) {
-  // One warp, lane = row.  The row lives in registers (statically indexed: the column loops are unrolled and
-  // predicated, the loop over the pivot column j stays rolled), a finished column is broadcast through shared memory.
-  // Two earlier versions took 31-35 us per block column: all-shuffle with every loop unrolled (~100 KB of straight-line
-  // code) and all-shared-memory with read-modify-write inner loops (one shared-memory round trip per element).
-  // Arithmetic and its order are those of the first version (right-looking column updates; one accumulator,
-  // ascending t, in the inverse), except that the inverse multiplies by the pivots' reciprocal square roots.
-  __shared__ T sl[NB][NB + 1];     // the block on entry, L (zero above the diagonal) on exit
-  __shared__ T sx[NB][NB + 1];     // the inverse, for the coalesced store
+  // 32 warps, one thread per element (r = warp, c = lane).  Three single-warp formulations (all shuffles and fully
+  // unrolled; all shared memory; row in registers) took 29-35 us per block column: one warp issuing ~14 K mostly
+  // dependent instructions.  Here a column step is two block barriers and one multiply-add per thread, and a row of
+  // the inverse is a warp-level dot product per column.  The factorisation's arithmetic and its order are unchanged
+  // (right-looking: element (r, c) receives -L[r][j] L[c][j] for j = 0 .. c-1 in order); the inverse sums its dot
+  // products as a shuffle tree instead of serially.
+  __shared__ T sl[NB][NB + 1];     // L (zero above the diagonal)
   __shared__ T scol[NB];           // the column being eliminated
   __shared__ T sinv[NB];           // 1 / L[j][j]
-  const int lane = threadIdx.x;
-  const T* blk = A + ((long long)kb * NB) * Mp + kb * NB;
-#pragma unroll 4
-  for (int r = 0; r < NB; ++r) sl[r][lane] = blk[(long long)r * Mp + lane];
-  __syncwarp();
-  T a[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = sl[lane][c];
+  __shared__ T sd;                 // the pivot
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  T a = A[((long long)kb * NB + r) * Mp + kb * NB + c];
   int bad = 0;
 #pragma unroll 1
   for (int j = 0; j < NB; ++j) {
-    T aj = T(0);
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (c == j) aj = a[c];
-    T d = __shfl_sync(0xffffffffu, aj, j);
+    if (r == j && c == j) sd = a;
+    __syncthreads();
+    T d = sd;
     if (!(d > T(0))) {
       if (bad == 0) bad = kb * NB + j + 1;
       d = T(1);
@@ -111,59 +103,43 @@ __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __res
     const T inv = rsqrt(d);
     T sq = d * inv;
     sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
-    T lj = T(0);
-    if (lane == j) lj = sq;
-    else if (lane > j) lj = aj * inv;
-    scol[lane] = lj;
-    sl[lane][j] = lj;
-    if (lane == j) sinv[j] = inv;
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      const T lc = scol[c];
-      if (c > j && lane >= c) a[c] -= lj * lc;
+    if (c == j) {
+      T lj = T(0);
+      if (r == j) lj = sq;
+      else if (r > j) lj = a * inv;
+      a = lj;
+      scol[r] = lj;
+      if (r == j) sinv[j] = inv;
     }
-    __syncwarp();
+    __syncthreads();
+    if (c > j && r >= c) a -= scol[r] * scol[c];
   }
-  // row `lane` of the inverse: x L = e_lane, back-substituted over the columns from the right
-  T x[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) x[c] = T(0);
+  sl[r][c] = (c <= r) ? a : T(0);
+  __syncthreads();
+  L[((long long)kb * NB + r) * Mp + kb * NB + c] = sl[r][c];
+  // row r of the inverse: x L = e_r, back-substituted over the columns from the right; lane t holds x[t]
+  T x = T(0);
 #pragma unroll 1
-  for (int j = NB - 1; j >= 0; --j) {
-    T sacc = (lane == j) ? T(1) : T(0);
+  for (int j = r; j >= 0; --j) {
+    T part = (c > j) ? x * sl[c][j] : T(0);
 #pragma unroll
-    for (int t = 0; t < NB; ++t) {
-      const T l = sl[t][j];
-      if (t > j) sacc -= x[t] * l;
-    }
-    const T xj = (j <= lane) ? sacc * sinv[j] : T(0);
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (c == j) x[c] = xj;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const T xj = (((r == j) ? T(1) : T(0)) - part) * sinv[j];
+    if (c == j) x = xj;
   }
-#pragma unroll
-  for (int c = 0; c < NB; ++c) sx[lane][c] = x[c];
-  __syncwarp();
-  T* lb = L + ((long long)kb * NB) * Mp + kb * NB;
-  T* db = Dinv + ((long long)kb * NB) * NB;
-#pragma unroll 4
-  for (int r = 0; r < NB; ++r) {
-    lb[(long long)r * Mp + lane] = (lane <= r) ? sl[r][lane] : T(0);
-    db[r * NB + lane] = sx[r][lane];
-  }
-  if (lane == 0 && bad != 0) atomicCAS(status, 0, bad);
+  Dinv[((long long)kb * NB + r) * NB + c] = x;
+  if (threadIdx.x == 0 && bad != 0) atomicCAS(status, 0, bad);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+__global__ void __launch_bounds__(NB * NB) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
                                                   int Mp, int kb, int* __restrict__ status) {
   chol_diag_body<T>(A, L, Dinv, Mp, kb, status);
 }
 
 // the fp64 factorisation (values) and the fp32 one (the reference's "did it fail" decision) side by side:
 // block 0 = double, block 1 = float
-__global__ void __launch_bounds__(32) k_chol_diag_both(const double* __restrict__ A, double* __restrict__ L,
+__global__ void __launch_bounds__(NB * NB) k_chol_diag_both(const double* __restrict__ A, double* __restrict__ L,
                                                        double* __restrict__ Dinv, const float* __restrict__ Af,
                                                        float* __restrict__ Lf, float* __restrict__ Dinvf, int Mp, int kb,
                                                        int* __restrict__ status) {
@@ -219,7 +195,7 @@ inline void cholesky(T* A, T* L, T* Dinv, int Mp, int* status, cudaStream_t st) 
   cudaMemsetAsync(L, 0, sizeof(T) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
   for (int kb = 0; kb < nblk; ++kb) {
-    k_chol_diag<T><<<1, NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
+    k_chol_diag<T><<<1, NB * NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
     const int rem = nblk - kb - 1;
     if (rem > 0) k_chol_trail<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb);
   }
@@ -231,7 +207,7 @@ inline void cholesky_both(double* A, double* L, double* Dinv, float* Af, float* 
   cudaMemsetAsync(Lf, 0, sizeof(float) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
   for (int kb = 0; kb < nblk; ++kb) {
-    k_chol_diag_both<<<2, NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb, status);
+    k_chol_diag_both<<<2, NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb, status);
     const int rem = nblk - kb - 1;
     if (rem > 0) k_chol_trail_both<<<dim3(rem, rem, 2), NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb);
   }
