@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .svi import shard_bounds
 
 STREAMING_MODES = ("uniform", "now", "exp", "uniform_now", "exp_now", "uniform_exp")
 
@@ -131,9 +132,10 @@ class StreamingData:
 def streaming_epoch(svi, data: StreamingData, epoch: int, epochs: int, streaming_inference: str,
                     streaming_size: int = 1, streaming_subepochs: int = 1, streaming_truncate: int = -1,
                     streaming_exp: float = 1.0, streaming_weight: float = 0.1, streaming_batch: bool = False,
-                    rng=None, eps_fn=None) -> float:
+                    rng=None, eps_fn=None, shard=None) -> float:
     """One epoch of the reference's streaming loop (train_script.py:394-460): ``streaming_subepochs`` steps, each on a
-    freshly drawn multiset of rows, every loss scaled by the full data set's ``1 / len(xs)``.  ``svi``: a
+    freshly drawn multiset of rows, every loss scaled by the full data set's ``1 / len(xs)``.  ``shard=(rank, world)``
+    splits each drawn multiset across the ranks of a data-parallel job (``svi`` all-reduces the gradients).  ``svi``: a
     :class:`gdrf_b200.svi.SVI` / ``FusedSVI``.  ``eps_fn(n_rows)`` may supply the guide's draws (tests).  Returns the
     last loss like the reference's loop variable."""
     n_data = len(data)
@@ -141,6 +143,9 @@ def streaming_epoch(svi, data: StreamingData, epoch: int, epochs: int, streaming
     for _ in range(streaming_subepochs):
         selection = streaming_selection(epoch, n_data, epochs, streaming_inference, streaming_size, streaming_truncate,
                                         streaming_exp, streaming_weight, streaming_batch, rng)
+        if shard is not None:     # observation-sharded data parallelism: every rank draws the SAME multiset (same seeded
+            lo, hi = shard_bounds(len(selection), *shard)     # generator) and evaluates its contiguous slice of it
+            selection = selection[lo:hi]
         xs_stream, ws_stream = data.gather(selection)
         eps = eps_fn(xs_stream.shape[0]) if eps_fn is not None else None
         loss = svi.step(xs=xs_stream, ws=ws_stream, subsample=False, eps=eps, n_global=n_data)

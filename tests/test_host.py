@@ -272,3 +272,40 @@ def test_checkpoint_interchange_follows_the_reference_resume_logic(tmp_path):
     assert n_m == n and best_m == float("-inf")
     s = strip_optimizer(ck2)
     assert s["optimizer"] is None and s["epoch"] == -1
+
+
+def test_streaming_epoch_shards_one_multiset_across_ranks():
+    """Data-parallel streaming: every rank draws the same multiset from the same seeded generator and takes its
+    contiguous slice; the slices partition the selection, every step carries the full data set's N."""
+    import numpy as np
+    from gdrf_b200.streaming import streaming_epoch, streaming_selection
+
+    class Data:
+        def __init__(self, n):
+            self.n, self.seen = n, []
+        def __len__(self):
+            return self.n
+        def gather(self, sel):
+            self.seen.append(np.asarray(sel).copy())
+            return torch.zeros(len(sel), 2), torch.zeros(len(sel), 3, dtype=torch.int32)
+
+    class Svi:
+        def __init__(self):
+            self.calls = []
+        def step(self, xs, ws, subsample=False, eps=None, n_global=None):
+            self.calls.append((xs.shape[0], n_global))
+            return 1.0
+
+    kw = dict(epoch=40, epochs=90, streaming_inference="exp", streaming_size=37, streaming_subepochs=2,
+              streaming_exp=0.1)
+    rs = np.random.RandomState(5)
+    whole = [streaming_selection(40, 90, 90, "exp", 37, streaming_exp=0.1, rng=rs) for _ in range(2)]
+    parts = []
+    for rank in range(3):
+        d, s = Data(90), Svi()
+        streaming_epoch(s, d, rng=np.random.RandomState(5), shard=(rank, 3), **kw)
+        assert [c[1] for c in s.calls] == [90, 90]
+        parts.append(d.seen)
+    for sub in range(2):
+        assert np.array_equal(np.concatenate([parts[r][sub] for r in range(3)]), whole[sub])
+        assert [len(parts[r][sub]) for r in range(3)] == [13, 12, 12]
