@@ -133,8 +133,13 @@ class SparseMultinomialGDRF(nn.Module):
         # make_wt_matrix (abstract_gdrf.py:57-84): softmax over the *topic* axis of beta, then stored through
         # the stacked-simplex constraint (unconstrained = log p, constrained = row softmax)
         wt = torch.softmax(self._dirichlet_param, dim=-2)
-        if randomize_wt_matrix:
-            wt = torch.softmax(torch.randn_like(wt), dim=-2)
+        best = -1 if randomize_metric is None else randomize_metric(wt, self)
+        if randomize_wt_matrix:     # the reference never updates `best`: the LAST candidate that beats the initial score wins
+            for _ in range(1 if randomize_metric is None else randomize_iters):
+                possible = torch.softmax(torch.randn_like(wt), dim=-2)
+                score = 0 if randomize_metric is None else randomize_metric(possible, self)
+                if score > best:
+                    wt = possible
         self._word_topic_matrix_map_unconstrained = nn.Parameter(wt.log())
         self._eps_generator: Optional[torch.Generator] = None
         self.num_particles = 1

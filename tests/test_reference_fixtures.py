@@ -178,3 +178,28 @@ def test_cuda_svi_follows_reference_trajectory(name, fused):
         diff = (v - ref).abs()
         assert diff.mean().item() < (5e-3 if k in HYPER else 2e-4) and diff.max().item() < 6.1e-2, \
             (k, diff.mean().item(), diff.max().item())
+
+
+def test_randomised_word_topic_init_matches_the_reference_constructor():
+    """``randomize_wt_matrix`` / ``randomize_metric`` / ``randomize_iters`` (abstract_gdrf.py:57-84): same candidates from
+    the same torch seed, same acceptance rule (the reference never updates its best score: the last candidate that beats
+    the initial score wins).  tests/golden/ref_wt_init.npz comes from the reference's constructor
+    (oracle/make_wt_fixture.py)."""
+    import os
+    from gdrf_b200 import RBF, SparseMultinomialGDRF
+
+    def metric(wt, model):      # the one oracle/make_wt_fixture.py handed to the reference
+        return float(wt.max(dim=-2).values.sum())
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wt_init.npz"))
+    for name, kw in (("plain", dict(randomize_wt_matrix=True)),
+                     ("metric", dict(randomize_wt_matrix=True, randomize_metric=metric, randomize_iters=7)),
+                     ("metric_off", dict(randomize_wt_matrix=False, randomize_metric=metric))):
+        torch.manual_seed(1234)
+        m = SparseMultinomialGDRF(num_observation_categories=9, num_topic_categories=4, world=[(0.0, 1.0)] * 2,
+                                  kernel=RBF(2, variance=torch.tensor(1.3), lengthscale=torch.tensor(0.4)),
+                                  dirichlet_param=0.1, n_points=4, inducing_init="grid", device="cpu", jitter=1e-4,
+                                  maxjitter=15, **kw)
+        ref = torch.from_numpy(d[name])
+        assert torch.allclose(m._word_topic_matrix_map_unconstrained.detach(), ref, rtol=1e-5, atol=1e-6), name
+    assert not np.allclose(d["plain"], d["metric"]) and not np.allclose(d["plain"], d["metric_off"])
