@@ -35,6 +35,18 @@ def main():
             dirichlet_param=0.1, n_points=4, inducing_init="grid", device="cpu", jitter=1e-4, maxjitter=15,
             xs=xs, ws=ws, **kw)
         out[name] = dict(m.named_parameters())["_word_topic_matrix_map_unconstrained"].detach().numpy()
+    # inducing_init="random" on a non-unit world: sorted uniform draws per dimension, scaled into the unit cube, then the
+    # interval(0, 1) round trip and u_scale_tril = chol(k(Z, Z) + jitter) of THOSE points (sparse_gdrf.py:54-110)
+    torch.manual_seed(4321)
+    pyro.clear_param_store()
+    kernel = gp.kernels.Matern32(D, variance=torch.tensor(2.0), lengthscale=torch.tensor(0.5))
+    xs2 = xs * torch.tensor([2.0, 3.0]) + torch.tensor([1.0, -1.0])
+    m = models.SparseMultinomialGDRF(
+        num_observation_categories=V, num_topic_categories=K, world=[(1.0, 3.0), (-1.0, 2.0)], kernel=kernel,
+        dirichlet_param=0.1, n_points=[3, 4], inducing_init="random", device="cpu", jitter=1e-4, maxjitter=15,
+        xs=xs2, ws=ws)
+    for k, v in m.named_parameters():
+        out["random_init/" + k] = v.detach().numpy()
     np.savez(OUT, **out)
     print("wrote", OUT, {k: v.shape for k, v in out.items()})
 

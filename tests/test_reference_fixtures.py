@@ -203,3 +203,24 @@ def test_randomised_word_topic_init_matches_the_reference_constructor():
         ref = torch.from_numpy(d[name])
         assert torch.allclose(m._word_topic_matrix_map_unconstrained.detach(), ref, rtol=1e-5, atol=1e-6), name
     assert not np.allclose(d["plain"], d["metric"]) and not np.allclose(d["plain"], d["metric_off"])
+
+
+def test_random_inducing_init_on_a_non_unit_world_matches_the_reference_constructor():
+    """``inducing_init="random"`` with ``world`` other than the unit cube (sparse_gdrf.py:54-110): the same sorted
+    uniform draws per dimension from the same torch seed, scaled into the unit cube, stored through interval(0, 1), and
+    ``u_scale_tril`` initialised to the Cholesky factor of the kernel at those points."""
+    import os
+    from gdrf_b200 import Matern32, SparseMultinomialGDRF
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wt_init.npz"))
+    torch.manual_seed(4321)
+    m = SparseMultinomialGDRF(num_observation_categories=9, num_topic_categories=4, world=[(1.0, 3.0), (-1.0, 2.0)],
+                              kernel=Matern32(2, variance=torch.tensor(2.0), lengthscale=torch.tensor(0.5)),
+                              dirichlet_param=0.1, n_points=[3, 4], inducing_init="random", device="cpu", jitter=1e-4,
+                              maxjitter=15)
+    mine = dict(m.named_parameters())
+    names = {k[len("random_init/"):] for k in d.files if k.startswith("random_init/")}
+    assert set(mine) == names
+    for k in names:
+        ref = torch.from_numpy(d["random_init/" + k])
+        assert mine[k].shape == ref.shape, k
+        assert torch.allclose(mine[k].detach(), ref, rtol=1e-4, atol=2e-5), (k, (mine[k].detach() - ref).abs().max().item())
