@@ -151,6 +151,90 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+PROFILE_SUMMARY = os.path.join(ROOT, "profiles", "r02_gemm_ncu_summary.json")
+PROFILE_FALLBACK = os.path.join(ROOT, "profiles", "r01j_gemm_ncu_summary.json")
+
+
+def roofline_block(prof, steps, n_local, ms_step_rank0, M, K, flags, _lib):
+    """`roofline` of the JSON line from the CUDA-event records of the timed region (gdrf_profile_read: one record per
+    launch, none dropped): algorithmic flops of the launches actually recorded / their summed duration."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        peak_tf, peak_src = float(peaks.get("bf16_tflops_sustained", 1384.6)), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    else:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    tri = 2.0 * (M * M / 2.0) * K                 # triangular-aware flops per observation of one W*S_k contraction
+    alg = {"G1": 2.0 * M * M / 2, "G2_fwd": tri, "scale_w": 0.0, "G3": tri, "G4": 2.0 * M * M / 2, "G5": 2.0 * M * M,
+           "G6": tri}
+    Mp = (M + 255) // 256 * 256
+    MBk = Mp // 64
+    full_width = bool(flags & _lib.FLAG_FULL_WIDTH)
+    # MMA work actually issued per logical multiply-add: products per split x whole 64-row k-blocks of 256-wide tiles of
+    # the triangular operand (minus the column groups the narrow diagonal-block MMAs leave out) x padding of M to 256
+    def issued_factor(kind):
+        mma = {"G1": 6, "G2_fwd": 6 if (flags & _lib.FLAG_FWD_BF16) else 3}.get(kind, 3)
+        if kind in ("G2_fwd", "G3", "G6"):
+            narrow = 0 if full_width else {"G2_fwd": 6, "G3": 4}.get(kind, 0)
+            pad = sum((MBk - 4 * j) * 4 - narrow for j in range(MBk // 4)) / (MBk * MBk / 2.0)
+        elif kind in ("G1", "G4"):
+            pad = sum((MBk - 4 * j) * 4 for j in range(MBk // 4)) / (MBk * MBk / 2.0)
+        else:
+            pad = 1.0
+        return mma, pad * (float(Mp) / M) ** 2
+    try:
+        summ = json.load(open(PROFILE_SUMMARY if os.path.exists(PROFILE_SUMMARY) else PROFILE_FALLBACK))
+    except Exception:
+        summ = {}
+    tags = {"G2_fwd": "G2<2>", "G3": "<G3>", "G6": "<G6>", "G1": "<G1T", "G4": "<G4T", "G5": "<G5T", "scale_w": "k_scale_w"}
+    per_kernel = {}
+    for kind, (ms, n) in prof.items():
+        if n <= 0 or ms <= 0:
+            continue
+        entry = {"ms_per_step": ms / steps, "launches_per_step": n / steps, "avg_launch_ms": ms / n}
+        if alg.get(kind, 0) > 0:
+            # every observation of the shard passes through each contraction once per step
+            tf = alg[kind] * n_local * steps / (ms * 1e-3) / 1e12
+            mma, pad = issued_factor(kind)
+            entry.update({"achieved_tflops": tf, "frac": tf / peak_tf, "issued_frac": tf * mma * pad / peak_tf,
+                          "mma_per_product": mma, "tile_padding": pad})
+        rec = next((v for k, v in summ.items() if tags.get(kind, "?") in k), None)
+        if rec:
+            entry["traffic"] = rec.get("dram_bytes")
+            if rec.get("distinct_bytes"):
+                entry["traffic_over_distinct"] = rec["dram_bytes"] / rec["distinct_bytes"]
+            if rec.get("sm_mhz"):
+                entry["ncu_sm_mhz"] = rec["sm_mhz"]
+        per_kernel[kind] = entry
+    doms = [k for k in per_kernel if "frac" in per_kernel[k]]
+    if not doms:
+        return None
+    dom = max(doms, key=lambda k: per_kernel[k]["ms_per_step"])
+    d = per_kernel[dom]
+    total_ms = sum(e["ms_per_step"] for e in per_kernel.values())
+    problems = []
+    if total_ms > 1.02 * ms_step_rank0:
+        problems.append(f"profiled kernels sum to {total_ms:.1f} ms/step > step {ms_step_rank0:.1f} ms")
+    if any(e.get("issued_frac", 0) > 1.3 for e in per_kernel.values()):
+        problems.append("issued_frac > 1.3 of the measured bf16 peak")
+    if any(abs(e["launches_per_step"] - round(e["launches_per_step"])) > 1e-6 for e in per_kernel.values()):
+        problems.append("launch records are not a whole number per step")
+    if problems:      # a roofline that does not follow from the records is not printed
+        return {"error": "; ".join(problems), "all_contractions_ms_per_step": {k: e["ms_per_step"] for k, e in per_kernel.items()}}
+    return {"bound": "tensor", "kernel": f"gemm_tc2_kernel<{dom}>", "achieved": d["achieved_tflops"], "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": d["frac"], "traffic": d.get("traffic"),
+            "issued": {"tflops": d["issued_frac"] * peak_tf, "frac": d["issued_frac"], "mma_per_product": d["mma_per_product"],
+                       "tile_padding": d["tile_padding"],
+                       "note": "issued 16-bit MMA flops / peak: the tensor-pipe utilisation this kernel runs at"},
+            "traffic_note": "dram__bytes_read+write per launch, ncu --set full, one 18 944-observation chunk (profiles/)",
+            "peak_source": peak_src, "avg_launch_ms": d["avg_launch_ms"], "launches": int(round(d["launches_per_step"] * steps)),
+            "share_of_step": d["ms_per_step"] / ms_step_rank0,
+            "note": "algorithmic flops: triangular-aware, each fp32 multiply-add counted once; the kernel issues 3 "
+                    "16-bit MMAs per logical product (error-compensated split)",
+            "all_contractions_ms_per_step": {k: e["ms_per_step"] for k, e in per_kernel.items()},
+            "per_kernel": per_kernel}
+
+
 def cpu_reference_rate(cfg, sample_rows, steps, warmup):
     """The reference's CPU path: the fp32 oracle executed op for op as the reference does (two conditionals,
     unfused ops, N x V probabilities materialised, torch autograd backward), all host threads, on a bounded
@@ -358,49 +442,7 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel ----------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        peak_tf, peak_src = float(peaks.get("bf16_tflops_sustained", 1384.6)), "MEASURED_PEAKS.json bf16_tflops_sustained"
-    else:
-        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
-    tri = 2.0 * (M * M / 2.0) * K                 # triangular-aware flops per observation of one W*S_k contraction
-    alg = {"G1": 2.0 * M * M / 2, "G2_fwd": tri, "scale_w": 0.0, "G3": tri, "G4": 2.0 * M * M / 2, "G5": 2.0 * M * M,
-           "G6": tri}
-    kernel_ms = {k: v[0] for k, v in prof.items()}
-    dom = max((k for k in kernel_ms if alg.get(k, 0) > 0), key=kernel_ms.get)
-    dom_ms, dom_n = prof[dom]
-    roofline = None
-    traffic = None
-    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r01j_gemm_ncu_summary.json")))
-        tag = {"G2_fwd": "G2<2>", "G3": "<G3>", "G6": "<G6>", "G1": "<G1T", "G4": "<G4T", "G5": "<G5T"}[dom]
-        traffic = next(v["dram_bytes"] for k, v in summ.items() if tag in k)
-    except Exception:
-        traffic = None
-    if dom_n > 0 and dom_ms > 0:
-        per_launch_ms = dom_ms / dom_n
-        obs_per_launch = n_local * steps / dom_n
-        achieved = alg[dom] * obs_per_launch / (per_launch_ms * 1e-3) / 1e12
-        # what the tensor pipe is actually asked to do: 3 16-bit MMAs per logical product, and whole 64-row k-blocks
-        # of 256-wide tiles where the triangular operand is half empty (Mp / 64 blocks per side)
-        MBk = (M + 255) // 256 * 4
-        # ... minus the 64-column groups the narrow diagonal-block MMAs leave out (6 of 16 per tile in G2, 4 in G3)
-        narrow = 0 if (flags & _lib.FLAG_FULL_WIDTH) else {"G2_fwd": 6, "G3": 4}.get(dom, 0)
-        pad = (sum((MBk - 4 * j) * 4 - narrow for j in range(MBk // 4)) / (MBk * MBk / 2.0)
-               if dom in ("G2_fwd", "G3", "G6") else 1.0)
-        issued = achieved * 3.0 * pad * (float(MBk * 64) / M) ** 2
-        roofline = {"bound": "tensor", "kernel": f"gemm_tc2_kernel<{dom}>", "achieved": achieved, "peak": peak_tf,
-                    "issued": {"tflops": issued, "frac": issued / peak_tf, "mma_per_product": 3, "tile_padding": pad,
-                               "note": "issued 16-bit MMA flops / peak: the tensor-pipe utilisation this kernel runs at"},
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                    "traffic_note": "dram__bytes_read+write per launch, ncu --set full, one 18 944-observation chunk (profiles/)",
-                    "peak_source": peak_src,
-                    "avg_launch_ms": per_launch_ms, "launches": dom_n,
-                    "share_of_step": dom_ms / (ms_dev if ms_dev > 0 else 1.0),
-                    "note": "algorithmic flops: triangular-aware, each fp32 multiply-add counted once; the kernel "
-                            "issues 3 16-bit MMAs per logical product (error-compensated split)",
-                    "all_contractions_ms_per_step": {k: v / steps for k, v in kernel_ms.items()}}
+    roofline = roofline_block(prof, steps, n_local, ms_dev / steps, M, K, flags, _lib)
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -101,6 +101,36 @@ __device__ __forceinline__ void split8h(const float* v, uint4 (&pk)[P]) {
 
 enum { FMT_F16 = 0, FMT_BF16 = 1 };   // tcgen05 kind::f16 operand formats (instruction descriptor encoding)
 
+// two-plane split in the format chosen at run time (FMT_F16: 22 significant bits, |x| < 65504; FMT_BF16: 16 bits, any
+// fp32 range) -- the backward operands follow the forward's format (GDRF_FLAG_FWD_BF16)
+__device__ __forceinline__ void split8x2(int fmt, const float* v, uint4 (&pk)[2]) {
+  if (fmt == FMT_F16) split8h<2>(v, pk);
+  else split8<2>(v, pk);
+}
+
+// Power-of-two scale s with s * bound in [2^13, 2^14): operands written as fp16 planes are multiplied by s (exact) so
+// that they sit well inside the fp16 range whatever the magnitude of the gradients flowing through them; the
+// consuming contraction's epilogue multiplies by 1/s.  Pure bit arithmetic, so every kernel that recomputes it from the
+// same bound gets the same value.  bound <= 0 (an all-zero chunk) gives s = 1.
+__device__ __forceinline__ float pow2_scale(float bound, float* inv) {
+  const int eb = (int)((__float_as_uint(bound) >> 23) & 0xff);
+  if (!(bound > 0.f) || eb == 0 || eb == 255) { *inv = 1.f; return 1.f; }
+  int se = 13 - (eb - 127);                 // 2^(eb-127) <= bound < 2^(eb-126)
+  se = se < -100 ? -100 : (se > 100 ? 100 : se);
+  *inv = __uint_as_float((uint32_t)(127 - se) << 23);
+  return __uint_as_float((uint32_t)(127 + se) << 23);
+}
+
+// per-chunk scalars (zeroed together with q at the start of every chunk) and per-step scalars (zeroed by the prologue /
+// at the start of a step): running maxima kept as float bit patterns, and the power-of-two operand scales derived from them
+enum { CS_G2MAX = 0, CS_GLOCMAX = 1, CS_GV0MAX = 2, CS_DWMAX = 3, CS_SG_INV = 4, CS_SD_INV = 5, CS_COUNT = 64 };
+enum { PS_SMAX = 0, PS_LINVMAX = 1, PS_UMAX = 2, PS_COUNT = 64 };
+
+// running maximum of non-negative floats kept as their bit patterns (ordered like unsigned integers)
+__device__ __forceinline__ void atomic_max_abs(unsigned* slot, float absval) {
+  atomicMax(slot, __float_as_uint(absval));
+}
+
 __device__ __forceinline__ float plane_to_float(const bf16* p, int fmt) {
   return fmt == FMT_BF16 ? __bfloat162float(*p) : __half2float(*reinterpret_cast<const __half*>(p));
 }

@@ -1,8 +1,10 @@
 // C ABI of gdrf_b200 (include/gdrf_b200.h): workspace planning and the per-step kernel schedule.
 #include "../../include/gdrf_b200.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -33,29 +35,32 @@ int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
 constexpr int DEFAULT_SMS = 148;
 
 // ---- optional instrumentation (bench.py): kernel-launch counter and CUDA-event timing of the contractions ----
-long long g_launches = 0;
-bool g_profile = false;
+// The only process-global state of the library (include/gdrf_b200.h, "Instrumentation"): an atomic launch counter and,
+// while profiling is enabled, a mutex-guarded list of event pairs that grows with the run (nothing is dropped).
+std::atomic<long long> g_launches{0};
+std::atomic<bool> g_profile{false};
 enum { PK_G1 = 0, PK_G2F, PK_G2B, PK_G3, PK_G4, PK_G5, PK_G6, PK_COUNT };
 struct ProfRec { int kind; cudaEvent_t a, b; };
-constexpr int PROF_MAX = 4096;
-ProfRec g_prof[PROF_MAX];
-int g_prof_n = 0;
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_event_pool;
 
-cudaEvent_t prof_event() {
+cudaEvent_t prof_event() {   // g_prof_mu held
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ProfScope {
-  int idx = -1; cudaStream_t st;
+  cudaEvent_t b = nullptr; cudaStream_t st;
   ProfScope(int kind, cudaStream_t s) : st(s) {
-    if (g_profile && g_prof_n < PROF_MAX) {
-      idx = g_prof_n++;
-      g_prof[idx].kind = kind; g_prof[idx].a = prof_event(); g_prof[idx].b = prof_event();
-      cudaEventRecord(g_prof[idx].a, st);
+    if (g_profile.load(std::memory_order_relaxed)) {
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      ProfRec r{kind, prof_event(), prof_event()};
+      g_prof.push_back(r);
+      b = r.b;
+      cudaEventRecord(r.a, st);
     }
   }
-  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+  ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
 struct Plan {
@@ -64,12 +69,12 @@ struct Plan {
   long long ncp;          // padded rows per chunk (stride of the [K][ncp] arrays)
   int chunk_rows;
   // persistent
-  size_t acc, ck, du, dphi, dz, c5, phisum, status_pad;
+  size_t acc, ck, du, dphi, dz, c5, phisum, ps;
   size_t L64, Linv64, tmpA, tmpB, dinv, dinv32;
-  size_t linv_pl, st_pl, st16_pl, w16_pl;
+  size_t linv_pl, linv16_pl, st_pl, w16_pl;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
   // per chunk
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
-  size_t wsq, srow, arow, cnt, gv0, floc, q, fvar, theta, g_loc, g2, g1;
+  size_t wsq, srow, arow, cnt, gv0, floc, cs, q, fvar, theta, g_loc, g2, g1;   // cs sits right in front of q: one memset
   size_t total;
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
 };
@@ -111,7 +116,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.c5 = bump(off, sizeof(double) * Mp2);
   p.zero_bytes = (long long)off;
   p.phisum = bump(off, sizeof(float) * p.K);
-  p.status_pad = bump(off, 256);
+  p.ps = bump(off, sizeof(unsigned) * PS_COUNT);
   p.L64 = bump(off, sizeof(double) * Mp2);
   p.Linv64 = bump(off, sizeof(double) * Mp2);
   p.tmpA = bump(off, sizeof(double) * Mp2);
@@ -119,8 +124,8 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.dinv = bump(off, sizeof(double) * (size_t)p.Mp * NB);
   p.dinv32 = bump(off, sizeof(float) * (size_t)p.Mp * NB);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
-  p.st_pl = bump(off, sizeof(bf16) * 3 * (size_t)p.K * Mp2);
-  p.st16_pl = bump(off, sizeof(bf16) * 2 * (size_t)p.K * Mp2);
+  p.linv16_pl = bump(off, sizeof(bf16) * 2 * Mp2);
+  p.st_pl = bump(off, sizeof(bf16) * 4 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
   p.w_pl = bump(off, sizeof(bf16) * 3 * nm);
@@ -135,6 +140,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.gv0 = bump(off, sizeof(float) * p.ncp);
   const size_t kn = (size_t)p.K * p.ncp;
   p.floc = bump(off, sizeof(double) * kn);
+  p.cs = bump(off, sizeof(unsigned) * CS_COUNT);     // 256 bytes: q follows immediately
   p.q = bump(off, sizeof(double) * kn);
   p.fvar = bump(off, sizeof(float) * kn);
   p.theta = bump(off, sizeof(float) * kn);
@@ -155,6 +161,13 @@ PlaneMat plane_mat(void* ws, size_t off, long long rows, long long cols) {
   m.col_blocks = (int)(cols / 64);
   m.plane_stride = rows * cols;
   return m;
+}
+
+// operand planes of S in the two formats (they share Plan::st_pl)
+PlaneMat st_bf16(void* ws, const Plan& p) { return plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp); }
+PlaneMat st_f16_perm(void* ws, const Plan& p) { return plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp); }
+PlaneMat st_f16_nat(void* ws, const Plan& p) {
+  return plane_mat(ws, p.st_pl + sizeof(bf16) * 2 * (size_t)p.K * p.Mp * p.Mp, (long long)p.K * p.Mp, p.Mp);
 }
 
 Hyper make_hyper(const gdrf_shape* s, const gdrf_inputs* in) {
@@ -263,7 +276,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, p.Mp);
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
-  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp);
+  PlaneMat stm = st_bf16(ws, p);
 #define GDRF_KXZ_PLANES(DT, KID) \
   k_kxz_planes<DT, KID><<<dim3(p.MB, RT), 256, 0, st>>>(in->xs + n0 * p.D, nc, in->z, p.M, hp, kxz)
   GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_PLANES);
@@ -287,7 +300,8 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
-    CU(cudaMemsetAsync(at<double>(ws, p.q), 0, sizeof(double) * (size_t)p.K * p.ncp, st));
+    // q and the per-chunk scalars in front of it
+    CU(cudaMemsetAsync(at<char>(ws, p.cs), 0, (p.q - p.cs) + sizeof(double) * (size_t)p.K * p.ncp, st));
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
       G2<0>::Params g{};
       g.w = w; g.st = stm; g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
@@ -295,7 +309,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<0>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
     } else {                                 // fp16 2 x 2 planes (22-bit operands), 3 products
       G2<2>::Params g{};
-      g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp);
+      g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = st_f16_perm(ws, p);
       g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
       g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
@@ -315,24 +329,29 @@ __global__ void k_scale(const float* __restrict__ g, long long n, const float* _
     dst[i] = s * g[i];
 }
 
-__global__ void k_export_floc(const double* __restrict__ floc, int ncp, int nc, float* __restrict__ out,
+template <typename T>
+__global__ void k_export_floc(const double* __restrict__ floc, int ncp, int nc, T* __restrict__ out,
                               long long n_stride) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-  if (n < nc) out[(long long)k * n_stride + n] = (float)floc[(long long)k * ncp + n];
+  if (n < nc) out[(long long)k * n_stride + n] = (T)floc[(long long)k * ncp + n];
 }
 
 // f_var[k, n] = clamp(variance - |W_n|^2, 0) + q[k, n]   (pyro conditional, full_cov=False)
+template <typename T>
 __global__ void k_export_fvar(const double* __restrict__ q, const double* __restrict__ wsq,
-                              const float* __restrict__ variance, int ncp, int nc, float* __restrict__ out,
+                              const float* __restrict__ variance, int ncp, int nc, T* __restrict__ out,
                               long long n_stride) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-  if (n < nc) out[(long long)k * n_stride + n] = (float)(fmax((double)variance[0] - wsq[n], 0.0) + q[(long long)k * ncp + n]);
+  if (n < nc) out[(long long)k * n_stride + n] = (T)(fmax((double)variance[0] - wsq[n], 0.0) + q[(long long)k * ncp + n]);
 }
 
-// status stays >0 on a failed factorisation; otherwise -1 flags an fp16-range overflow of S or W (|W| <= sigma)
-__global__ void k_merge_status(const int* __restrict__ range_flag, const float* __restrict__ variance,
+// status stays >0 on a failed factorisation; otherwise -1 flags that an operand of the fp16 planes may leave the fp16
+// range: S itself, T = W S_k (|T| <= |W_n| |S_k[:, j]| <= sqrt(variance M) max|S|), Linv, or W (|W| <= sqrt(variance))
+__global__ void k_merge_status(const unsigned* __restrict__ ps, const float* __restrict__ variance, int M,
                                int* __restrict__ status) {
-  if (*status == 0 && (*range_flag != 0 || !(variance[0] < 3.0e9f))) *status = -1;
+  const float smax = __uint_as_float(ps[PS_SMAX]), lmax = __uint_as_float(ps[PS_LINVMAX]), var = variance[0];
+  const bool ok = smax < 60000.f && smax * sqrtf(var * (float)M) < 60000.f && lmax < 60000.f && var < 3.0e9f;
+  if (*status == 0 && !ok) *status = -1;
 }
 
 __global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms) {
@@ -389,35 +408,65 @@ __global__ void __launch_bounds__(256) k_perplexity(int N, int K, int V, const f
   }
 }
 
+template <typename T>
+int marginal_moments_impl(const gdrf_shape* s, const gdrf_inputs* in, T* out_floc, T* out_fvar, void* ws,
+                                 size_t ws_bytes, gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !ws || !out_floc) return fail(1, "null pointer argument%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
+  if (out_fvar && !in->u_scale_tril) return fail(1, "the marginal variance needs u_scale_tril%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = num_sms();
+  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
+    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
+    const int RT = (nc + 127) / 128;
+    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, out_fvar != nullptr, false, sms, st)) return e;
+    k_export_floc<T><<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
+                                                                out_floc + n0, (long long)s->n_local);
+    LAUNCH_CHECK();
+    if (out_fvar) {
+      k_export_fvar<T><<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.q), at<double>(ws, p.wsq),
+                                                                  in->variance, (int)p.ncp, nc, out_fvar + n0,
+                                                                  (long long)s->n_local);
+      LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* gdrf_last_error(void) { return g_err; }
 
-long long gdrf_launch_count(void) { return g_launches; }
+long long gdrf_launch_count(void) { return g_launches.load(); }
 
 int gdrf_profile_enable(int on) {
-  g_profile = on != 0;
+  g_profile.store(on != 0);
   return 0;
 }
 
-// ms[7], launches[7]: summed CUDA-event time and launch count of G1, G2-forward, G2-backward, G3, G4, G5, G6
+// ms[7], launches[7]: summed CUDA-event time and launch count of G1, G2-forward, k_scale_w, G3, G4, G5, G6
 // since the last read.  Synchronises the device.
 int gdrf_profile_read(double* ms, long long* launches) {
   if (!ms || !launches) return fail(1, "null pointer argument%s");
   for (int i = 0; i < PK_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
   CU(cudaDeviceSynchronize());
-  for (int i = 0; i < g_prof_n; ++i) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (const ProfRec& r : g_prof) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b) == cudaSuccess) {
-      ms[g_prof[i].kind] += t;
-      launches[g_prof[i].kind] += 1;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.kind] += t;
+      launches[r.kind] += 1;
     }
-    g_event_pool.push_back(g_prof[i].a);
-    g_event_pool.push_back(g_prof[i].b);
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
   }
-  g_prof_n = 0;
+  g_prof.clear();
   return 0;
 }
 
@@ -550,24 +599,28 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   } else {
     cholesky<double>(kuu, L, at<double>(ws, p.dinv), p.Mp, dev_status, st);
   }
-  g_launches += 2 * (p.Mp / NB);
+  g_launches += 2 * (p.Mp / NB) - 2;   // + the one LAUNCH_CHECK counts
   LAUNCH_CHECK();
   tri_inverse(L, at<double>(ws, p.dinv), Linv, p.Mp, st);
-  g_launches += 2 * (p.Mp / NB);
+  g_launches += 2 * (p.Mp / NB) - 2;
   LAUNCH_CHECK();
+  const bool f16 = (s->flags & GDRF_FLAG_FWD_BF16) == 0;
+  unsigned* ps = at<unsigned>(ws, p.ps);
+  CU(cudaMemsetAsync(ps, 0, sizeof(unsigned) * PS_COUNT, st));
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
-  k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv);
+  k_pack_linv<<<dim3(p.MB, p.MT), 256, 0, st>>>(Linv, p.M, p.Mp, linv, plane_mat(ws, p.linv16_pl, p.Mp, p.Mp), ps);
   LAUNCH_CHECK();
   if (in->u_scale_tril) {
-    // operand planes of S for this step; an entry outside the fp16 range turns the status into -1 so the
-    // caller runs the forward row-norm contraction on the 24-bit bf16 path instead (GDRF_FLAG_FWD_BF16)
-    int* range_flag = at<int>(ws, p.status_pad);
-    CU(cudaMemsetAsync(range_flag, 0, sizeof(int), st));
-    k_pack_st<<<dim3(p.MB, p.MB, p.K), 256, 0, st>>>(in->u_scale_tril, p.K, p.M, p.Mp,
-                                                     plane_mat(ws, p.st_pl, (long long)p.K * p.Mp, p.Mp),
-                                                     plane_mat(ws, p.st16_pl, (long long)p.K * p.Mp, p.Mp), range_flag);
+    // operand planes of S for this step: fp16 pairs (22 bits) unless the caller asked for bf16 (GDRF_FLAG_FWD_BF16);
+    // in fp16 mode a value that may leave the fp16 range turns the status into -1, and the caller repeats the
+    // prologue and runs the step with GDRF_FLAG_FWD_BF16
+    const dim3 grid(p.MB, p.MB, p.K);
+    if (f16) k_pack_st<true><<<grid, 256, 0, st>>>(in->u_scale_tril, p.K, p.M, p.Mp, st_bf16(ws, p), st_f16_perm(ws, p), st_f16_nat(ws, p), ps);
+    else k_pack_st<false><<<grid, 256, 0, st>>>(in->u_scale_tril, p.K, p.M, p.Mp, st_bf16(ws, p), st_f16_perm(ws, p), st_f16_nat(ws, p), ps);
     LAUNCH_CHECK();
-    k_merge_status<<<1, 1, 0, st>>>(range_flag, in->variance, dev_status);
+  }
+  if (f16) {
+    k_merge_status<<<1, 1, 0, st>>>(ps, in->variance, p.M, dev_status);
     LAUNCH_CHECK();
   }
   return 0;
@@ -600,7 +653,15 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
-  PlaneMat stm = plane_mat(ws, p.st_pl, (long long)K * Mp, Mp);
+  // 16-bit operand planes of the backward follow the forward's format: fp16 pairs (22 bits) by default
+  const bool f16 = (s->flags & GDRF_FLAG_FWD_BF16) == 0;
+  const int fmt = f16 ? FMT_F16 : FMT_BF16;
+  PlaneMat st_b = f16 ? st_f16_nat(ws, p) : st_bf16(ws, p);                       // B of dW (G3)
+  PlaneMat linv_b = f16 ? plane_mat(ws, p.linv16_pl, Mp, Mp) : linv;              // B of dKxz (G4)
+  PlaneMat w_b = f16 ? plane_mat(ws, p.w16_pl, p.ncp, Mp) : w;                    // B of C5 (G5)
+  unsigned* cs = at<unsigned>(ws, p.cs);
+  unsigned* ps = at<unsigned>(ws, p.ps);
+  const float* cs_f = at<float>(ws, p.cs);
   PlaneMat tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)K * Mp);
   PlaneMat wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)K * Mp);
   float* dwf = at<float>(ws, p.dwf);
@@ -609,6 +670,11 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   if (!cont) {
     k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
     LAUNCH_CHECK();
+    if (want_grad) {
+      CU(cudaMemsetAsync(ps + PS_UMAX, 0, sizeof(unsigned), st));
+      k_absmax<<<32, 256, 0, st>>>(in->u_loc, (long long)K * M, ps + PS_UMAX);
+      LAUNCH_CHECK();
+    }
   }
 
   // tiles of dS on / below the diagonal (i tile of 128 rows, j tile of 256 columns)
@@ -647,19 +713,19 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
                                              at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq),   \
                                              in->eps, hp, at<float>(ws, p.phisum), at<float>(ws, p.g_loc),         \
                                              at<float>(ws, p.g2), at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, \
-                                             RT * 128)
+                                             RT * 128, cs)
     GDRF_DISPATCH_KQ(K, GDRF_OBS_FINALIZE);
 #undef GDRF_OBS_FINALIZE
     LAUNCH_CHECK();
     if (!want_grad) continue;
     {
       ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
-      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm);
+      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm, fmt, in->variance, cs);
       LAUNCH_CHECK();
     }
     {
       G3::Params g{};
-      g.tp = tpm; g.st = stm; g.g2 = at<float>(ws, p.g2); g.dw = dwf;
+      g.tp = tpm; g.st = st_b; g.g2 = at<float>(ws, p.g2); g.dw = dwf; g.cs = cs; g.fmt = fmt;
       g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
       g.varn = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_FULL_WIDTH)) ? 0 : 1;
       g.isplit = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA)) ? 0 : 1;
@@ -670,12 +736,13 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
       CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
-                                                       in->u_loc, K, M, (int)p.ncp, dwt);
+                                                       in->u_loc, K, M, (int)p.ncp, dwt, fmt, in->variance, cs, ps);
       LAUNCH_CHECK();
     }
     if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
     {
       g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
+      g6.fmt = fmt; g6.inv_scale = cs_f + CS_SG_INV;
       // (topic, tile) items in units of CTA pairs: as many whole rounds of the sms / 2 pairs as fit run unsplit; the
       // items of the last, partial round are cut along the observations so that this round is full as well
       const int base = K * g6.ntile, pairs = base / 2, clusters = sms / 2, NBt = 2 * RT;
@@ -693,7 +760,10 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, n_items6, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
     }
     {
-      auto fill = [&](auto& g) { g.dwt = dwt; g.linv = linv; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp; };
+      auto fill = [&](auto& g) {
+        g.dwt = dwt; g.linv = linv_b; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+        g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
+      };
       ProfScope ps(PK_G4, st);
       ++g_launches;
       if ((s->flags & (GDRF_FLAG_REF_G4 | GDRF_FLAG_SINGLE_CTA)) != 0) {
@@ -716,7 +786,8 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     {
       const int NBt = 2 * RT;
       auto fill = [&](auto& g, int splits) {
-        g.dwt = dwt; g.w = w; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+        g.dwt = dwt; g.w = w_b; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+        g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
         if (splits > NBt) splits = NBt;
         if (splits < 1) splits = 1;
         const int per = (NBt + splits - 1) / splits;
@@ -754,7 +825,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
     dgemm<true, false, 3, false>(Linv, tB, tA, Mp, st);                      // L^-T Phi, Phi lower
     dgemm<false, false, 2, false>(tA, Linv, tB, Mp, st);                     // (...) L^-1
-    g_launches += 5;
+    g_launches += 5;   // 4 fp64 products + 2 tril ops, one counted by LAUNCH_CHECK
     LAUNCH_CHECK();
     k_kuu_backward<<<M, 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
     LAUNCH_CHECK();
@@ -795,30 +866,12 @@ int gdrf_marginal_mean(const gdrf_shape* s, const gdrf_inputs* in, float* out_fl
 
 int gdrf_marginal_moments(const gdrf_shape* s, const gdrf_inputs* in, float* out_floc, float* out_fvar, void* ws,
                           size_t ws_bytes, gdrf_stream_t stream) {
-  Plan p;
-  if (int e = make_plan(s, p)) return e;
-  if (int e = check_device()) return e;
-  if (!in || !ws || !out_floc) return fail(1, "null pointer argument%s");
-  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
-  if (out_fvar && !in->u_scale_tril) return fail(1, "the marginal variance needs u_scale_tril%s");
-  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int sms = num_sms();
-  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
-    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
-    const int RT = (nc + 127) / 128;
-    if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, out_fvar != nullptr, false, sms, st)) return e;
-    k_export_floc<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.floc), (int)p.ncp, nc,
-                                                             out_floc + n0, (long long)s->n_local);
-    LAUNCH_CHECK();
-    if (out_fvar) {
-      k_export_fvar<<<dim3((nc + 255) / 256, p.K), 256, 0, st>>>(at<double>(ws, p.q), at<double>(ws, p.wsq),
-                                                               in->variance, (int)p.ncp, nc, out_fvar + n0,
-                                                               (long long)s->n_local);
-      LAUNCH_CHECK();
-    }
-  }
-  return 0;
+  return marginal_moments_impl<float>(s, in, out_floc, out_fvar, ws, ws_bytes, stream);
+}
+
+int gdrf_marginal_moments_f64(const gdrf_shape* s, const gdrf_inputs* in, double* out_floc, double* out_fvar, void* ws,
+                              size_t ws_bytes, gdrf_stream_t stream) {
+  return marginal_moments_impl<double>(s, in, out_floc, out_fvar, ws, ws_bytes, stream);
 }
 
 int gdrf_perplexity_terms(const gdrf_shape* s, const gdrf_inputs* in, const float* floc, double* out,

@@ -13,6 +13,7 @@
 // path element for element (it is a device-side checker, not a fallback: the product never selects it).
 #pragma once
 #include <type_traits>
+#include <utility>
 #include "common.cuh"
 
 namespace gdrf {
@@ -129,6 +130,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
          | ((uint32_t)(N >> 3) << 17)  // [17,23) N >> 3
          | ((uint32_t)(M >> 4) << 24); // [24,29) M >> 4
 }
+
+// operand format of a policy: the compile-time P::FMT, or Params::fmt when the policy's operands come in either format
+template <class P, class = void>
+struct FmtOf {
+  __host__ __device__ static int get(const typename P::Params&) { return P::FMT; }
+};
+template <class P>
+struct FmtOf<P, std::void_t<decltype(std::declval<typename P::Params>().fmt)>> {
+  __host__ __device__ static int get(const typename P::Params& p) { return p.fmt; }
+};
 
 // (plane_a, plane_b) products kept by the issue loops: all pairs with pa + pb <= max(PA, PB) - 1
 
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, P::BN, P::A_MN, P::B_MN, P::FMT);
+      const uint32_t idesc = make_idesc(128, P::BN, P::A_MN, P::B_MN, FmtOf<P>::get(prm));
       constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
       uint32_t it = 0, unit = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -538,7 +549,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
     if (lane == 0) {
       if (rank == 0) {
         // ------------------------------ MMA issuer (leader CTA) ------------------------------
-        constexpr uint32_t idesc = make_idesc(256, 256, P::A_MN, P::B_MN, P::FMT);
+        const int fmt = FmtOf<P>::get(prm);
+        const uint32_t idesc = make_idesc(256, 256, P::A_MN, P::B_MN, fmt);
         constexpr int ORD = (P::PA > P::PB ? P::PA : P::PB) - 1;
         uint32_t it = 0, unit = 0;
         for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
@@ -563,7 +575,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
               uint32_t idesc_k = idesc, d_k = d_tmem;
               if constexpr (VarN<P>::value != 0) {
                 const int ncols = P::ncols(prm, P::kblock(kit, kn), kn);   // first k-block is full width by contract
-                idesc_k = make_idesc(256, ncols, P::A_MN, P::B_MN, P::FMT);
+                idesc_k = make_idesc(256, ncols, P::A_MN, P::B_MN, fmt);
                 d_k = d_tmem + (128 - (ncols >> 1));
               }
 #pragma unroll
@@ -665,6 +677,7 @@ __global__ void __launch_bounds__(32 * P::EPI_WARPS) gemm_ref_kernel(const typen
   constexpr int NCH = (P::BN / 32) / (P::EPI_WARPS / 4);
   const int c_begin = (threadIdx.x >> 7) * NCH;
   const int n_items = P::num_items(prm);
+  const int fmt = FmtOf<P>::get(prm);
   typename P::Epi epi;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int nsub = P::num_subs(prm, item);
@@ -682,7 +695,7 @@ __global__ void __launch_bounds__(32 * P::EPI_WARPS) gemm_ref_kernel(const typen
             for (int pl = P::PA - 1; pl >= 0; --pl) {
               const bf16* src = P::A_MN ? P::a_src(prm, item, sub, kit, pl, row >> 6) + tile_off(kk, row & 63)
                                         : P::a_src(prm, item, sub, kit, pl, 0) + tile_off(row, kk);
-              a += plane_to_float(src, P::FMT);
+              a += plane_to_float(src, fmt);
             }
             for (int j = 0; j < 32; ++j) {
               const int col = c * 32 + j;
@@ -690,7 +703,7 @@ __global__ void __launch_bounds__(32 * P::EPI_WARPS) gemm_ref_kernel(const typen
               for (int pl = P::PB - 1; pl >= 0; --pl) {
                 const bf16* src = P::B_MN ? P::b_src(prm, item, sub, kit, pl, col >> 6) + tile_off(kk, col & 63)
                                           : P::b_src(prm, item, sub, kit, pl, col >> 7) + tile_off(col & 127, kk);
-                b += plane_to_float(src, P::FMT);
+                b += plane_to_float(src, fmt);
               }
               v[j] = fmaf(a, b, v[j]);
             }

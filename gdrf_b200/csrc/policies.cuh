@@ -210,9 +210,9 @@ struct G2 {
         const int col0 = (s0 + sub) * BN + tile_col(c0);     // (k * NT + jt) * BN == k * Mp + jt * BN
 #pragma unroll
         for (int g = 0; g < 4; g += 2) {
-          uint4 pa[2], pb[2];
-          split8<2>(&v[g * 8], pa);
-          split8<2>(&v[g * 8 + 8], pb);
+          uint4 pa[2], pb[2];       // T planes in the forward's format: fp16 pairs (22 bits) or bf16 pairs
+          split8x2(FMT, &v[g * 8], pa);
+          split8x2(FMT, &v[g * 8 + 8], pb);
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) store16<true>(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
         }
@@ -234,13 +234,15 @@ struct G2 {
 // ---------------------------------------------------------------------------------------------
 struct G3 {
   static constexpr int EPI_WARPS = 8;
-  static constexpr int FMT = FMT_BF16;
+  static constexpr int FMT = FMT_BF16;   // overridden at run time by Params::fmt
   static constexpr int PA = 2, PB = 2, BN = 256;
   static constexpr bool A_MN = false, B_MN = true;
   struct Params {
-    PlaneMat tp, st;
+    PlaneMat tp, st;   // st: natural-order planes in the format of tp (fp16 pairs: ST16N; bf16 pairs: ST)
     const float* g2;   // [K][ncp]
     float* dw;         // [ncp][Mp] fp32
+    unsigned* cs;      // per-chunk scalars: max |dW| is recorded in cs[CS_DWMAX] (sizes the scale of the dWtot planes)
+    int fmt;           // FMT_F16 / FMT_BF16 of both operands
     int RT, MB, K, JT, Mp, ncp;
     int varn;          // CTA pairs only: narrow MMAs in the diagonal block + the column order that goes with them
     // CTA pairs: items are (column tile, 256-row pair tile), widest column tile first, two consecutive items = the two
@@ -338,6 +340,14 @@ struct G3 {
       const int it = col_tile(p, item, sub);
       const int half = last_c0 >> 7;
       float* base = p.dw + (long long)(rt * 128 + row) * p.Mp + it * 256;
+      {
+        float mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) mx = fmaxf(mx, fabsf(acc[j]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((row & 31) == 0 && mx > 0.f) atomic_max_abs(p.cs + CS_DWMAX, mx);
+      }
       // 64-column groups held by this thread: natural order, or [g0 g2 | g3 g1] under varn
       float4* d0 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 192 : 0) : half * 128));
       float4* d1 = reinterpret_cast<float4*>(base + (p.varn ? (half ? 64 : 128) : half * 128 + 64));
@@ -362,8 +372,10 @@ struct G4T {
   static constexpr bool A_MN = false, B_MN = true;
   static constexpr int CB = BN / 64;
   struct Params {
-    PlaneMat dwt, linv;
-    float* dkxz;   // [ncp][Mp] fp32
+    PlaneMat dwt, linv;   // both in format `fmt` (fp16 pairs: dWtot scaled by s_d, LINV16; bf16 pairs: LINV planes 0, 1)
+    float* dkxz;          // [ncp][Mp] fp32
+    const float* inv_scale;   // 1 / s_d (cs[CS_SD_INV]), applied to the accumulator
+    int fmt;
     int RT, MB, Mp;
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
@@ -377,12 +389,14 @@ struct G4T {
     return p.linv.base + pl * p.linv.plane_stride + p.linv.block_off(mb >> 1, sub * CB + pc) + (mb & 1) * 4096;
   }
   struct Epi {
-    __device__ void item_begin(const Params&, int, int) {}
+    float inv;
+    __device__ void item_begin(const Params& p, int, int) { inv = p.inv_scale[0]; }
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int sub, int row, int c0, const float (&v)[32]) {
       float4* dst = reinterpret_cast<float4*>(p.dkxz + (long long)(item * 128 + row) * p.Mp + sub * BN + c0);
 #pragma unroll
-      for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      for (int g = 0; g < 8; ++g)
+        dst[g] = make_float4(inv * v[4 * g], inv * v[4 * g + 1], inv * v[4 * g + 2], inv * v[4 * g + 3]);
     }
     __device__ void sub_end(const Params&, int, int, int) {}
     __device__ void item_end(const Params&, int, int) {}
@@ -401,8 +415,10 @@ struct G5T {
   static constexpr bool A_MN = true, B_MN = true;
   static constexpr int CB = BN / 64;
   struct Params {
-    PlaneMat dwt, w;
-    double* c5;   // [Mp][Mp]
+    PlaneMat dwt, w;      // both in format `fmt` (fp16 pairs: dWtot scaled by s_d, W16; bf16 pairs: W planes 0, 1)
+    double* c5;           // [Mp][Mp]
+    const float* inv_scale;   // 1 / s_d
+    int fmt;
     int RT, MB, Mp, MT, splits, nb_per_split;
   };
   // item = (split, column tile bt of BN columns, 128-row tile at), at fastest: with BN = 256 the items 2t, 2t + 1 are
@@ -425,13 +441,14 @@ struct G5T {
     return p.w.base + pl * p.w.plane_stride + p.w.block_off(nb >> 1, bt * CB + pc) + (nb & 1) * 4096;
   }
   struct Epi {
-    __device__ void item_begin(const Params&, int, int) {}
+    double inv;
+    __device__ void item_begin(const Params& p, int, int) { inv = (double)p.inv_scale[0]; }
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
       const int t = item % per_split(p), at = t % p.MT, bt = t / p.MT;
       double* dst = p.c5 + (long long)(at * 128 + row) * p.Mp + bt * BN + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, (double)v[j]);
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, inv * (double)v[j]);
     }
     __device__ void sub_end(const Params&, int, int, int) {}
     __device__ void item_end(const Params&, int, int) {}
@@ -449,8 +466,10 @@ struct G6 {
   static constexpr bool A_MN = true, B_MN = true;
   static constexpr int MAX_TILES = 512;
   struct Params {
-    PlaneMat wg, tp;
+    PlaneMat wg, tp;   // both in format `fmt`; WG carries the power-of-two scale s_g
     float* ds;   // [K][M][M] fp32, unpadded gradient accumulator
+    const float* inv_scale;   // 1 / s_g (cs[CS_SG_INV]), applied to the accumulator
+    int fmt;
     // items [0, n_whole) contract the whole observation range of the chunk and own their tile (plain += on dS);
     // each of the remaining (topic, tile) pairs is cut into tail_sp pieces of tail_per 64-observation blocks that add
     // atomically -- sized by the host so that the last round of the persistent CTAs / CTA pairs is full
@@ -498,7 +517,8 @@ struct G6 {
     return b_at(p, decode(p, item), kit, pl, pc);
   }
   struct Epi {
-    __device__ void item_begin(const Params&, int, int) {}
+    float inv;
+    __device__ void item_begin(const Params& p, int, int) { inv = p.inv_scale[0]; }
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
       const Item it = decode(p, item);
@@ -509,11 +529,11 @@ struct G6 {
       if (it.whole) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j0 + j <= i) dst[j0 + j] += v[j];
+          if (j0 + j <= i) dst[j0 + j] = fmaf(inv, v[j], dst[j0 + j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j0 + j <= i) atomicAdd(dst + j0 + j, v[j]);
+          if (j0 + j <= i) atomicAdd(dst + j0 + j, inv * v[j]);
       }
     }
     __device__ void sub_end(const Params&, int, int, int) {}

@@ -93,48 +93,63 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
 }
 
 // ---------------------------------------------------------------------------------------------
-// ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110), 3 planes; zero elsewhere.
+// ST[(k, j), i] = S_k[i, j] for i >= j (u_scale_tril, sparse_gdrf.py:100-110); zero elsewhere.
+//   F16 = true : two fp16 planes (22-bit operands) twice -- `st16` with the rows of every 256-row tile permuted for the
+//                forward contraction's narrow MMAs (policies.cuh, G2) and `st16n` in natural order for dW (G3)
+//   F16 = false: three bf16 planes (`st`; any fp32 range) for the 24-bit forward and the bf16 backward
+// max |S| goes to ps[PS_SMAX]: the prologue turns it into the "leaves the fp16 range" status.
 // grid (Mp/64 [j tile], Mp/64 [i tile], K), 256 threads; transposes through shared memory.
 // ---------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(256) k_pack_st(const float* __restrict__ S, int K, int M, int Mp, PlaneMat st,
-                                                 PlaneMat st16, int* __restrict__ range_flag) {
+                                                 PlaneMat st16, PlaneMat st16n, unsigned* __restrict__ ps) {
   __shared__ float tile[64][65];
   const int jt = blockIdx.x, it = blockIdx.y, k = blockIdx.z;
+  float mx = 0.f;
   for (int t = threadIdx.x; t < 64 * 64; t += 256) {
     const int ii = t >> 6, jj = t & 63;
     const int i = it * 64 + ii, j = jt * 64 + jj;
-    tile[ii][jj] = (i < M && j < M && i >= j) ? S[((long long)k * M + i) * M + j] : 0.f;
+    const float v = (i < M && j < M && i >= j) ? S[((long long)k * M + i) * M + j] : 0.f;
+    tile[ii][jj] = v;
+    mx = fmaxf(mx, fabsf(v));
   }
   __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_abs(ps + PS_SMAX, mx);
   for (int t = threadIdx.x; t < 64 * 8; t += 256) {
     const int jj = t >> 3, g = t & 7;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = tile[g * 8 + e][jj];
-    uint4 pk[3];
-    split8<3>(v, pk);
     const int row = k * Mp + jt * 64 + jj;
+    if (!F16) {
+      uint4 pk[3];
+      split8<3>(v, pk);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
-    bool over = false;
+      for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(st.elem(pl, row, it * 64 + g * 8)) = pk[pl];
+    } else {
+      uint4 hk[2];
+      split8h<2>(v, hk);
+      // permuted copy: rows of every 256-row tile in the order [g3a g2a g1a g0a | g0b g1b g2b g3b] (policies.cuh, G2)
+      const int jl = (jt * 64 + jj) & 255, X = jl >> 6, w32 = jl & 31;
+      const int pos = (jl & 32) ? 128 + 32 * X + w32 : 32 * (3 - X) + w32;
+      const int row16 = row - jl + pos;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) over |= !(fabsf(v[e]) < 60000.f);
-    if (over) atomicExch(range_flag, 1);
-    uint4 hk[2];
-    split8h<2>(v, hk);
-#pragma unroll
-    // fp16 planes: rows of every 256-row tile in the order [g3a g2a g1a g0a | g0b g1b g2b g3b] (policies.cuh, G2)
-    const int jl = (jt * 64 + jj) & 255, X = jl >> 6, w32 = jl & 31;
-    const int pos = (jl & 32) ? 128 + 32 * X + w32 : 32 * (3 - X) + w32;
-    const int row16 = row - jl + pos;
-#pragma unroll
-    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(st16.elem(pl, row16, it * 64 + g * 8)) = hk[pl];
+      for (int pl = 0; pl < 2; ++pl) {
+        *reinterpret_cast<uint4*>(st16.elem(pl, row16, it * 64 + g * 8)) = hk[pl];
+        *reinterpret_cast<uint4*>(st16n.elem(pl, row, it * 64 + g * 8)) = hk[pl];
+      }
+    }
   }
 }
 
-// LINV planes (3) from the fp64 inverse Cholesky factor [Mp][Mp]; identity padding is dropped.
-__global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Linv, int M, int Mp, PlaneMat linv) {
+// LINV planes (3 bf16 for the whitening G1; 2 fp16 for dKxz, G4) from the fp64 inverse Cholesky factor [Mp][Mp];
+// identity padding is dropped.  max |Linv| goes to ps[PS_LINVMAX].
+__global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Linv, int M, int Mp, PlaneMat linv,
+                                                   PlaneMat linv16, unsigned* __restrict__ ps) {
   const int cb = blockIdx.x, rt = blockIdx.y;
+  float mx = 0.f;
   for (int t = threadIdx.x; t < 128 * 8; t += 256) {
     const int r = t >> 3, g = t & 7;
     const int m = rt * 128 + r;
@@ -143,12 +158,30 @@ __global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Li
     for (int e = 0; e < 8; ++e) {
       const int i = cb * 64 + g * 8 + e;
       v[e] = (m < M && i <= m) ? (float)Linv[(long long)m * Mp + i] : 0.f;
+      mx = fmaxf(mx, fabsf(v[e]));
     }
     uint4 pk[3];
     split8<3>(v, pk);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(linv.elem(pl, m, cb * 64 + g * 8)) = pk[pl];
+    uint4 hk[2];
+    split8h<2>(v, hk);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(linv16.elem(pl, m, cb * 64 + g * 8)) = hk[pl];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_abs(ps + PS_LINVMAX, mx);
+}
+
+// max |x| over a small array (u_loc) into a per-step slot
+__global__ void k_absmax(const float* __restrict__ x, long long n, unsigned* __restrict__ slot) {
+  float mx = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_abs(slot, mx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,9 +548,13 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
                                                       Hyper hp, const float* __restrict__ phisum,
                                                       float* __restrict__ g_loc, float* __restrict__ g2,
                                                       float* __restrict__ gv0, double* __restrict__ ck,
-                                                      double* __restrict__ acc, int npad) {
+                                                      double* __restrict__ acc, int npad,
+                                                      unsigned* __restrict__ cs) {
   __shared__ double scratch[32];
   __shared__ float cks[8 * KQ];
+  __shared__ unsigned smax[3];
+  if (threadIdx.x < 3) smax[threadIdx.x] = 0u;
+  float mx_g2 = 0.f, mx_gl = 0.f;
   const int sub = threadIdx.x & 7;
   const int n = blockIdx.x * 32 + (threadIdx.x >> 3);
   for (int t = threadIdx.x; t < 8 * KQ; t += 256) cks[t] = 0.f;
@@ -562,6 +599,8 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
       }
       g_loc[o] = gm;            // padding rows are zeroed
       g2[o] = 2.f * gv;
+      mx_g2 = fmaxf(mx_g2, fabsf(2.f * gv));
+      mx_gl = fmaxf(mx_gl, fabsf(gm));
     }
   }
 #pragma unroll
@@ -576,8 +615,20 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
       llc = lgamma((double)cnt[n] + 1.0);
     }
     gv0[n] = g0;
+    if (g0 != 0.f) atomicMax(&smax[2], __float_as_uint(fabsf(g0)));
+  }
+  // chunk-wide maxima of the backward weights: they size the power-of-two scales of the fp16 operand planes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx_g2 = fmaxf(mx_g2, __shfl_xor_sync(0xffffffffu, mx_g2, o));
+    mx_gl = fmaxf(mx_gl, __shfl_xor_sync(0xffffffffu, mx_gl, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx_g2 > 0.f) atomicMax(&smax[0], __float_as_uint(mx_g2));
+    if (mx_gl > 0.f) atomicMax(&smax[1], __float_as_uint(mx_gl));
   }
   __syncthreads();
+  if (threadIdx.x < 3 && smax[threadIdx.x] != 0u) atomicMax(cs + CS_G2MAX + threadIdx.x, smax[threadIdx.x]);
   for (int k = threadIdx.x; k < K; k += 256)
     if (cks[k] != 0.f) atomicAdd(&ck[k], (double)cks[k]);
   dnoise = block_sum(dnoise, scratch);
@@ -668,14 +719,19 @@ __global__ void __launch_bounds__(256) k_du(PlaneMat w, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// WG[n, (k, m)] = g2[k, n] * W[n, m]  (2 bf16 planes): the per-topic row-weighted copies of W that turn
-// dS_k = W^T diag(g2_k) T_k into a plain contraction.  grid (MB, RT), 256 threads; W's block is rebuilt once
-// and rescaled K times.
+// WG[n, (k, m)] = s_g * g2[k, n] * W[n, m]  (two planes, fp16 or bf16): the per-topic row-weighted copies of W that
+// turn dS_k = W^T diag(g2_k) T_k into a plain contraction.  s_g is the power-of-two scale that puts
+// max |g2| * sqrt(variance) (>= max |WG|: |W_n| <= sqrt(k(x, x))) at 2^13..2^14; G6's epilogue multiplies by 1 / s_g
+// (cs[CS_SG_INV]).  grid (MB, RT), 256 threads; W's block is rebuilt once and rescaled K times.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __restrict__ g2, int K, int MB, int ncp,
-                                                 PlaneMat wg) {
+                                                 PlaneMat wg, int fmt, const float* __restrict__ variance,
+                                                 unsigned* __restrict__ cs) {
   const int cb = blockIdx.x, rt = blockIdx.y;
   const int g = threadIdx.x & 7;            // 8 lanes cover the eight 16-byte chunks of one 128-byte row
+  float inv_s;
+  const float s_g = pow2_scale(__uint_as_float(cs[CS_G2MAX]) * sqrtf(variance[0]), &inv_s);
+  if (cb == 0 && rt == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cs)[CS_SG_INV] = inv_s;
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int r = it * 32 + (threadIdx.x >> 3);
@@ -687,12 +743,12 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
     join8<3>(pk, wj);
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float sc = g2[(long long)k * ncp + n];
+      const float sc = s_g * g2[(long long)k * ncp + n];
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = sc * wj[j];
       uint4 out[2];
-      split8<2>(v, out);
+      split8x2(fmt, v, out);
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl)      // streaming store: 2.4 GB per chunk, read back only after it left L2
         __stcs(reinterpret_cast<uint4*>(wg.elem(pl, n, (k * MB + cb) * 64 + g * 8)), out[pl]);
@@ -701,15 +757,25 @@ __global__ void __launch_bounds__(256) k_scale_w(PlaneMat w, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// dWtot = dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m]   -> 2 planes
+// dWtot = s_d * (dW (from G3) + sum_k g_loc[k, n] u_loc[k, m] - 2 gv0[n] W[n, m])   -> 2 planes (fp16 or bf16)
+// s_d: power-of-two scale from the bound max|dW| + K max|g_loc| max|u_loc| + 2 max|gv0| sqrt(variance); the epilogues of
+// G4 / G5 multiply by 1 / s_d (cs[CS_SD_INV]).
 // grid (MB, RT), 256 threads: 8 lanes per 128-byte row, a thread owns 4 rows (r, r + 32, r + 64, r + 96) x 8 columns;
 // the rank-K update runs first on a 4 x 8 register tile (per topic: one 16-byte load of g for the 4 rows, two of u).
 // dynamic shared memory: u block [K][72] | g tile [K][128] with row r stored at (r & 31) * 4 + (r >> 5)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __restrict__ dw, int Mp,
                                                      const float* __restrict__ g_loc, const float* __restrict__ gv0,
-                                                     const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt) {
+                                                     const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt,
+                                                     int fmt, const float* __restrict__ variance,
+                                                     unsigned* __restrict__ cs, const unsigned* __restrict__ ps) {
   extern __shared__ __align__(16) float dwf_smem[];
+  float inv_sd;
+  const float s_d = pow2_scale(__uint_as_float(cs[CS_DWMAX]) +
+                                   (float)K * __uint_as_float(cs[CS_GLOCMAX]) * __uint_as_float(ps[PS_UMAX]) +
+                                   2.f * __uint_as_float(cs[CS_GV0MAX]) * sqrtf(variance[0]),
+                               &inv_sd);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cs)[CS_SD_INV] = inv_sd;
   float* us = dwf_smem;            // [K][72]: 64 columns, the upper 32 shifted by 4 words (bank spread)
   float* gs = us + K * 72;         // [K][128]
   const int cb = blockIdx.x, rt = blockIdx.y;
@@ -758,9 +824,9 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     const float m2g = -2.f * gv0[n];
     float o8[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o8[j] = fmaf(m2g, wj[j], dd[j]) + v[q][j];
-    uint4 out[2];      // G4 and G5 consume dWtot as two bf16 planes
-    split8<2>(o8, out);
+    for (int j = 0; j < 8; ++j) o8[j] = s_d * (fmaf(m2g, wj[j], dd[j]) + v[q][j]);
+    uint4 out[2];      // G4 and G5 consume dWtot as two 16-bit planes
+    split8x2(fmt, o8, out);
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, n, col)) = out[pl];
   }

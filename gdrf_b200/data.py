@@ -12,7 +12,10 @@ import torch
 def load_counts_csv(path: str, dimensions: int, device="cpu") -> Tuple[torch.Tensor, torch.Tensor, List[Tuple[float, float]]]:
     """Returns (xs float32 [N, D] in [0, 1], ws int32 [N, V], world = [(min, max)] per dimension of xs)."""
     import pandas as pd
-    dataset = pd.read_csv(filepath_or_buffer=path, index_col=list(range(dimensions)), header=0).fillna(0).astype(int)
+    # parse_dates=True as the reference passes it: a date-indexed 1-D file (the MVCO hourly series) becomes datetime64,
+    # whose differences normalise to [0, 1] like any numeric index
+    dataset = pd.read_csv(filepath_or_buffer=path, index_col=list(range(dimensions)), header=0,
+                          parse_dates=True).fillna(0).astype(int)
     index = dataset.index
     index = index.values if dimensions == 1 else np.array(index.to_list())
     index = index - index.min(axis=-dimensions, keepdims=True)

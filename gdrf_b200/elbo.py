@@ -107,13 +107,17 @@ class _Call:
         """jittercholesky (utils.py:27-40): escalate until the factorisation succeeds."""
         lib = _lib.load()
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        for nj in range(int(maxjitter)):
+
+        def run(nj):
             _lib.check(lib.gdrf_prologue(ctypes.byref(self.shape), ctypes.byref(self.inputs), float(jitter), nj,
                                          self.workspace.data_ptr(), self.ws_bytes, self.stream, status.data_ptr()))
-            st = int(status.item())          # the one host read-back of the step (mirrors try/except)
-            if st == -1:                     # factorised, but an operand leaves the fp16 range: 24-bit bf16 forward
+            return int(status.item())        # the one host read-back of the step (mirrors try/except)
+
+        for nj in range(int(maxjitter)):
+            st = run(nj)
+            if st == -1:                     # factorised, but an operand may leave the fp16 range: repack as bf16 planes
                 self.shape.flags |= _lib.FLAG_FWD_BF16
-                st = 0
+                st = run(nj)
             if st == 0:
                 return nj
         raise RuntimeError("reached max jitter, covariance is unstable")
@@ -311,8 +315,9 @@ def marginal_mean(xs, Z, variance, lengthscale, u_loc, kernel: str = "rbf", jitt
 
 def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: str = "rbf", jitter: float = 1e-8,
                      maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0,
-                     scale_mixture=None):
-    """(f_loc, f_var), each [K, N]: ``SparseGDRF.forward(Xnew, full_cov=False)`` (sparse_gdrf.py:277-319)."""
+                     scale_mixture=None, dtype=torch.float32):
+    """(f_loc, f_var), each [K, N]: ``SparseGDRF.forward(Xnew, full_cov=False)`` (sparse_gdrf.py:277-319).
+    ``dtype=torch.float64`` returns the moments as the library holds them (gdrf_marginal_moments_f64)."""
     K, M = u_loc.shape
     N = xs.shape[0]
     dev = xs.device
@@ -321,10 +326,11 @@ def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: 
                  torch.ones(K, 1, device=dev), torch.ones(K, 1, device=dev), torch.zeros(K, N, device=dev),
                  _lib.KERNEL_IDS[kernel], 0, flags, chunk_rows, scale_mixture)
     call.prologue(jitter, maxjitter)
-    floc = torch.empty(K, N, dtype=torch.float32, device=dev)
-    fvar = torch.empty(K, N, dtype=torch.float32, device=dev)
-    _lib.check(_lib.load().gdrf_marginal_moments(ctypes.byref(call.shape), ctypes.byref(call.inputs), floc.data_ptr(),
-                                                 fvar.data_ptr(), call.workspace.data_ptr(), call.ws_bytes, call.stream))
+    floc = torch.empty(K, N, dtype=dtype, device=dev)
+    fvar = torch.empty(K, N, dtype=dtype, device=dev)
+    fn = _lib.load().gdrf_marginal_moments_f64 if dtype == torch.float64 else _lib.load().gdrf_marginal_moments
+    _lib.check(fn(ctypes.byref(call.shape), ctypes.byref(call.inputs), floc.data_ptr(), fvar.data_ptr(),
+                  call.workspace.data_ptr(), call.ws_bytes, call.stream))
     return floc, fvar
 
 

@@ -18,7 +18,6 @@ guide=scale(m.guide), ...)`` (``train_script.py:365-371``) sees the identical lo
 from __future__ import annotations
 
 import warnings
-import weakref
 from typing import Callable, List, Optional, Tuple, Union
 
 import torch
@@ -204,10 +203,12 @@ class SparseMultinomialGDRF(nn.Module):
     def _scaled(self, xs: torch.Tensor) -> torch.Tensor:
         # the reference asserts the bounds on every call (topic_model.py:177: one device->host sync each, three per
         # step); a tensor that was already checked and has not been written since is not checked again
-        ref, ver = getattr(self, "_bounds_checked", (None, -1))
-        if ref is None or ref() is not xs or ver != xs._version:
+        # (a plain tuple, not a weak reference: the reference checkpoints the whole module with torch.save,
+        # train_script.py:490-500, so every attribute has to pickle)
+        key = (id(xs), xs.data_ptr(), tuple(xs.shape), xs._version)
+        if getattr(self, "_bounds_checked", None) != key:
             assert self._check_bounds(xs)
-            self._bounds_checked = (weakref.ref(xs), xs._version)
+            self._bounds_checked = key
         return self.scale(xs.to(self.device).float())
 
     def _check_Xnew_shape(self, Xnew: torch.Tensor):
@@ -221,7 +222,11 @@ class SparseMultinomialGDRF(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     def seed_eps(self, seed: int) -> None:
-        self._eps_generator = torch.Generator(device=self.device).manual_seed(int(seed))
+        """Seeds the generator of the guide's self-drawn ``eps``.  Under torch.distributed every rank draws for its own
+        observations, so the rank is folded into the seed (identical streams would correlate the shards)."""
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self._eps_generator = torch.Generator(device=self.device).manual_seed(int(seed) + 1000003 * rank)
 
     def elbo(self, xs: torch.Tensor, ws: torch.Tensor, eps: Optional[torch.Tensor] = None,
              n_global: Optional[int] = None, n_offset: int = 0, include_prior: bool = True,
@@ -239,8 +244,9 @@ class SparseMultinomialGDRF(nn.Module):
                           "(sparse_gdrf.py:380); gdrf_b200 scales once for model and guide")
             self._warned_world = True
         N = x.shape[0]
-        if eps is None:
+        if eps is None:     # drawn here for exactly these observations: the window into eps starts at 0
             eps = torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
+            n_offset = 0
         n_global = N if n_global is None else int(n_global)
         ws = ws.to(self.device)
 

@@ -25,6 +25,17 @@ def allreduce_grads_(params, group=None) -> None:
         o += g.numel()
 
 
+def global_count(n_local: int, device, group=None) -> int:
+    """The N of the reference's ``poutine.scale(1/N)`` (train_script.py:365) when every rank holds a shard: the sum of
+    the shard sizes.  A caller that does not pass ``n_global`` gets this instead of silently normalising by its own
+    shard (which would make the all-reduced loss and gradients world_size times too large)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(n_local)
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
 def shard_bounds(n: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of n observations for `rank`."""
     base, rem = divmod(n, world)
@@ -77,6 +88,8 @@ class SVI:
 
     def loss_and_grads(self, xs, ws, eps=None, n_global=None, n_offset=0) -> torch.Tensor:
         rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
+        if n_global is None:
+            n_global = global_count(xs.shape[0], xs.device, self.group)
         elbo = self.module.elbo(xs, ws, eps=eps, n_global=n_global, n_offset=n_offset, include_prior=(rank == 0))
         loss = -elbo
         loss.backward()
@@ -129,12 +142,31 @@ class FusedSVI:
             if module._kernel_kind == "rationalquadratic":
                 parts.append(module._kernel.scale_mixture_unconstrained.reshape(-1))
             self.theta_u = torch.cat([p.detach().float() for p in parts]).contiguous().to(dev)
+            # the module's parameters become views of the flat buffer: what FusedSVI trains is what the module
+            # evaluates (perplexity, kernel_lengthscale, checkpoints -- train_script.py:468-500) with nothing to sync
+            o = 0
+            for p_, n_ in self._targets():
+                if p_ is not None:
+                    p_.data = self.theta_u[o:o + n_].view_as(p_)
+                o += n_
         self.theta_c = torch.empty_like(self.theta_u)
         self.mom1 = torch.zeros_like(self.theta_u)
         self.mom2 = torch.zeros_like(self.theta_u)
         self.row_scratch = torch.empty(K, dtype=torch.float32, device=dev)
         self.shape = _lib.Shape(n_local=1, n_offset=0, n_eps=1, d=D, m=M, k=K, v=V,
                                 kernel_id=_lib.KERNEL_IDS[module._kernel_kind], ls_dim=self.ls_dim, chunk_rows=0, flags=0)
+
+    def _targets(self):
+        m = self.m
+        K, M, V, D = m.K, m.M, m.V, m.D
+        t = [(m.u_scale_tril_unconstrained, K * M * M), (m.u_loc_unconstrained, K * M),
+             (m._word_topic_matrix_map_unconstrained, K * V),
+             (m._inducing_points_unconstrained if self.learn_z else None, M * D),
+             (m._kernel.variance_unconstrained, 1), (m._kernel.lengthscale_unconstrained, self.ls_dim),
+             (m.noise_unconstrained, 1)]
+        if m._kernel_kind == "rationalquadratic":
+            t.append((m._kernel.scale_mixture_unconstrained, 1))
+        return t
 
     def _views(self):
         from .elbo import split_grad
@@ -153,9 +185,10 @@ class FusedSVI:
         c = self.constrain()
         x = m._scaled(xs)
         N = x.shape[0]
-        n_global = N if n_global is None else int(n_global)
-        if eps is None:
+        n_global = global_count(N, m.device, self.group) if n_global is None else int(n_global)
+        if eps is None:     # drawn for exactly these observations
             eps = torch.randn(m.K, N, device=m.device, generator=m._eps_generator)
+            n_offset = 0
         rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
         terms, g, _ = elbo_value_and_grads(x, ws.to(m.device), c["Z"], c["variance"], c["lengthscale"], c["u_loc"],
                                            c["u_scale_tril"], c["noise"], c["phi"], m._dirichlet_param, eps,
@@ -183,19 +216,11 @@ class FusedSVI:
         return float((-elbo / n_global).item())
 
     def write_back(self) -> None:
-        """Copies the flat unconstrained buffer back into the module's parameters."""
-        m = self.m
-        K, M, V, D = m.K, m.M, m.V, m.D
+        """Kept for callers of the first version: the module's parameters are views of the flat buffer, so there is
+        nothing to copy (a parameter that was re-assigned since is re-attached)."""
         o = 0
         with torch.no_grad():
-            targets = [(m.u_scale_tril_unconstrained, K * M * M), (m.u_loc_unconstrained, K * M),
-                       (m._word_topic_matrix_map_unconstrained, K * V),
-                       (m._inducing_points_unconstrained if self.learn_z else None, M * D),
-                       (m._kernel.variance_unconstrained, 1), (m._kernel.lengthscale_unconstrained, self.ls_dim),
-                       (m.noise_unconstrained, 1)]
-            if m._kernel_kind == "rationalquadratic":
-                targets.append((m._kernel.scale_mixture_unconstrained, 1))
-            for p, n in targets:
-                if p is not None:
-                    p.copy_(self.theta_u[o:o + n].view_as(p))
+            for p, n in self._targets():
+                if p is not None and p.data_ptr() != self.theta_u[o:o + n].data_ptr():
+                    p.data = self.theta_u[o:o + n].view_as(p)
                 o += n

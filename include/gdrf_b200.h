@@ -8,8 +8,10 @@
  *   gdrf/models/sparse_gdrf.py:161-186   log_topic_probs (evaluation path)
  * (and the pyro.contrib.gp kernels / `conditional` / torch.distributions code those call).
  *
- * Ownership: the caller owns every buffer (inputs, outputs, workspace); the library allocates nothing and
- * keeps no global state besides a thread-local error string.  All pointers are DEVICE pointers unless
+ * Ownership: the caller owns every buffer (inputs, outputs, workspace); the library allocates no device memory and
+ * keeps no state between calls besides a thread-local error string and the optional instrumentation at the end of
+ * this header (an atomic launch counter; a mutex-guarded list of CUDA events while profiling is enabled).  Calls on
+ * different (workspace, stream) pairs are independent and may be issued from different host threads.  All pointers are DEVICE pointers unless
  * stated otherwise.  All work is enqueued on `stream`; no call synchronises the device.  The only value
  * the host has to read back between calls is the 4-byte Cholesky status (to reproduce the try/except
  * escalation of jittercholesky).  Every entry point returns 0 on success and a non-zero code otherwise
@@ -34,9 +36,11 @@ enum {
   GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
   GDRF_FLAG_INCLUDE_PRIOR = 2,    /* add the Dirichlet log-density of phi and its gradient (one rank only)   */
   GDRF_FLAG_CHOL_FP32_STATUS = 4, /* decide not-PD with an fp32 factorisation of the reference's fp32 Kuu    */
-  GDRF_FLAG_FWD_BF16 = 16,        /* forward row-norm contraction on 3 bf16 planes / 6 products (24-bit operands,
-                                     any fp32 range) instead of 2 fp16 planes / 3 products (22-bit, |x| < 6e4);
-                                     required when gdrf_prologue reported status -1                          */
+  GDRF_FLAG_FWD_BF16 = 16,        /* every 16-bit operand plane is bf16 (any fp32 range): the forward row-norm
+                                     contraction runs on 3 bf16 planes / 6 products (24-bit operands) and the
+                                     backward contractions on bf16 pairs (16-bit), instead of fp16 pairs / 3 products
+                                     (22-bit operands, |x| < 6e4) everywhere.  Pass it to gdrf_prologue AND
+                                     gdrf_elbo_step when gdrf_prologue reported status -1                    */
   GDRF_FLAG_CONTINUE = 64,        /* gdrf_elbo_step: keep the accumulators of the previous call on this workspace
                                      (second and later sub-shards of one step streamed from host memory)       */
   GDRF_FLAG_PARTIAL = 128,        /* gdrf_elbo_step: more sub-shards follow; skip the per-step epilogue (Cholesky
@@ -99,8 +103,9 @@ int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
 
 /* Kuu = k(Z,Z) + (sum_{i<=njitter} jitter*10^i) I, its Cholesky factor and inverse, packed for the tensor
  * pipe (also packs u_scale_tril when in->u_scale_tril is non-NULL); *dev_status (DEVICE int) = 0 when the
- * factorisation succeeded, 1 + the failing column when it did not, -1 when it succeeded but u_scale_tril or the
- * kernel variance leave the fp16 range (then pass GDRF_FLAG_FWD_BF16 to gdrf_elbo_step).
+ * factorisation succeeded, 1 + the failing column when it did not, -1 when it succeeded but u_scale_tril, L^-1, the
+ * kernel variance or the bound sqrt(variance m) max|u_scale_tril| on T = W S_k may leave the fp16 range (then call
+ * gdrf_prologue again, and gdrf_elbo_step, with GDRF_FLAG_FWD_BF16; with that flag the status is never -1).
  * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39).          */
 int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
                   size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
@@ -128,6 +133,12 @@ int gdrf_marginal_mean(const gdrf_shape* shape, const gdrf_inputs* in, float* ou
  * NULL.  Requires gdrf_prologue (which packs u_scale_tril).                                                 */
 int gdrf_marginal_moments(const gdrf_shape* shape, const gdrf_inputs* in, float* out_floc, float* out_fvar,
                           void* workspace, size_t workspace_bytes, gdrf_stream_t stream);
+
+/* The same moments as the library holds them internally (fp64 per-observation chain): [k, n_local] fp64.  The
+ * reference's outputs are fp32; this variant exists so that a caller (and the parity tests) can see the marginal
+ * variance -- which the model uses as a *scale*, sparse_gdrf.py:403-405 -- below fp32 resolution.               */
+int gdrf_marginal_moments_f64(const gdrf_shape* shape, const gdrf_inputs* in, double* out_floc, double* out_fvar,
+                              void* workspace, size_t workspace_bytes, gdrf_stream_t stream);
 
 /* perplexity pieces (abstract_gdrf.py:137-139): out[0] = sum w log(word_probs), out[1] = sum w  (fp64),
  * from f_loc [k, n_local]; the N x V word-probability matrix is never materialised.                        */
@@ -163,9 +174,10 @@ int gdrf_clipped_adam_step(const gdrf_shape* shape, float* theta_u, const float*
 int gdrf_gather_rows(const float* xs, const int32_t* ws, const int64_t* index, int64_t n_sel, int64_t n_rows, int32_t d,
                      int32_t v, float* xs_out, int32_t* ws_out, int* dev_status, gdrf_stream_t stream);
 
-/* Instrumentation for bench.py: kernels launched by this process so far; CUDA-event timing of the six
- * contractions (ms[7] / launches[7] in the order G1, G2, k_scale_w, G3, G4, G5, G6, summed since
- * the previous read; the read synchronises the device).  Off by default.                                   */
+/* Instrumentation for bench.py -- the library's only process-global state: kernels launched by this process so far
+ * (atomic counter); CUDA-event timing of the six contractions (ms[7] / launches[7] in the order G1, G2, k_scale_w,
+ * G3, G4, G5, G6, summed over EVERY launch since the previous read -- the record list grows with the run; the read
+ * synchronises the device and recycles the events).  Off by default.                                        */
 long long gdrf_launch_count(void);
 int gdrf_profile_enable(int on);
 int gdrf_profile_read(double* ms, long long* launches);

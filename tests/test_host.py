@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     from gdrf_b200.build import build
     build()
     header = open(os.path.join(ROOT, "include", "gdrf_b200.h")).read()
-    declared = set(re.findall(r"\b(gdrf_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(gdrf_[a-z0-9_]+)\s*\(", header))
     assert {"gdrf_workspace_bytes", "gdrf_prologue", "gdrf_elbo_step", "gdrf_elbo_backward",
             "gdrf_marginal_mean", "gdrf_last_error"} <= declared
     lib = _lib.load()
@@ -152,6 +152,10 @@ assert abs(loss.item() - full["loss"].item()) < 1e-10 * abs(full["loss"].item())
 for k in O.GRAD_NAMES:
     gk = m.p[k].grad if k != "u_scale_tril" else m.p[k].grad.tril()
     assert O.rel_err(gk, g[k]) < 1e-9, k
+# without n_global the shards' sizes are all-reduced (never "my own shard size": the sum would be world x too large)
+m.zero_grad()
+loss2 = SVI(m).loss_and_grads(inp.xs[lo:hi], inp.ws[lo:hi], eps=inp.eps, n_offset=lo)
+assert abs(loss2.item() - full["loss"].item()) < 1e-10 * abs(full["loss"].item()), (loss2.item(), full["loss"].item())
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -182,6 +186,31 @@ def test_csv_ingest_matches_reference_recipe(tmp_path):
     p1.write_text("t,a,b\n10,1,0\n20,0,5\n40,2,2\n")
     xs1, ws1, world1 = load_counts_csv(str(p1), 1)
     assert xs1.shape == (3, 1) and torch.allclose(xs1[:, 0], torch.tensor([0.0, 1.0 / 3.0, 1.0]))
+    # a date-indexed 1-D series (the MVCO hourly file): parse_dates=True, train_script.py:256
+    p2 = tmp_path / "dates.csv"
+    p2.write_text("t,a,b\n2021-08-19 00:00:00,1,0\n2021-08-19 01:00:00,0,5\n2021-08-19 03:00:00,2,2\n")
+    xs2, ws2, world2 = load_counts_csv(str(p2), 1)
+    assert xs2.shape == (3, 1) and torch.allclose(xs2[:, 0], torch.tensor([0.0, 1.0 / 3.0, 1.0]))
+    assert ws2.tolist() == [[1, 0], [0, 5], [2, 2]] and world2 == [(0.0, 1.0)]
+
+
+def test_whole_module_checkpoint_line_of_the_reference_works(tmp_path):
+    """train_script.py:490-500 saves ``deepcopy(model).half()`` with torch.save: every attribute of the drop-in has to
+    pickle, also after model calls have cached their bounds check and seeded the draw generator."""
+    import copy
+    from gdrf_b200 import RBF, SparseMultinomialGDRF
+    m = SparseMultinomialGDRF(num_observation_categories=21, num_topic_categories=3, world=[(0.0, 1.0)] * 2,
+                              kernel=RBF(2, variance=torch.tensor(25.0), lengthscale=torch.tensor([0.1])),
+                              dirichlet_param=0.01, n_points=6, inducing_init="grid", device="cpu", jitter=1e-4,
+                              maxjitter=15)
+    xs = torch.rand(10, 2)
+    m._scaled(xs)          # what every elbo / log_topic_probs / perplexity call does first
+    m.seed_eps(3)
+    path = tmp_path / "last.pt"
+    torch.save({"epoch": 0, "model": copy.deepcopy(m).half()}, path)
+    back = torch.load(path, weights_only=False)["model"].float()
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), back.named_parameters()):
+        assert n1 == n2 and torch.allclose(p1, p2, atol=2e-2, rtol=1e-2)
 
 
 def test_streaming_sampler_reproduces_the_reference_source_lines():
