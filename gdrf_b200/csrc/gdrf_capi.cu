@@ -74,7 +74,7 @@ struct Plan {
   size_t linv_pl, linv16_pl, st_pl, w16_pl;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
   // per chunk
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
-  size_t wsq, srow, arow, cnt, gv0, floc, cs, q, fvar, theta, g_loc, g2, g1;   // cs sits right in front of q: one memset
+  size_t srow, arow, cnt, gv0, floc, cs, wsq, q, fvar, theta, g_loc, g2, g1;   // cs | wsq | q are contiguous: one memset
   size_t total;
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
 };
@@ -133,14 +133,14 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tp_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.wg_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.dwf = bump(off, sizeof(float) * nm);
-  p.wsq = bump(off, sizeof(double) * p.ncp);
   p.srow = bump(off, sizeof(float) * p.ncp);
   p.arow = bump(off, sizeof(float) * p.ncp);
   p.cnt = bump(off, sizeof(float) * p.ncp);
   p.gv0 = bump(off, sizeof(float) * p.ncp);
   const size_t kn = (size_t)p.K * p.ncp;
   p.floc = bump(off, sizeof(double) * kn);
-  p.cs = bump(off, sizeof(unsigned) * CS_COUNT);     // 256 bytes: q follows immediately
+  p.cs = bump(off, sizeof(unsigned) * CS_COUNT);     // 256 bytes; wsq and q follow immediately: one memset per chunk
+  p.wsq = bump(off, sizeof(double) * p.ncp);
   p.q = bump(off, sizeof(double) * kn);
   p.fvar = bump(off, sizeof(float) * kn);
   p.theta = bump(off, sizeof(float) * kn);
@@ -277,6 +277,9 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, p.Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, p.Mp, p.Mp);
   PlaneMat stm = st_bf16(ws, p);
+  // per-chunk scalars, |W_n|^2 and (with_var) q are accumulated into: cleared together
+  CU(cudaMemsetAsync(at<char>(ws, p.cs), 0,
+                     with_var ? (p.q - p.cs) + sizeof(double) * (size_t)p.K * p.ncp : (p.q - p.cs), st));
 #define GDRF_KXZ_PLANES(DT, KID) \
   k_kxz_planes<DT, KID><<<dim3(p.MB, RT), 256, 0, st>>>(in->xs + n0 * p.D, nc, in->z, p.M, hp, kxz)
   GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_PLANES);
@@ -285,7 +288,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   {
     auto fill = [&](auto& g) {
       g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq);
-      g.RT = RT; g.MB = p.MB;
+      g.RT = RT; g.MB = p.MB; g.segk = (s->flags & GDRF_FLAG_NO_SEGMENTS) ? 0 : 1;
     };
     ProfScope ps(PK_G1, st);
     ++g_launches;
@@ -300,8 +303,6 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
   LAUNCH_CHECK();
   if (with_var) {
-    // q and the per-chunk scalars in front of it
-    CU(cudaMemsetAsync(at<char>(ws, p.cs), 0, (p.q - p.cs) + sizeof(double) * (size_t)p.K * p.ncp, st));
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
       G2<0>::Params g{};
       g.w = w; g.st = stm; g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
@@ -313,6 +314,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
       g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
+      g.segk = (s->flags & GDRF_FLAG_SEGMENTED_FWD) ? 1 : 0;
       const bool pairs = (s->flags & (GDRF_FLAG_REF_G2 | GDRF_FLAG_SINGLE_CTA)) == 0;
       g.ksplit = pairs ? topic_split(p.K, (RT + 1) / 2, sms / 2) : 0;
       const int n_items = pairs ? ((RT + 1) / 2) * 2 * g.ksplit : RT;

@@ -291,18 +291,21 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
             const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
             bool first = (kit == 0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int phase = 0; phase < 2; ++phase) {      // corrections first, hi * hi last (see gemm_tc2_kernel)
 #pragma unroll
-              for (int pa = 0; pa < P::PA; ++pa) {
+              for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                for (int pb = 0; pb < P::PB; ++pb) {
-                  if (pa + pb > ORD) continue;
-                  const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
-                  const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
-                  const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
-                  const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
-                  umma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
-                  first = false;
+                for (int pa = 0; pa < P::PA; ++pa) {
+#pragma unroll
+                  for (int pb = 0; pb < P::PB; ++pb) {
+                    if (pa + pb > ORD || ((pa + pb == 0) != (phase == 1))) continue;
+                    const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                    const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                    const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                    const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                    umma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                    first = false;
+                  }
                 }
               }
             }
@@ -431,6 +434,24 @@ struct VarCtx<P, true> {
   __device__ static type make(const typename P::Params& p, int item, int sub) { return P::make_ctx(p, item, sub); }
 };
 
+// Segmented accumulation (policy declares `SEGK = 1` and Params::segk): every 64-deep k-block of a tile is
+// accumulated in a FRESH TMEM buffer (the two buffers alternate per k-block instead of per tile), the epilogue warps
+// drain each k-block and add it into fp32 registers with round-to-nearest, and the policy's epilogue runs on the register
+// sums.  Inside a k-block the small correction products (hi*lo, lo*hi) are issued first, while the accumulator is still
+// small, and the hi*hi products last.  Why: the tensor pipe's fp32 accumulation costs about one ulp of the running sum
+// per MMA (measured: the marginal variance off by 2.3e-7 relative, random -- which the model turns into 2e-4 of
+// gradient error because it uses that variance as the *scale* of the guide's draw, sparse_gdrf.py:403-405); with 12
+// MMAs per k-block and a dense contraction that is 4 ulp of T.  Segmented, an MMA's error is an ulp of ONE k-block's
+// share of T, and only 4 MMAs per k-block meet a non-negligible accumulator.
+template <class P, class = void>
+struct SegK { static constexpr int value = 0; };
+template <class P>
+struct SegK<P, std::void_t<decltype(P::SEGK)>> { static constexpr int value = P::SEGK; };
+template <class P, bool = (SegK<P>::value != 0)>
+struct SegOn { __device__ static bool get(const typename P::Params&) { return false; } };
+template <class P>
+struct SegOn<P, true> { __device__ static bool get(const typename P::Params& p) { return p.segk != 0; } };
+
 template <class P>
 struct Gemm2Cfg {
   static_assert(P::BN == 256, "pair kernel computes 256 x 256 tiles");
@@ -556,13 +577,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
         for (int item2 = cluster_id; item2 < n_items2; item2 += n_clusters) {
           const int item = min(2 * item2, n_items1 - 1);
           const int nsub = P::num_subs(prm, item);
-          for (int sub = 0; sub < nsub; ++sub, ++unit) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kn = P::k_iters(prm, item, sub);
+            if constexpr (SegK<P>::value != 0) if (SegOn<P>::get(prm)) {
+              // one TMEM buffer per k-block; corrections first, hi * hi last
+              for (int kit = 0; kit < kn; ++kit, ++it, ++unit) {
+                const int acc = unit & 1;
+                const uint32_t aph = (unit >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1;
+                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&peer_full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + P::PA * Cfg::A_BYTES;
+                uint32_t idesc_k = idesc, d_k = tmem_base + acc * 256;
+                if constexpr (VarN<P>::value != 0) {
+                  const int ncols = P::ncols(prm, P::kblock(kit, kn), kn);
+                  idesc_k = make_idesc(256, ncols, P::A_MN, P::B_MN, fmt);
+                  d_k += (128 - (ncols >> 1));
+                }
+                bool first = true;
+#pragma unroll
+                for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int pa = 0; pa < P::PA; ++pa) {
+#pragma unroll
+                      for (int pb = 0; pb < P::PB; ++pb) {
+                        if (pa + pb > ORD || ((pa + pb == 0) != (phase == 1))) continue;
+                        const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                        const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                        const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                        const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                        umma2_f16(d_k, da, db, idesc_k, first ? 0u : 1u);
+                        first = false;
+                      }
+                    }
+                  }
+                }
+                umma2_commit_mc(&empty_bar[s]);
+                umma2_commit_mc(&tfull_bar[acc]);
+              }
+              continue;
+            }
             const int acc = unit & 1;
             const uint32_t aph = (unit >> 1) & 1;
+            ++unit;
             mbar_wait(&tempty_bar[acc], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
-            const int kn = P::k_iters(prm, item, sub);
             for (int kit = 0; kit < kn; ++kit, ++it) {
               const int s = it % NST;
               const uint32_t ph = (it / NST) & 1;
@@ -578,19 +644,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
                 idesc_k = make_idesc(256, ncols, P::A_MN, P::B_MN, fmt);
                 d_k = d_tmem + (128 - (ncols >> 1));
               }
+              // the small correction products of the split first, hi * hi last: an MMA costs about an ulp of the
+              // accumulator it adds into, and the accumulator is smallest before this k-block's main products arrive
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
+              for (int phase = 0; phase < 2; ++phase) {
 #pragma unroll
-                for (int pa = 0; pa < P::PA; ++pa) {
+                for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                  for (int pb = 0; pb < P::PB; ++pb) {
-                    if (pa + pb > ORD) continue;
-                    const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
-                    const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
-                    const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
-                    const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
-                    umma2_f16(d_k, da, db, idesc_k, first ? 0u : 1u);
-                    first = false;
+                  for (int pa = 0; pa < P::PA; ++pa) {
+#pragma unroll
+                    for (int pb = 0; pb < P::PB; ++pb) {
+                      if (pa + pb > ORD || ((pa + pb == 0) != (phase == 1))) continue;
+                      const uint32_t a_addr = sa + pa * Cfg::A_BYTES + (P::A_MN ? ks * 2048 : ks * 32);
+                      const uint32_t b_addr = sb + pb * Cfg::B_BYTES + (P::B_MN ? ks * 2048 : ks * 32);
+                      const uint64_t da = make_smem_desc(a_addr, P::A_MN ? 8192 : 16, 1024);
+                      const uint64_t db = make_smem_desc(b_addr, P::B_MN ? 8192 : 16, 1024);
+                      umma2_f16(d_k, da, db, idesc_k, first ? 0u : 1u);
+                      first = false;
+                    }
                   }
                 }
               }
@@ -632,10 +703,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<P>(), 1
       const int item = valid ? item_raw : n_items1 - 1;
       const int nsub = P::num_subs(prm, item);
       if (valid) epi.item_begin(prm, item, row);
-      for (int sub = 0; sub < nsub; ++sub, ++unit) {
+      for (int sub = 0; sub < nsub; ++sub) {
+        if (valid) epi.sub_begin(prm, item, sub, row);
+        if constexpr (SegK<P>::value != 0) if (SegOn<P>::get(prm)) {
+          // segmented accumulation: drain every k-block's TMEM buffer into fp32 registers (round-to-nearest adds)
+          static_assert(SegK<P>::value == 0 || NCH == 4, "segmented accumulation: 8 epilogue warps x 128 columns");
+          float sum[4][32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c][j] = 0.f;
+          const int kn = P::k_iters(prm, item, sub);
+          for (int kit = 0; kit < kn; ++kit, ++unit) {
+            const int acc = unit & 1;
+            const uint32_t aph = (unit >> 1) & 1;
+            int w0 = 0, w1 = 256;                              // accumulator columns this k-block's MMAs wrote
+            if constexpr (VarN<P>::value != 0) {
+              const int ncols = P::ncols(prm, P::kblock(kit, kn), kn);
+              w0 = 128 - (ncols >> 1);
+              w1 = 128 + (ncols >> 1);
+            }
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int c0 = (c_begin + c) * 32;
+              if (c0 >= w0 && c0 + 32 <= w1) {                 // warp-uniform
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[c][j] += v[j];
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+              else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+          }
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) epi.chunk(prm, item, sub, row, (c_begin + c) * 32, sum[c]);
+            epi.sub_end(prm, item, sub, row);
+          }
+          continue;
+        }
         const int acc = unit & 1;
         const uint32_t aph = (unit >> 1) & 1;
-        if (valid) epi.sub_begin(prm, item, sub, row);
+        ++unit;
         mbar_wait(&tfull_bar[acc], aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;

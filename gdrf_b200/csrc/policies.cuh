@@ -44,17 +44,19 @@ __device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int
                  : "memory");
 }
 
-// sum of 32 squares: four independent fp32 partial sums of 8 terms, combined in fp64
+// sum of 32 squares in fp64 (four independent chains): the row norms feed the marginal variance, which the model uses
+// as a scale -- an fp32 partial sum here (3e-8 relative) is already visible in the gradients
 __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    s0 = fmaf(v[j], v[j], s0);
-    s1 = fmaf(v[8 + j], v[8 + j], s1);
-    s2 = fmaf(v[16 + j], v[16 + j], s2);
-    s3 = fmaf(v[24 + j], v[24 + j], s3);
+    const double a = v[j], b = v[8 + j], c = v[16 + j], d = v[24 + j];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+    s2 = fma(c, c, s2);
+    s3 = fma(d, d, s3);
   }
-  return ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
+  return (s0 + s1) + (s2 + s3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -62,15 +64,18 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------
 template <int BN_>
 struct G1T {
-  static constexpr int EPI_WARPS = 4;
+  static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter (segmented accumulation: 128 columns each)
+  static constexpr int SEGK = (BN_ == 256) ? 1 : 0;
   static constexpr int PA = 3, PB = 3, BN = BN_;     // 128: one CTA per tile; 256: CTA pair (gemm_tc2_kernel)
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
   static constexpr int CB = BN / 64, PCS = BN / 128;
   struct Params {
     PlaneMat kxz, linv, w, w16;   // w16: fp16 2-plane copy of W for the forward row-norm contraction
-    double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients)
+    double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients); zeroed by the
+                   // caller, the column halves of a row add their partial sums
     int RT, MB;
+    int segk;      // CTA pairs: segmented accumulation (gemm_tc.cuh, SegK)
   };
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.MB / CB; }
@@ -104,7 +109,7 @@ struct G1T {
       acc += sumsq32(v);
     }
     __device__ void sub_end(const Params&, int, int, int) {}
-    __device__ void item_end(const Params& p, int item, int row) { p.wsq[item * 128 + row] = acc; }
+    __device__ void item_end(const Params& p, int item, int row) { atomicAdd(&p.wsq[item * 128 + row], acc); }
   };
 };
 using G1 = G1T<128>;
@@ -132,6 +137,7 @@ struct G2 {
     int store_t;       // write TP (gradient pass)
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
     int varn;          // CTA pairs: 1 = narrow MMAs in the diagonal blocks, 0 = full width (GDRF_FLAG_FULL_WIDTH, A/B)
+    int segk;          // CTA pairs: 1 = segmented accumulation (gemm_tc.cuh, SegK), 0 = one TMEM accumulation per tile
     // CTA pairs: items are (256-row pair tile, group of K / ksplit topics), two consecutive items = the two 128-row
     // halves of one pair tile.  A chunk with fewer than 74 pair tiles (the last chunk of a shard) then still fills
     // the machine: ksplit is chosen by the host so that ceil(pair tiles * ksplit / 74) / ksplit is smallest.
@@ -163,6 +169,7 @@ struct G2 {
   // rank 1 the first N/2 of its, and the MMA covers accumulator columns [128 - N/2, 128 + N/2).  The k-blocks are
   // walked last-to-first so that the first MMA is full width; 15 % fewer MMA columns per tile row.
   static constexpr int VARN = (MODE == 2) ? 1 : 0;
+  static constexpr int SEGK = (MODE == 2) ? 1 : 0;
   __device__ static int kblock(int kit, int kn) { return kn - 1 - kit; }
   __device__ static int ncols(const Params& p, int kb, int) {
     return (kb >= 4 || p.varn == 0) ? 256 : 64 * (kb + 1);

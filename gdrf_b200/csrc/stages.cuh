@@ -48,41 +48,43 @@ __global__ void __launch_bounds__(256) k_kxz_planes(const float* __restrict__ xs
   const int D = DT ? DT : hp.D;
   const int cb = blockIdx.x, rt = blockIdx.y;
   const int g = threadIdx.x & 7;
-  float il[DM], zl[8][DM];
+  // fp64 throughout: the scaled distance is an argument of exp(), which turns its relative rounding error into
+  // |r2 / 2| times as much in K_xz, and the whitening W = Kxz L^-T amplifies that again by its cancellation
+  double il[DM], zl[8][DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d)
-    if (d < D) il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
+    if (d < D) il[d] = 1.0 / (double)hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = cb * 64 + g * 8 + j;
 #pragma unroll
     for (int d = 0; d < DM; ++d)
-      if (d < D) zl[j][d] = (col < M) ? Z[col * D + d] : 0.f;
+      if (d < D) zl[j][d] = (col < M) ? (double)Z[col * D + d] : 0.0;
   }
-  const float var = hp.variance[0];
-  const float alpha = (KID == KERNEL_RQ) ? hp.alpha[0] : 1.f;
+  const double var = hp.variance[0];
+  const double alpha = (KID == KERNEL_RQ) ? (double)hp.alpha[0] : 1.0;
   const int cvalid = min(8, M - (cb * 64 + g * 8));     // columns of this thread inside M (may be <= 0)
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const int r = w * 32 + (threadIdx.x >> 3);
     const int n = rt * 128 + r;
-    float x[DM];
+    double x[DM];
 #pragma unroll
     for (int d = 0; d < DM; ++d)
-      if (d < D) x[d] = (n < nc) ? xs[(long long)n * D + d] : 0.f;
+      if (d < D) x[d] = (n < nc) ? (double)xs[(long long)n * D + d] : 0.0;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float r2 = 0.f;
+      double r2 = 0.0;
 #pragma unroll
       for (int d = 0; d < DM; ++d)
         if (d < D) {
-          const float t = (x[d] - zl[j][d]) * il[d];     // difference first: exact for nearby points
-          r2 = fmaf(t, t, r2);
+          const double t = (x[d] - zl[j][d]) * il[d];
+          r2 = fma(t, t, r2);
         }
-      float k, dk;
-      kernel_eval<float>(KID, r2, k, dk, alpha);
-      v[j] = (n < nc && j < cvalid) ? var * k : 0.f;
+      double k, dk;
+      kernel_eval<double>(KID, r2, k, dk, alpha);
+      v[j] = (n < nc && j < cvalid) ? (float)(var * k) : 0.f;
     }
     uint4 pk[3];
     split8<3>(v, pk);
@@ -858,10 +860,11 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
       il[d] = 1.f / hp.lengthscale[hp.ls_dim == 1 ? 0 : d];
       z[d] = (i < M) ? Z[i * D + d] : 0.f;
     }
-  float dz[DM], dl[DM];
+  // fp64 running sums: these are sums over all observations of large terms of both signs
+  double dz[DM], dl[DM];
 #pragma unroll
-  for (int d = 0; d < DM; ++d) dz[d] = dl[d] = 0.f;
-  float dv = 0.f, da = 0.f;
+  for (int d = 0; d < DM; ++d) dz[d] = dl[d] = 0.0;
+  double dv = 0.0, da = 0.0;
   const float alpha = (KID == KERNEL_RQ) ? hp.alpha[0] : 1.f;
   const float* col = dkxz + i;
   for (int rb = r0; rb < r1; rb += 128) {
@@ -886,40 +889,40 @@ __global__ void __launch_bounds__(128) k_kxz_backward(const float* __restrict__ 
           }
         float k, dk, dka = 0.f;
         kernel_eval<float>(KID, r2, k, dk, alpha, &dka);
-        dv = fmaf(g, k, dv);
-        if (KID == KERNEL_RQ) da = fmaf(g, dka, da);
+        dv += (double)(g * k);
+        if (KID == KERNEL_RQ) da += (double)(g * dka);
         const float h = g * dk;
 #pragma unroll
         for (int d = 0; d < DM; ++d)
           if (d < D) {
             const float ht = h * t[d];
-            dz[d] += ht;
-            dl[d] = fmaf(ht, t[d], dl[d]);
+            dz[d] += (double)ht;
+            dl[d] += (double)(ht * t[d]);
           }
       }
     }
   }
-  const float c = -2.f * hp.variance[0];
+  const double c = -2.0 * (double)hp.variance[0];
   if (i < M)
 #pragma unroll
     for (int d = 0; d < DM; ++d)
-      if (d < D) atomicAdd(&dz_acc[i * D + d], (double)(c * il[d] * dz[d]));
-  double dvs = block_sum((double)dv, scratch);
+      if (d < D) atomicAdd(&dz_acc[i * D + d], c * (double)il[d] * dz[d]);
+  double dvs = block_sum(dv, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dvs);
   if (KID == KERNEL_RQ) {
-    double das = block_sum((double)(hp.variance[0] * da), scratch);
+    double das = block_sum((double)hp.variance[0] * da, scratch);
     if (threadIdx.x == 0) atomicAdd(&acc[ACC_DALPHA], das);
   }
   if (hp.ls_dim == 1) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int d = 0; d < DM; ++d)
-      if (d < D) s += c * il[d] * dl[d];
-    double t = block_sum((double)s, scratch);
+      if (d < D) s += c * (double)il[d] * dl[d];
+    double t = block_sum(s, scratch);
     if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS], t);
   } else {
     for (int d = 0; d < D; ++d) {
-      double t = block_sum((double)(c * il[d] * dl[d]), scratch);
+      double t = block_sum(c * (double)il[d] * dl[d], scratch);
       if (threadIdx.x == 0) atomicAdd(&acc[ACC_DLS + d], t);
     }
   }

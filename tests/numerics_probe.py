@@ -27,9 +27,11 @@ def main():
     from gdrf_b200.elbo import marginal_moments
     out_path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     base = _lib.FLAG_CHOL_FP32_STATUS
-    variants = {"fp16x3 (default)": base, "bf16x6": base | _lib.FLAG_FWD_BF16,
-                "plain-FMA checker, fp16 planes": base | _lib.FLAG_REF_G[1] | _lib.FLAG_REF_G[2],
-                "fp16x3 full width": base | _lib.FLAG_FULL_WIDTH}
+    variants = {"default (fp16x3, whitening segmented)": base,
+                "nothing segmented": base | _lib.FLAG_NO_SEGMENTS,
+                "whitening + forward segmented": base | _lib.FLAG_SEGMENTED_FWD,
+                "bf16x6": base | _lib.FLAG_FWD_BF16,
+                "plain-FMA checker, fp16 planes": base | _lib.FLAG_REF_G[1] | _lib.FLAG_REF_G[2]}
     res = []
     for name, kw in CASES.items():
         inp = O.make_problem(**kw)

@@ -20,6 +20,8 @@ from oracle import gdrf_oracle as O  # noqa: E402
 from tests.helpers import FULL_CASES, GOLDEN_CASES, fullsize_errors, load_fullsize, load_golden  # noqa: E402
 
 LIVE = {
+    "smoke_700": (dict(N=700, D=2, K=3, V=24, grid=[6, 6], kernel="rbf", seed=5), 700),
+    "sweep_300": (dict(N=300, D=2, K=3, V=2, grid=[5, 7], kernel="matern52", seed=400), 300),
     "c2_shape_3000": (dict(N=3000, D=1, K=8, V=174, grid=[1000], kernel="matern32", seed=71), 3000),
     "c3_shape_20k": (dict(N=20000, D=2, K=16, V=128, grid=[16, 16], kernel="rbf", seed=61), 20000),
     "c4_shape_6000": (dict(N=6000, D=3, K=32, V=512, grid=[16, 8, 8], kernel="rbf", seed=52), 2000),

@@ -1,30 +1,31 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run on the B200 box: pytest -m gpu.
 
-Gate: the fp64 oracle (same inputs, same fixed posterior draws eps, same jitter level).
-  * ELBO and its four terms: |rel err| <= 1e-5  (north_star asks <= 1e-4)
-  * gradients w.r.t. u_loc, u_scale_tril, phi, noise, norm-wise per tensor: <= GRAD_TOL = 1e-4, *or* no
-    worse than 2x the error the fp32 oracle -- the reference's own arithmetic -- makes against fp64 on that
-    tensor at that size.
-  * gradients w.r.t. the kernel hyper-parameters and inducing points (variance, lengthscale, Z): these are
-    sums over observations of large contributions of both signs that cancel to a small residual; at the
-    fixture sizes (N ~ 1e3) the fp32 reference itself is 1e-4 ... 1e-3 off fp64 on them (SURVEY.md section 7,
-    hard part 1) and the 16-bit R operand of the backward contractions adds unbiased noise of the same kind.
-    Gate: <= HYPER_TOL = 5e-3 here, and <= 1e-3 at N = 20 000 (test_c3_shape_20k_observations_...):
-    the noise averages out as 1/sqrt(N).  DESIGN.md "Numerics" has the measurements.
+Same inputs, same fixed posterior draws eps, same jitter level.  Three distances are computed for every gradient tensor
+(norm-wise relative): CUDA vs the fp64 oracle, the fp32 oracle -- the reference's own arithmetic -- vs fp64, CUDA vs
+the fp32 oracle.  ONE gate everywhere (tests/helpers.py:parity_ok, tolerance 1e-4 = north_star's):
+    err(CUDA, fp64) <= max(1e-4, err(fp32 oracle, fp64))   or   err(CUDA, fp32 oracle) <= 1e-4
+i.e. within 1e-4 of the truth; where the fp32 reference is itself further than that from the truth, no further than the
+reference is (factor 1.0); or within 1e-4 of the fp32 reference, which is what north_star literally names.
+ELBO and its four terms: |rel err| <= 1e-5 against fp64.
+DESIGN.md "Numerics" holds the measured table (tests/parity_table.py prints it).
 """
 import numpy as np
 import pytest
 import torch
 
 from oracle import gdrf_oracle as O
-from tests.helpers import GOLDEN_CASES, load_golden
+from tests.helpers import (FULL_CASES, GOLDEN_CASES, TOL, assert_parity, fullsize_errors, load_fullsize, load_golden,
+                           parity_ok)
 
 pytestmark = pytest.mark.gpu
 
 ELBO_TOL = 1e-5
-GRAD_TOL = 1e-4
-HYPER_TOL = 5e-3
 HYPER = ("variance", "lengthscale", "Z")
+
+
+def _three_way(g, N, g64, g32, names=None):
+    names = names or [k for k in g64 if k in g]
+    return {k: (O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k]), O.rel_err(-g[k] / N, g32[k])) for k in names}
 
 
 def _dev():
@@ -62,11 +63,7 @@ def _check_against_golden(inp, d, terms, g, nj, grad_names=O.GRAD_NAMES):
         ref64 = torch.from_numpy(d[f"f64_grad_{k}"])
         ref32 = torch.from_numpy(d[f"f32_grad_{k}"]).double()
         ours = -g[k] / N
-        err = O.rel_err(ours, ref64)
-        err32 = O.rel_err(ref32, ref64)
-        report[k] = (err, err32)
-        tol = HYPER_TOL if k in HYPER else max(GRAD_TOL, 2.0 * err32)
-        assert err <= tol, (k, err, err32)
+        report[k] = (O.rel_err(ours, ref64), O.rel_err(ref32, ref64), O.rel_err(ours, ref32))
     return report
 
 
@@ -74,23 +71,21 @@ def _check_against_golden(inp, d, terms, g, nj, grad_names=O.GRAD_NAMES):
 def test_golden_parity(name):
     inp, d = load_golden(name)
     terms, g, nj = _run(inp)
-    rep = _check_against_golden(inp, d, terms, g, nj)
-    print(name, {k: (f"{a:.1e}", f"fp32-oracle {b:.1e}") for k, (a, b) in rep.items()})
+    assert_parity(_check_against_golden(inp, d, terms, g, nj), name)
 
 
 def test_c1_reference_defaults_escalate_jitter_like_the_reference():
     """C1 (data/data_2d_artificial.csv at train() defaults): the fp32 Cholesky of the reference needs 5
     escalations; the CUDA path must land on the same level and then match the fp64 oracle at that level.
-    At this conditioning the kernel hyper-parameter gradients of the fp32 reference are pure noise
-    (rel err >> 1 against fp64), so only the well-posed ones are gated."""
+    At this conditioning the kernel hyper-parameter gradients of the fp32 reference are pure noise (rel err >= 1
+    against fp64): the gate then only asks the CUDA path to be closer to fp64 than that -- it is at 2e-4 ... 7e-4."""
     inp, d = load_golden("c1_artificial2d")
     terms, g, nj = _run(inp)
     assert nj == int(d["njitter"]) == 5
     N = inp.xs.shape[0]
     elbo = (terms[0] + terms[3] + terms[2] - terms[1]).item()
     assert abs(-elbo / N - float(d["f64_loss"])) <= ELBO_TOL * abs(float(d["f64_loss"]))
-    for k in ("phi", "noise"):
-        assert O.rel_err(-g[k] / N, torch.from_numpy(d[f"f64_grad_{k}"])) <= 2e-4, k
+    assert_parity(_check_against_golden(inp, d, terms, g, nj), "C1")
 
 
 def test_max_jitter_raises_like_the_reference():
@@ -108,7 +103,7 @@ def test_tensor_path_matches_plain_fma_checker():
     t_rf, g_rf, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_REF_ALL)
     assert torch.allclose(t_tc, t_rf, rtol=1e-6, atol=1e-3)
     for k in g_tc:   # both carry the same split; only summation order differs
-        assert O.rel_err(g_tc[k], g_rf[k]) < (2 * HYPER_TOL if k in HYPER else 1e-3), k
+        assert O.rel_err(g_tc[k], g_rf[k]) < 1e-3, (k, O.rel_err(g_tc[k], g_rf[k]))
 
 
 def test_narrow_diagonal_mmas_agree_with_full_width():
@@ -125,11 +120,12 @@ def test_narrow_diagonal_mmas_agree_with_full_width():
             assert O.rel_err(g_n[k], g_f[k]) < (1e-3 if k in HYPER else 2e-5), (grid, k, O.rel_err(g_n[k], g_f[k]))
         # the single-CTA instantiations of the same policies (cta_group::1, one item per 128-row tile, natural item
         # order) read the same permuted fp16 ST planes; their work is cut differently (128-row tiles, other split of
-        # the observation range in dS), so fp32 partial sums differ more than between the two pair variants
+        # the observation range in dS) and their whitening is not segmented, so fp32 partial sums differ more than
+        # between the two pair variants
         t_s, g_s, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_SINGLE_CTA)
         assert torch.allclose(t_n, t_s, rtol=1e-7, atol=1e-3)
         for k in g_n:
-            assert O.rel_err(g_n[k], g_s[k]) < (1e-3 if k in HYPER else 2e-4), (grid, k, O.rel_err(g_n[k], g_s[k]))
+            assert O.rel_err(g_n[k], g_s[k]) < (1e-3 if k in HYPER else 5e-4), (grid, k, O.rel_err(g_n[k], g_s[k]))
 
 
 def test_fp16_forward_agrees_with_24bit_forward_and_falls_back_out_of_range():
@@ -150,6 +146,38 @@ def test_fp16_forward_agrees_with_24bit_forward_and_falls_back_out_of_range():
     elbo = (t2[0] + t2[3] + t2[2] - t2[1]).item()
     assert abs(elbo - o64["elbo"].item()) <= 1e-4 * abs(o64["elbo"].item())
     assert all(torch.isfinite(v).all() for v in g2.values())
+
+
+def test_marginal_variance_noise_and_the_segmented_forward():
+    """The marginal variance f_var is the *scale* of the guide's draw (sparse_gdrf.py:403-405), so its relative error
+    times f_var (~1e3 at these parameters) is the absolute error of mu: 2e-7 of noise there is 2e-4 in the gradients.
+    Read back in fp64 (gdrf_marginal_moments_f64) and compared with the fp64 oracle, element by element: the default
+    path stays below 2.5e-7 (the fp32 oracle -- the reference's arithmetic -- is at 1.6e-5), and the opt-in segmented
+    accumulation of T = W S_k (GDRF_FLAG_SEGMENTED_FWD: a fresh TMEM accumulator per 64-deep k-block, summed in
+    registers) is tighter still."""
+    from gdrf_b200 import _lib
+    from gdrf_b200.elbo import marginal_moments
+    inp = O.make_problem(N=8192, D=2, K=16, V=128, grid=[16, 16], kernel="rbf", seed=61)
+    with torch.no_grad():
+        o = O.elbo_terms(inp.to(torch.float64), twice=False)
+        o32 = O.elbo_terms(inp, twice=False)
+    c = lambda t: t.cuda()
+    std = {}
+    for name, fl in (("default", _lib.FLAG_CHOL_FP32_STATUS),
+                     ("segmented", _lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_SEGMENTED_FWD),
+                     ("unsegmented whitening", _lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_NO_SEGMENTS)):
+        floc, fvar = marginal_moments(c(inp.xs), c(inp.Z), c(inp.variance), c(inp.lengthscale), c(inp.u_loc),
+                                      c(inp.u_scale_tril), inp.kernel, inp.jitter, inp.maxjitter, flags=fl,
+                                      dtype=torch.float64)
+        e = (fvar.cpu() - o["f_var"]) / o["f_var"]
+        std[name] = e.std().item()
+        assert e.abs().max().item() < 3e-6, (name, e.abs().max().item())
+        assert O.rel_err(floc.cpu(), o["f_loc"]) < 5e-7, name
+    e32 = ((o32["f_var"].double() - o["f_var"]) / o["f_var"]).std().item()
+    print("relative noise of f_var:", {k: f"{v:.2e}" for k, v in std.items()}, f"fp32 oracle {e32:.2e}")
+    assert std["default"] < 2.5e-7 < e32
+    assert std["segmented"] < 0.8 * std["default"]
+    assert std["default"] <= 1.05 * std["unsegmented whitening"]
 
 
 def test_chunk_streaming_and_sharding_are_exact_properties():
@@ -256,11 +284,9 @@ def test_autograd_function_and_model_dropin():
 
 
 def test_c3_shape_20k_observations_against_fp64_and_fp32_oracles():
-    """BASELINE configs[2] shape (K=16, V=128, M=256, 2-D RBF) at N = 20 000.  Gate against the fp64 oracle;
-    the fp32 oracle (the reference's own arithmetic) is evaluated beside it: at this shape d ll / d mu is
-    O(counts ~ 700) and W = Kxz L^-T carries the 24-bit input rounding amplified by the whitening, so fp32
-    arithmetic itself sits at 1e-4 ... 3e-4 on u_loc / u_scale_tril.  The CUDA path must be within 1e-4 or no
-    worse than 2x that fp32 error; the ill-conditioned hyper-parameter sums within 1e-3."""
+    """BASELINE configs[2] shape (K=16, V=128, M=256, 2-D RBF) at N = 20 000, both oracles evaluated live.  At this
+    shape d ll / d mu is O(counts ~ 700) and the marginal variance (~1e3) is the *scale* of the guide's draw, so fp32
+    arithmetic itself sits at 3e-4 ... 1e-3 on u_loc / u_scale_tril / Z; the CUDA path is 4-5x closer to fp64."""
     inp = O.make_problem(N=20000, D=2, K=16, V=128, grid=[16, 16], kernel="rbf", seed=61)
     o64, g64 = O.loss_and_grads(inp.to(torch.float64), twice=False)
     o32, g32 = O.loss_and_grads(inp, twice=False)
@@ -268,12 +294,26 @@ def test_c3_shape_20k_observations_against_fp64_and_fp32_oracles():
     N = inp.xs.shape[0]
     elbo = (t[0] + t[3] + t[2] - t[1]).item()
     assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
-    errs = {k: O.rel_err(-g[k] / N, g64[k]) for k in O.GRAD_NAMES}
-    errs32 = {k: O.rel_err(g32[k], g64[k]) for k in O.GRAD_NAMES}
-    print("N=20000 ours", {k: f"{v:.1e}" for k, v in errs.items()})
-    print("N=20000 fp32 oracle", {k: f"{v:.1e}" for k, v in errs32.items()})
-    for k, e in errs.items():
-        assert e <= (1e-3 if k in HYPER else max(GRAD_TOL, 2.0 * errs32[k])), (k, e, errs32[k])
+    assert_parity(_three_way(g, N, g64, g32, O.GRAD_NAMES), "C3 shape, N=20000")
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_full_size_configurations_against_committed_oracle_fixtures(name):
+    """BASELINE configs[1..4] at (or, for C4 / C5, towards) their full sizes: C2 and C3 at N = 100 000, the headline C4
+    shape at N = 100 000, the C5 stress shape at N = 4 096.  The fp64 AND fp32 oracles were evaluated in observation
+    chunks by oracle/make_fullsize_fixtures.py and committed (tests/golden/full_*.npz: the four ELBO terms, every small
+    gradient in full, a seeded 100 000-entry sample of d/d u_scale_tril); the inputs are regenerated from the seed."""
+    inp, d = load_fullsize(name)
+    t, g, nj = _run(inp)
+    N = inp.xs.shape[0]
+    assert nj == int(d["f64_njitter"])
+    for i, k in enumerate(("lp_mu", "lq", "ll", "lp_phi")):
+        ref = float(d[f"f64_{k}"])
+        assert abs(t[i].item() - ref) <= ELBO_TOL * max(1.0, abs(ref)), (k, t[i].item(), ref)
+    e64 = float(d["f64_lp_mu"] + d["f64_lp_phi"] + d["f64_ll"] - d["f64_lq"])
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - e64) <= ELBO_TOL * abs(e64)
+    assert_parity(fullsize_errors(g, d, N), name)
 
 
 def test_evaluation_path_matches_oracle():
@@ -320,10 +360,7 @@ def test_c2_shape_matern32_1d_m1000():
     N = inp.xs.shape[0]
     elbo = (t[0] + t[3] + t[2] - t[1]).item()
     assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
-    for k in O.GRAD_NAMES:
-        err, err32 = O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k])
-        print("C2", k, f"{err:.1e} (fp32 oracle {err32:.1e})")
-        assert err <= (HYPER_TOL if k in HYPER else max(GRAD_TOL, 2.0 * err32)), (k, err, err32)
+    assert_parity(_three_way(g, N, g64, g32, O.GRAD_NAMES), "C2 shape, N=3000")
 
 
 def test_c5_shape_matern52_k64_v1024_m2048():
@@ -346,74 +383,6 @@ def test_c5_shape_matern52_k64_v1024_m2048():
         assert O.rel_err(ga[k] + gb[k], g[k]) < 1e-4, k
 
 
-def _oracle_chunked_f64(inp, rows):
-    """fp64 oracle over observation chunks (the ELBO and its gradient are sums over observations; the Dirichlet
-    prior is counted once): what makes full-size comparisons fit in host memory."""
-    N = inp.xs.shape[0]
-    terms = {k: 0.0 for k in ("lp_mu", "lq", "ll")}
-    grads, lp_phi = None, None
-    for lo in range(0, N, rows):
-        hi = min(N, lo + rows)
-        sub = O.OracleInputs(**{**inp.__dict__, "xs": inp.xs[lo:hi], "ws": inp.ws[lo:hi], "eps": inp.eps[:, lo:hi],
-                                "n_global": N})
-        o, g = O.loss_and_grads(sub.to(torch.float64), twice=False, include_prior=(lo == 0))
-        for k in terms:
-            terms[k] += o[k].item()
-        lp_phi = o["lp_phi"].item() if lp_phi is None else lp_phi
-        grads = g if grads is None else {k: grads[k] + g[k] for k in g}
-    elbo = terms["lp_mu"] + lp_phi + terms["ll"] - terms["lq"]
-    return elbo, grads
-
-
-def test_c3_full_size_100k_observations_against_the_fp64_oracle():
-    """BASELINE configs[2] at its FULL size (N = 100 000, K = 16, V = 128, M = 256): ELBO and every gradient against the
-    fp64 oracle evaluated in observation chunks.  Measured: ELBO 1e-8; variance 1e-5, noise 2e-6, phi 8e-8; u_loc
-    1.5e-4, u_scale_tril 1.7e-4, lengthscale 1.4e-4, Z 2.5e-4 -- the last four sit at the floor the fp32 reference
-    itself has against fp64 at this shape (1.3e-4 ... 3e-4, test_c3_shape_20k_...): the 24-bit rounding of Kxz amplified
-    by the whitening W = Kxz L^-T does not average out with N.  The unbiased noise of the 16-bit backward operands
-    does: the hyper-parameter gradients are 10x closer than at N ~ 1e3."""
-    inp = O.make_problem(N=100000, D=2, K=16, V=128, grid=[16, 16], kernel="rbf", seed=61)
-    elbo64, g64 = _oracle_chunked_f64(inp, 20000)
-    t, g, _ = _run(inp)
-    N = inp.xs.shape[0]
-    elbo = (t[0] + t[3] + t[2] - t[1]).item()
-    assert abs(elbo - elbo64) <= ELBO_TOL * abs(elbo64)
-    errs = {k: O.rel_err(-g[k] / N, g64[k]) for k in O.GRAD_NAMES}
-    print("C3 full size", {k: f"{v:.1e}" for k, v in errs.items()})
-    for k, e in errs.items():
-        assert e <= (5e-4 if k in HYPER else 2e-4), (k, e)
-
-
-def test_c4_shape_gradients_against_the_fp64_oracle():
-    """The headline shape (K = 32, V = 512, M = 1024, 3-D RBF) at N = 6000: every gradient against the fp64 oracle, with
-    the fp32 oracle (the reference's arithmetic) beside it."""
-    inp = O.make_problem(N=6000, D=3, K=32, V=512, grid=[16, 8, 8], kernel="rbf", seed=52)
-    elbo64, g64 = _oracle_chunked_f64(inp, 2000)
-    _, g32 = O.loss_and_grads(O.OracleInputs(**{**inp.__dict__, "xs": inp.xs[:2000], "ws": inp.ws[:2000],
-                                                  "eps": inp.eps[:, :2000], "n_global": 6000}), twice=False)
-    t, g, _ = _run(inp)
-    N = inp.xs.shape[0]
-    elbo = (t[0] + t[3] + t[2] - t[1]).item()
-    assert abs(elbo - elbo64) <= ELBO_TOL * abs(elbo64)
-    errs = {k: O.rel_err(-g[k] / N, g64[k]) for k in O.GRAD_NAMES}
-    print("C4 shape N=6000", {k: f"{v:.1e}" for k, v in errs.items()})
-    for k, e in errs.items():
-        assert e <= (HYPER_TOL if k in HYPER else 3e-4), (k, e)
-
-
-def test_c5_shape_gradients_against_the_fp64_oracle():
-    """The stress shape (K = 64, V = 1024, M = 2048, 3-D Matern-5/2) at N = 768: gradients against the fp64 oracle."""
-    inp = O.make_problem(N=768, D=3, K=64, V=1024, grid=[16, 16, 8], kernel="matern52", seed=82)
-    o64, g64 = O.loss_and_grads(inp.to(torch.float64), twice=False)
-    _, g32 = O.loss_and_grads(inp, twice=False)
-    t, g, _ = _run(inp)
-    N = inp.xs.shape[0]
-    for k in O.GRAD_NAMES:
-        err, err32 = O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k])
-        print("C5 shape", k, f"{err:.1e} (fp32 oracle {err32:.1e})")
-        assert err <= (2 * HYPER_TOL if k in HYPER else max(3e-4, 2.0 * err32)), (k, err, err32)
-
-
 def test_exponential_kernel_and_particles():
     """Exponential kernel (train_script.py:93-99 KERNEL_DICT) against the oracle; num_particles > 1 averages ELBOs."""
     inp = O.make_problem(N=1100, D=2, K=3, V=30, grid=[6, 6], kernel="exponential", seed=91)
@@ -423,9 +392,7 @@ def test_exponential_kernel_and_particles():
     N = inp.xs.shape[0]
     elbo = (t[0] + t[3] + t[2] - t[1]).item()
     assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item())
-    for k in O.GRAD_NAMES:
-        err, err32 = O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k])
-        assert err <= (HYPER_TOL if k in HYPER else max(GRAD_TOL, 2.0 * err32)), (k, err, err32)
+    assert_parity(_three_way(g, N, g64, g32, O.GRAD_NAMES), "exponential")
     from gdrf_b200 import Exponential, SparseMultinomialGDRF
     m = SparseMultinomialGDRF(num_observation_categories=30, num_topic_categories=3, world=[(0.0, 1.0)] * 2,
                               kernel=Exponential(2, variance=inp.variance, lengthscale=inp.lengthscale),
@@ -467,19 +434,14 @@ def test_shape_sweep_against_fp64_oracle(N, D, K, V, grid, kernel):
         assert abs(t[i].item() - o64[k].item()) <= ELBO_TOL * abs(o64[k].item()) + 1e-3, k
     elbo = (t[0] + t[3] + t[2] - t[1]).item()
     assert abs(elbo - o64["elbo"].item()) <= ELBO_TOL * abs(o64["elbo"].item()) + 1e-3
-    for k in ("u_loc", "u_scale_tril", "phi", "noise"):
-        ref = g64[k]
-        if ref.norm() < 1e-12:
+    names = O.GRAD_NAMES + (("scale_mixture",) if kernel == "rationalquadratic" else ())
+    rows = {}
+    for k in names:
+        if g64[k].norm() < 1e-12:          # e.g. one topic: the softmax is constant and d/d mu vanishes
             assert (-g[k] / N).norm() < 1e-6, k
             continue
-        err, err32 = O.rel_err(-g[k] / N, ref), O.rel_err(g32[k], ref)
-        assert err <= max(2 * GRAD_TOL, 2.0 * err32), (k, err, err32)
-    hyper = HYPER + (("scale_mixture",) if kernel == "rationalquadratic" else ())
-    rep = {k: (O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k]), g64[k].norm().item()) for k in hyper}
-    print("sweep", (N, D, K, V, grid, kernel), {k: (f"{a:.1e}", f"fp32 {b:.1e}", f"|g| {c:.1e}") for k, (a, b, c) in rep.items()})
-    for k, (err, err32, nrm) in rep.items():
-        if nrm > 1e-12:
-            assert err <= max(2 * HYPER_TOL, 2.0 * err32), (k, err, err32)
+        rows[k] = (O.rel_err(-g[k] / N, g64[k]), O.rel_err(g32[k], g64[k]), O.rel_err(-g[k] / N, g32[k]))
+    assert_parity(rows, f"sweep {(N, D, K, V, grid, kernel)}")
 
 
 def test_fused_svi_matches_autograd_plus_torch_adam():
