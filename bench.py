@@ -283,18 +283,224 @@ def run_reference(args, cfg_name, cfg):
     print(json.dumps(line), flush=True)
 
 
-def _flat_of(g):
-    """The gradient views returned by split_grad share one flat buffer; recover it for a single all-reduce."""
-    base = g["u_scale_tril"]
-    total = sum(v.numel() for v in g.values())
-    return base.reshape(-1).as_strided((total,), (1,))
-
-
 def _prod(xs):
     p = 1
     for x in xs:
         p *= x
     return p
+
+
+class Bench:
+    """One configuration on this rank's shard: data, parameters, and timed passes through the PUBLIC surface of the
+    package (gdrf_b200.elbo.elbo_value_and_grads / elbo_value_and_grads_from_host, gdrf_b200.SparseMultinomialGDRF +
+    FusedSVI); the only private import is the instrumentation (launch counter, CUDA-event records)."""
+
+    def __init__(self, name, cfg, dev, rank, world, flags_extra=0):
+        import torch
+        from gdrf_b200 import _lib
+        from gdrf_b200.svi import shard_bounds
+        self.torch, self._lib = torch, _lib
+        self.name, self.cfg, self.dev, self.rank, self.world = name, cfg, dev, rank, world
+        N = cfg["N"]
+        lo, hi = shard_bounds(N, rank, world)
+        if N >= GEN_CHUNK * world:      # keep shards on generation-chunk boundaries: any sharding sees the same data
+            per = (N // GEN_CHUNK) // world * GEN_CHUNK
+            lo, hi = rank * per, (N if rank == world - 1 else (rank + 1) * per)
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        self.xs, self.ws, self.eps = gen_shard(cfg, lo, hi, dev)
+        self.prm, self.jitter, self.maxjitter = params_for(cfg, dev)
+        self.M = _prod(cfg["grid"])
+        self.flags = _lib.FLAG_CHOL_FP32_STATUS | int(flags_extra)
+        self.chunk_rows = int(os.environ.get("GDRF_BENCH_CHUNK_ROWS", "0"))
+
+    # ---- one ELBO + gradient evaluation over the shard, then the step's one collective ----
+    def step(self, eps=None):
+        import torch.distributed as dist
+        from gdrf_b200.elbo import elbo_value_and_grads, flat_gradient, terms_from_flat
+        p = self.prm
+        terms, g, _ = elbo_value_and_grads(self.xs, self.ws, p["Z"], p["variance"], p["lengthscale"], p["u_loc"],
+                                           p["u_scale_tril"], p["noise"], p["phi"], p["beta"],
+                                           self.eps if eps is None else eps, kernel=self.cfg["kernel"],
+                                           jitter=self.jitter, maxjitter=self.maxjitter, n_global=self.cfg["N"],
+                                           include_prior=(self.rank == 0), flags=self.flags, chunk_rows=self.chunk_rows)
+        if self.world > 1:        # small parameter gradients + the four ELBO terms in ONE all-reduce
+            flat = flat_gradient(g)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            terms = terms_from_flat(flat)
+        return terms, g
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed + K timed calls of fn, CUDA events on the current stream, barrier + synchronize on both sides,
+        max over ranks.  Returns (ms per step, this rank's own ms per step, last result)."""
+        import torch.distributed as dist
+        torch = self.torch
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            a.record()
+            out = fn()
+            b.record()
+        self.barrier()
+        mine = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([mine], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, mine / steps, out
+
+    def profiled(self, steps, warmup):
+        """`timed(self.step)` with the library's per-launch CUDA-event records and launch counter switched on."""
+        lib, _lib = self._lib.load(), self._lib
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        lib.gdrf_profile_enable(1)
+        _lib.profile_read()
+        l0 = lib.gdrf_launch_count()
+        ms, mine, out = self.timed(self.step, steps, 0)
+        launches = lib.gdrf_launch_count() - l0
+        prof = _lib.profile_read()
+        lib.gdrf_profile_enable(0)
+        return ms, mine, out, prof, int(launches)
+
+    def e2e(self, steps):
+        """Same metric through the host-buffer entry point: observations in pinned HOST memory, sub-shards copied
+        H2D on a second stream while the previous one computes, the four terms read back to the host every step.  The
+        134 MB gradient stays on the device (it feeds an on-device optimiser: FusedSVI)."""
+        import torch.distributed as dist
+        from gdrf_b200.elbo import elbo_value_and_grads_from_host, flat_gradient, terms_from_flat
+        torch, p, cfg = self.torch, self.prm, self.cfg
+        hx, hw, he = (t_.cpu().pin_memory() for t_ in (self.xs, self.ws, self.eps))
+        h_terms = torch.empty(4, dtype=torch.float64).pin_memory()
+        n_sub = max(2, min(8, self.n_local // 60000))
+        per = ((self.n_local + n_sub - 1) // n_sub + 255) // 256 * 256
+        D, K, V = cfg["D"], cfg["K"], cfg["V"]
+        staging = [dict(xs=torch.empty(per, D, dtype=torch.float32, device=self.dev),
+                        ws=torch.empty(per, V, dtype=torch.int32, device=self.dev),
+                        eps=torch.empty(K, per, dtype=torch.float32, device=self.dev)) for _ in range(2)]
+
+        def one():
+            tm, g_, _ = elbo_value_and_grads_from_host(
+                hx, hw, he, p["Z"], p["variance"], p["lengthscale"], p["u_loc"], p["u_scale_tril"], p["noise"],
+                p["phi"], p["beta"], kernel=cfg["kernel"], jitter=self.jitter, maxjitter=self.maxjitter,
+                n_global=cfg["N"], include_prior=(self.rank == 0), flags=self.flags, n_sub=n_sub, staging=staging)
+            if self.world > 1:
+                flat = flat_gradient(g_)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                tm = terms_from_flat(flat)
+            h_terms.copy_(tm, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_terms
+
+        ms, _, _ = self.timed(one, steps, 1)
+        h2d = hx.numel() * 4 + hw.numel() * 4 + he.numel() * 4
+        return {"value": cfg["N"] / (ms * 1e-3), "unit": "observations/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 32, "ms_per_step": ms,
+                "note": "host buffers -> C ABI; the four ELBO terms come back to the host, the gradient stays on the "
+                        "device for the on-device optimiser"}
+
+    def svi_step(self, steps, warmup):
+        """What the reference's caller drives every epoch (train_script.py:365-371,467): module -> constraint transforms
+        -> ELBO + gradient -> all-reduce -> optimiser, through SparseMultinomialGDRF + FusedSVI only."""
+        import gdrf_b200
+        from gdrf_b200.kernels import KERNEL_DICT
+        torch, cfg, p = self.torch, self.cfg, self.prm
+        kern = KERNEL_DICT[cfg["kernel"]](cfg["D"], variance=p["variance"].cpu(), lengthscale=p["lengthscale"].cpu())
+        m = gdrf_b200.SparseMultinomialGDRF(
+            num_observation_categories=cfg["V"], num_topic_categories=cfg["K"], world=[(0.0, 1.0)] * cfg["D"],
+            kernel=kern, dirichlet_param=0.01, n_points=list(cfg["grid"]), inducing_init="grid", device=str(self.dev),
+            jitter=self.jitter, maxjitter=self.maxjitter, fixed_inducing_points=False)
+        with torch.no_grad():
+            m.u_loc_unconstrained.copy_(p["u_loc"])
+            m._word_topic_matrix_map_unconstrained.copy_(p["phi"].log())
+        m.seed_eps(2024)
+        svi = gdrf_b200.FusedSVI(m, lr=1e-3)
+        ms, _, loss = self.timed(lambda: svi.step(self.xs, self.ws, n_global=cfg["N"]), steps, warmup)
+        return {"value": cfg["N"] / (ms * 1e-3), "unit": "observations/s", "ms_per_step": ms, "steps": steps,
+                "loss_after": loss, "path": "SparseMultinomialGDRF + FusedSVI.step (constrain -> ELBO+grad -> "
+                                            "all-reduce -> Adam), eps drawn on the device"}
+
+
+def other_config_record(name, cfg, dev, peak_info):
+    """One of the other BASELINE configurations on one GPU: value, dominant kernel and its roofline fraction."""
+    b = Bench(name, cfg, dev, 0, 1)
+    ms, mine, (terms, _), prof, launches = b.profiled(3, 3)
+    roof = roofline_block(prof, 3, b.n_local, mine, b.M, cfg["K"], b.flags, b._lib) or {}
+    t = terms.cpu()
+    rec = {"workload": f"{name}: N={cfg['N']} D={cfg['D']} K={cfg['K']} V={cfg['V']} M={b.M} {cfg['kernel']}",
+           "value": cfg["N"] / (ms * 1e-3), "unit": "observations/s", "ms_per_step": ms,
+           "loss": -float(t[0] + t[3] + t[2] - t[1]) / cfg["N"], "gpu_launches_per_step": launches // 3,
+           "dominant_kernel": roof.get("kernel"), "roofline_frac": roof.get("frac"),
+           "issued_frac": (roof.get("issued") or {}).get("frac"),
+           "alg_tflops_step": algorithmic_flops_per_obs(b.M, cfg["K"], cfg["V"]) * cfg["N"] / (ms * 1e-3) / 1e12}
+    if "error" in roof:
+        rec["roofline_error"] = roof["error"]
+    del b
+    return rec
+
+
+def c1_record(dev):
+    """BASELINE configs[0]: the shipped data/data_2d_artificial.csv (tests/golden/c1_artificial2d.npz holds it as
+    train_script.py:251-273 reads it) at train()'s defaults: K=5, 25 x 25 inducing grid, RBF, jitter 1e-8 with the
+    reference's escalation (lands on level 5)."""
+    import numpy as np
+    import torch
+    from gdrf_b200.elbo import elbo_value_and_grads
+    from gdrf_b200.models import host_jittercholesky
+    from gdrf_b200.kernels import KERNEL_DICT
+    d = np.load(os.path.join(ROOT, "tests", "golden", "c1_artificial2d.npz"))
+    t = lambda k: torch.from_numpy(np.asarray(d[k])).to(dev)
+    Z, var, ls = t("Z").float(), t("variance").float(), t("lengthscale").float()
+    K, M = d["u_loc"].shape
+    jitter, maxjitter = float(d["jitter"]), int(d["maxjitter"])
+    kern = KERNEL_DICT["rbf"](2, variance=var.cpu(), lengthscale=ls.cpu())
+    with torch.no_grad():
+        L = host_jittercholesky(kern(Z.cpu()).contiguous(), M, jitter, maxjitter)      # constructor init, sparse_gdrf.py:100-110
+    S = L.float().expand(K, M, M).contiguous().to(dev)
+    args = (t("xs").float(), t("ws").int(), Z, var, ls, t("u_loc").float(), S, t("noise").float(), t("phi").float(),
+            t("beta").float(), t("eps").float())
+    N = args[0].shape[0]
+
+    def one():
+        return elbo_value_and_grads(*args, kernel="rbf", jitter=jitter, maxjitter=maxjitter)
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in ev:
+        a.record()
+        terms, _, nj = one()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    tt = terms.cpu()
+    return {"workload": f"C1: data/data_2d_artificial.csv N={N} D=2 K={K} V={args[1].shape[1]} M={M} rbf, train() defaults",
+            "value": N / (ms * 1e-3), "unit": "observations/s", "ms_per_step": ms, "njitter": int(nj),
+            "loss": -float(tt[0] + tt[3] + tt[2] - tt[1]) / N,
+            "note": "latency-bound: 6 jitter escalations (6 prologues + 6 status read-backs) per step, as jittercholesky does"}
+
+
+def particles_record(dev):
+    """Shared-contraction particles at the C2 shape (scripts/mvco.py:136 runs num_particles=10): one particle vs ten."""
+    import torch
+    cfg = dict(CONFIGS["C2"])
+    b = Bench("C2", cfg, dev, 0, 1)
+    e10 = torch.randn(10, cfg["K"], b.n_local, device=dev, generator=torch.Generator(device=dev).manual_seed(77))
+    ms1, _, _ = b.timed(lambda: b.step(), 5, 3)
+    ms10, _, _ = b.timed(lambda: b.step(eps=e10), 5, 3)
+    del b
+    return {"workload": "C2 shape, N=100000", "ms_per_step_1_particle": ms1, "ms_per_step_10_particles": ms10,
+            "ratio": ms10 / ms1, "note": "one prologue and one pass of every contraction whatever the particle count; "
+                                         "the per-observation chain runs once per particle"}
 
 
 def main():
@@ -307,6 +513,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the number of observations (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip svi_step / other_configs / particles")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.n:
@@ -317,9 +524,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gdrf_b200 import _lib
-    from gdrf_b200.elbo import _Call
-    from gdrf_b200.svi import shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -332,117 +536,60 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
+    # C5 is BASELINE's 8-GPU weak-scaling stress config (1 M observations per GPU)
+    scaling = "weak" if args.config == "C5" else "strong"
+    if args.config == "C5" and not args.n:
+        cfg["N"] = 1_000_000 * world
     N, D, K, V = cfg["N"], cfg["D"], cfg["K"], cfg["V"]
-    M = _prod(cfg["grid"])
-    lo, hi = shard_bounds(N, rank, world)
-    if N >= GEN_CHUNK:      # keep shards on generation-chunk boundaries
-        per = (N // GEN_CHUNK) // world * GEN_CHUNK
-        lo, hi = rank * per, (N if rank == world - 1 else (rank + 1) * per)
-    xs, ws, eps = gen_shard(cfg, lo, hi, dev)
-    n_local = hi - lo
-    prm, jitter, maxjitter = params_for(cfg, dev)
-    lib = _lib.load()
-    flags = _lib.FLAG_CHOL_FP32_STATUS | (_lib.FLAG_INCLUDE_PRIOR if rank == 0 else 0)
-    flags |= int(os.environ.get("GDRF_BENCH_FLAGS", "0"))     # A/B switches (e.g. 32 = single-CTA contractions)
-
-    def one_step(x, w, e):
-        call = _Call(x, w, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],
-                     prm["noise"], prm["phi"], prm["beta"], e, _lib.KERNEL_IDS[cfg["kernel"]], 0, flags,
-                     int(os.environ.get("GDRF_BENCH_CHUNK_ROWS", "0")))
-        call.prologue(jitter, maxjitter)
-        terms, grad = call.step(True)
-        if world > 1:                      # the one collective of the step: small parameter gradients + ELBO terms
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-            dist.all_reduce(terms, op=dist.ReduceOp.SUM)
-        return terms, grad
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    b = Bench(args.config, cfg, dev, rank, world, int(os.environ.get("GDRF_BENCH_FLAGS", "0")))
+    M = b.M
 
     # ---------------- device-resident throughput ("value") ----------------
     for _ in range(warmup):
-        terms, grad = one_step(xs, ws, eps)
-    barrier()
-    lib.gdrf_profile_enable(1)
-    _lib.profile_read()
-    launches0 = lib.gdrf_launch_count()
+        b.step()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    barrier()
     t_wall = time.perf_counter()
-    for a, b in ev:
-        a.record()
-        terms, grad = one_step(xs, ws, eps)
-        b.record()
-    barrier()
+    ms_per_step, ms_mine, (terms, _), prof, launches = b.profiled(steps, 0)
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
-    launches = lib.gdrf_launch_count() - launches0
-    prof = _lib.profile_read()
-    lib.gdrf_profile_enable(0)
-    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
-    tmax = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_per_step = tmax.item() / steps
     value = N / (ms_per_step * 1e-3)
     t = terms.cpu()
     loss = -float(t[0] + t[3] + t[2] - t[1]) / N
 
-    # ---------------- end-to-end through the C ABI with host buffers ("e2e") ----------------
-    e2e = None
-    if not args.no_e2e:
-        hx, hw, he = (t_.cpu().pin_memory() for t_ in (xs, ws, eps))
-        h_terms = torch.empty(4, dtype=torch.float64).pin_memory()
-
-        from gdrf_b200.elbo import elbo_value_and_grads_from_host
-        n_sub = max(2, min(8, n_local // 60000))
-        per = ((n_local + n_sub - 1) // n_sub + 255) // 256 * 256
-        staging = [dict(xs=torch.empty(per, D, dtype=torch.float32, device=dev),
-                        ws=torch.empty(per, V, dtype=torch.int32, device=dev),
-                        eps=torch.empty(K, per, dtype=torch.float32, device=dev)) for _ in range(2)]
-
-
-        def e2e_step():
-            # public host-buffer API: sub-shards are copied H2D on a second stream while the previous one computes
-            tm, g_, _ = elbo_value_and_grads_from_host(
-                hx, hw, he, prm["Z"], prm["variance"], prm["lengthscale"], prm["u_loc"], prm["u_scale_tril"],
-                prm["noise"], prm["phi"], prm["beta"], kernel=cfg["kernel"], jitter=jitter, maxjitter=maxjitter,
-                n_global=N, include_prior=(rank == 0), flags=flags & ~_lib.FLAG_INCLUDE_PRIOR, n_sub=n_sub,
-                staging=staging)
-            if world > 1:
-                dist.all_reduce(_flat_of(g_), op=dist.ReduceOp.SUM)
-                dist.all_reduce(tm, op=dist.ReduceOp.SUM)
-            h_terms.copy_(tm, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return h_terms
-
-        e2e_step()
-        barrier()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for a, b in ev2:
-            a.record()
-            e2e_step()
-            b.record()
-        barrier()
-        ms2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        h2d = hx.numel() * 4 + hw.numel() * 4 + he.numel() * 4
-        e2e = {"value": N / (ms2.item() / steps * 1e-3), "unit": "observations/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32, "ms_per_step": ms2.item() / steps}
+    e2e = None if args.no_e2e else b.e2e(steps)
+    extras = not args.no_extras and not args.n
+    svi = b.svi_step(min(steps, 5), 2) if extras else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel ----------------
-    roofline = roofline_block(prof, steps, n_local, ms_dev / steps, M, K, flags, _lib)
+    roofline = roofline_block(prof, steps, b.n_local, ms_mine, M, K, b.flags, b._lib)
+    n_local, flags = b.n_local, b.flags
+    del b
+    torch.cuda.empty_cache()
+
+    other, particles = None, None
+    if extras and world == 1 and args.config == "C4":
+        from gdrf_b200.elbo import release_workspaces
+        other = {}
+        for name, n_override in (("C2", None), ("C3", None), ("C5", 131072)):
+            release_workspaces()
+            torch.cuda.empty_cache()
+            c = dict(CONFIGS[name])
+            if n_override:
+                c["N"] = n_override
+            other[name] = other_config_record(name, c, dev, None)
+            if n_override:
+                other[name]["workload"] += " (shape of C5 at a bounded N; throughput does not depend on N beyond the M x M prologue)"
+        other["C1"] = c1_record(dev)
+        release_workspaces()
+        torch.cuda.empty_cache()
+        particles = particles_record(dev)
+        release_workspaces()
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -451,14 +598,18 @@ def main():
         cpu_baseline.pop("ms_per_step", None)
 
     line = {"metric": METRIC, "value": value, "unit": "observations/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (error-compensated 16-bit-plane tcgen05 products: fp16x3 forward, bf16x3 backward, bf16x6 whitening W = Kxz L^-T; f32 accumulate; f64 per-observation chain and MxM prologue)",
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None,
+            "dtype": "f32 (error-compensated 16-bit-plane tcgen05 products: fp16x3 forward and backward (22-bit operands), "
+                     "bf16x6 whitening W = Kxz L^-T (24-bit); f32 accumulate; f64 per-observation chain and MxM prologue)",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: N={N} D={D} K={K} V={V} M={M} {cfg['kernel']}, sharded by "
                                    f"observation over {world} GPU(s)", "l2": "inputs (ws) exceed L2 every step",
-                       "parallelism": f"obs-shard x{world}", "jitter": jitter},
+                       "parallelism": f"obs-shard x{world}", "jitter": 1e-4,
+                       "api": "gdrf_b200.elbo.elbo_value_and_grads (public); one all-reduce of gradient + terms"},
             "loss": loss, "wall_s_timed": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "svi_step": svi, "other_configs": other,
+            "particles": particles,
             "alg_tflops_step": algorithmic_flops_per_obs(M, K, V) * N / (ms_per_step * 1e-3) / 1e12}
     print(json.dumps(line), flush=True)
     if world > 1:

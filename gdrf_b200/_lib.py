@@ -27,12 +27,14 @@ FLAG_REF_ALL = 0x3F << 8
 FLAG_FULL_WIDTH = 1 << 14
 FLAG_NO_SEGMENTS = 1 << 15
 FLAG_SEGMENTED_FWD = 1 << 16
+FLAG_TERMS_IN_GRAD = 1 << 17
+TERMS_TAIL = 8
 
 
 class Shape(ctypes.Structure):
     _fields_ = [("n_local", c_int64), ("n_offset", c_int64), ("n_eps", c_int64), ("d", c_int32),
                 ("m", c_int32), ("k", c_int32), ("v", c_int32), ("kernel_id", c_int32),
-                ("ls_dim", c_int32), ("chunk_rows", c_int32), ("flags", c_int32)]
+                ("ls_dim", c_int32), ("chunk_rows", c_int32), ("flags", c_int32), ("n_particles", c_int32)]
 
 
 class Inputs(ctypes.Structure):

@@ -95,6 +95,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   if (s->ls_dim != 1 && s->ls_dim != s->d) return fail(1, "ls_dim must be 1 or d%s");
   if (s->kernel_id < 0 || s->kernel_id > 4) return fail(1, "unknown kernel_id%s");
   if (s->chunk_rows < 0 || (s->chunk_rows % 256) != 0) return fail(1, "chunk_rows must be a multiple of 256%s");
+  if (s->n_particles < 0 || s->n_particles > 1024) return fail(1, "n_particles must be in [0, 1024]%s");
   p.D = s->d; p.M = s->m; p.K = s->k; p.V = s->v;
   p.Mp = (int)round_up_ll(s->m, 256);
   p.MB = p.Mp / 64; p.JT = p.Mp / 256; p.MT = p.Mp / 128;
@@ -192,7 +193,8 @@ int check_device() {
 }
 
 template <int KPW, int VJ>
-int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st) {
+int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st,
+                      double inv_p) {
   const int VC = VJ * 32;
   const size_t smem = sizeof(float) * lk_smem_floats(p.K, VC);
   CU(cudaFuncSetAttribute(k_likelihood<KPW, VJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -200,15 +202,17 @@ int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0
   const int grid = ntiles < sms ? ntiles : sms;
   k_likelihood<KPW, VJ><<<grid, LK_THREADS, smem, st>>>(
       nc, (int)p.ncp, p.K, p.V, in->ws + n0 * p.V, at<float>(ws, p.theta), at<float>(ws, p.srow), in->phi,
-      at<float>(ws, p.g1), at<float>(ws, p.arow), at<float>(ws, p.cnt), at<double>(ws, p.dphi), at<double>(ws, p.acc));
+      at<float>(ws, p.g1), at<float>(ws, p.arow), at<float>(ws, p.cnt), at<double>(ws, p.dphi), at<double>(ws, p.acc),
+      inv_p);
   LAUNCH_CHECK();
   return 0;
 }
 
-int dispatch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st) {
+int dispatch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st,
+                        double inv_p) {
   const int kpw = (p.K + 15) / 16;
   const int vj_need = (p.V + 31) / 32;
-#define LK(KPW, VJ) return launch_likelihood<KPW, VJ>(p, nc, in, n0, ws, sms, st)
+#define LK(KPW, VJ) return launch_likelihood<KPW, VJ>(p, nc, in, n0, ws, sms, st, inv_p)
   if (kpw <= 1) { if (vj_need <= 4) LK(1, 4); if (vj_need <= 8) LK(1, 8); LK(1, 16); }
   if (kpw <= 2) { if (vj_need <= 4) LK(2, 4); if (vj_need <= 8) LK(2, 8); LK(2, 16); }
   if (kpw <= 4) { if (vj_need <= 4) LK(4, 4); if (vj_need <= 8) LK(4, 8); LK(4, 16); }
@@ -356,12 +360,20 @@ __global__ void k_merge_status(const unsigned* __restrict__ ps, const float* __r
   if (*status == 0 && !ok) *status = -1;
 }
 
-__global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms) {
+// terms as fp64, and -- when the gradient buffer is there -- once more behind the gradient as four (hi, lo) fp32 pairs,
+// so that ONE fp32 all-reduce of the flat buffer carries the loss as well (hi + lo restores the value to fp32 accuracy of
+// the summed hi parts: the reference's loss is an fp32 number)
+__global__ void k_copy_terms(const double* __restrict__ acc, double* __restrict__ terms, float* __restrict__ tail) {
   if (threadIdx.x == 0) {
-    terms[0] = acc[ACC_LP_MU];
-    terms[1] = acc[ACC_LQ];
-    terms[2] = acc[ACC_LL];
-    terms[3] = acc[ACC_LP_PHI];
+    const double t[4] = {acc[ACC_LP_MU], acc[ACC_LQ], acc[ACC_LL], acc[ACC_LP_PHI]};
+    for (int i = 0; i < 4; ++i) {
+      terms[i] = t[i];
+      if (tail) {
+        const float hi = (float)t[i];
+        tail[2 * i] = hi;
+        tail[2 * i + 1] = (float)(t[i] - (double)hi);
+      }
+    }
   }
 }
 
@@ -644,6 +656,8 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   const Hyper hp = make_hyper(s, in);
   const int K = p.K, M = p.M, Mp = p.Mp;
 
+  const int P = s->n_particles > 1 ? s->n_particles : 1;
+  const double inv_p = 1.0 / P;
   const bool cont = (s->flags & GDRF_FLAG_CONTINUE) != 0;   // accumulators carry over from the previous call
   const bool partial = (s->flags & GDRF_FLAG_PARTIAL) != 0; // more sub-shards follow: skip the per-step epilogue
   if (!cont) {
@@ -700,25 +714,30 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
     if (int e = chunk_forward(s, in, p, ws, n0, nc, RT, true, want_grad, sms, st)) return e;
+    // the per-observation chain once per particle (draw of the guide): the marginal moments above do not depend on the
+    // draw; the ELBO terms and the backward weights (g_loc, g2, gv0) accumulate their mean over the particles
+    for (int pi = 0; pi < P; ++pi) {
+      const float* eps_p = in->eps + (long long)pi * K * s->n_eps;
 #define GDRF_OBS_PREPARE(KQ)                                                                                   \
   k_obs_prepare<KQ><<<(nc + 31) / 32, 256, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps,                \
                                                     at<double>(ws, p.floc), at<double>(ws, p.q), at<double>(ws, p.wsq), \
-                                                    in->eps, hp, at<float>(ws, p.phisum), at<float>(ws, p.fvar),   \
-                                                    at<float>(ws, p.theta), at<float>(ws, p.srow), acc)
-    GDRF_DISPATCH_KQ(K, GDRF_OBS_PREPARE);
+                                                    eps_p, hp, at<float>(ws, p.phisum), at<float>(ws, p.fvar),     \
+                                                    at<float>(ws, p.theta), at<float>(ws, p.srow), acc, inv_p)
+      GDRF_DISPATCH_KQ(K, GDRF_OBS_PREPARE);
 #undef GDRF_OBS_PREPARE
-    LAUNCH_CHECK();
-    if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st)) return e;
+      LAUNCH_CHECK();
+      if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st, inv_p)) return e;
 #define GDRF_OBS_FINALIZE(KQ)                                                                                  \
   k_obs_finalize<KQ><<<RT * 4, 256, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta), \
                                              at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),    \
                                              at<float>(ws, p.cnt), at<float>(ws, p.fvar), at<double>(ws, p.wsq),   \
-                                             in->eps, hp, at<float>(ws, p.phisum), at<float>(ws, p.g_loc),         \
+                                             eps_p, hp, at<float>(ws, p.phisum), at<float>(ws, p.g_loc),           \
                                              at<float>(ws, p.g2), at<float>(ws, p.gv0), at<double>(ws, p.ck), acc, \
-                                             RT * 128, cs)
-    GDRF_DISPATCH_KQ(K, GDRF_OBS_FINALIZE);
+                                             RT * 128, cs, (float)inv_p, pi == 0, pi == P - 1)
+      GDRF_DISPATCH_KQ(K, GDRF_OBS_FINALIZE);
 #undef GDRF_OBS_FINALIZE
-    LAUNCH_CHECK();
+      LAUNCH_CHECK();
+    }
     if (!want_grad) continue;
     {
       ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
@@ -845,7 +864,13 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
                                                            at<double>(ws, p.dphi), at<double>(ws, p.dz), out->grad);
     LAUNCH_CHECK();
   }
-  k_copy_terms<<<1, 32, 0, st>>>(acc, out->terms);
+  float* tail = nullptr;
+  if (want_grad && (s->flags & GDRF_FLAG_TERMS_IN_GRAD)) {
+    int64_t ge = 0;
+    gdrf_grad_elems(s, &ge);
+    tail = out->grad + ge;
+  }
+  k_copy_terms<<<1, 32, 0, st>>>(acc, out->terms, tail);
   LAUNCH_CHECK();
   return 0;
 }

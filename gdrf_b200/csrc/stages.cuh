@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(256) k_obs_prepare(int nc, int ncp, int K, lon
                                                      const double* __restrict__ wsq, const float* __restrict__ eps,
                                                      Hyper hp, const float* __restrict__ phisum,
                                                      float* __restrict__ fvar, float* __restrict__ theta,
-                                                     float* __restrict__ srow, double* __restrict__ acc) {
+                                                     float* __restrict__ srow, double* __restrict__ acc,
+                                                     double inv_p) {
   // fp64 throughout: mu carries f_var * eps with f_var = O(variance), and d ll / d mu = O(counts), so fp32
   // rounding of mu (1e-5 absolute) alone would cost 1e-4 ... 1e-3 relative in the gradients.
   __shared__ double scratch[32];
@@ -319,9 +320,9 @@ __global__ void __launch_bounds__(256) k_obs_prepare(int nc, int ncp, int K, lon
   if (live && sub == 0) srow[n] = (float)sr;
   lq = block_sum(lq, scratch);
   lp = block_sum(lp, scratch);
-  if (threadIdx.x == 0) {
-    atomicAdd(&acc[ACC_LQ], lq);
-    atomicAdd(&acc[ACC_LP_MU], lp);
+  if (threadIdx.x == 0) {      // inv_p = 1 / particles: the ELBO is the mean over the guide's draws
+    atomicAdd(&acc[ACC_LQ], lq * inv_p);
+    atomicAdd(&acc[ACC_LP_MU], lp * inv_p);
   }
 }
 
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
     k_likelihood(int nc, int ncp, int K, int V, const int* __restrict__ ws, const float* __restrict__ theta,
                  const float* __restrict__ srow, const float* __restrict__ phi, float* __restrict__ g1 /*[ncp][K]*/,
                  float* __restrict__ arow, float* __restrict__ cnt, double* __restrict__ dphi_acc /*[K][V]*/,
-                 double* __restrict__ acc) {
+                 double* __restrict__ acc, double inv_p) {
   constexpr int VC = VJ * 32;
   extern __shared__ __align__(16) float lk_smem[];
   float* phis = lk_smem;                                    // [K][VC + 1]
@@ -522,13 +523,13 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < VJ; ++j) {
           const int v = v0 + lane + 32 * j;
-          if (v < V && dacc[a][j] != 0.f) atomicAdd(&dphi_acc[(long long)k * V + v], (double)dacc[a][j]);
+          if (v < V && dacc[a][j] != 0.f) atomicAdd(&dphi_acc[(long long)k * V + v], (double)dacc[a][j] * inv_p);
         }
       }
     }
   }
   ll_local = block_sum(ll_local, scratch);
-  if (threadIdx.x == 0) atomicAdd(&acc[ACC_LL], ll_local);
+  if (threadIdx.x == 0) atomicAdd(&acc[ACC_LL], ll_local * inv_p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -539,6 +540,9 @@ __global__ void __launch_bounds__(LK_THREADS, 1)
 //   dELBO/dnoise = -1/sp + eps^2 f_var^2 / sp^3
 //   gv0_n = sum_k dELBO/df_var  where the clamp var0 = max(variance - |W_n|^2, 0) is inactive
 // Outputs: g_loc = g_mu, g2 = 2 dELBO/df_var (row scale of R), gv0; padding rows are zeroed.
+// Particles (Trace_ELBO(num_particles=P, vectorize_particles=True), train_script.py:330-335): the marginal moments do
+// not depend on the draw and every contraction of the backward is linear in (g_loc, g2, gv0), so the P passes of the
+// per-observation chain accumulate the MEAN of those weights here (first / last / inv_p) and the contractions run once.
 // 8 lanes per observation (lane j owns topics j, j + 8, ...; K <= 8 KQ), 256 threads = 32 observations.
 // ---------------------------------------------------------------------------------------------
 template <int KQ>
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
                                                       float* __restrict__ g_loc, float* __restrict__ g2,
                                                       float* __restrict__ gv0, double* __restrict__ ck,
                                                       double* __restrict__ acc, int npad,
-                                                      unsigned* __restrict__ cs) {
+                                                      unsigned* __restrict__ cs, float inv_p, int first, int last) {
   __shared__ double scratch[32];
   __shared__ float cks[8 * KQ];
   __shared__ unsigned smax[3];
@@ -597,27 +601,30 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
         dn += -isp + e2 * fv * fv * isp * isp * isp;
         gsum += gv;
         // c_k = sum_n theta[n][k] A_n / s_n  (the renormalisation term of d ll / d phi)
-        atomicAdd(&cks[k], th[i] * ratio);
+        atomicAdd(&cks[k], inv_p * th[i] * ratio);
       }
-      g_loc[o] = gm;            // padding rows are zeroed
-      g2[o] = 2.f * gv;
-      mx_g2 = fmaxf(mx_g2, fabsf(2.f * gv));
-      mx_gl = fmaxf(mx_gl, fabsf(gm));
+      const float gl_new = (first ? 0.f : g_loc[o]) + inv_p * gm;      // padding rows are zeroed
+      const float g2_new = (first ? 0.f : g2[o]) + inv_p * 2.f * gv;
+      g_loc[o] = gl_new;
+      g2[o] = g2_new;
+      mx_g2 = fmaxf(mx_g2, fabsf(g2_new));
+      mx_gl = fmaxf(mx_gl, fabsf(gl_new));
     }
   }
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-  dnoise = dn;
+  dnoise = (double)dn * (double)inv_p;
   if (sub == 0 && n < npad) {
     float g0 = 0.f;
     if (live) {
       const bool clamp_open = ((double)var - wsq[n]) >= 0.0;
       g0 = clamp_open ? gsum : 0.f;
-      dvar = g0;
-      llc = lgamma((double)cnt[n] + 1.0);
+      dvar = (double)g0 * (double)inv_p;
+      llc = lgamma((double)cnt[n] + 1.0) * (double)inv_p;
     }
-    gv0[n] = g0;
-    if (g0 != 0.f) atomicMax(&smax[2], __float_as_uint(fabsf(g0)));
+    const float g0_new = (first ? 0.f : gv0[n]) + inv_p * g0;
+    gv0[n] = g0_new;
+    if (g0_new != 0.f) atomicMax(&smax[2], __float_as_uint(fabsf(g0_new)));
   }
   // chunk-wide maxima of the backward weights: they size the power-of-two scales of the fp16 operand planes
 #pragma unroll
@@ -630,7 +637,7 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
     if (mx_gl > 0.f) atomicMax(&smax[1], __float_as_uint(mx_gl));
   }
   __syncthreads();
-  if (threadIdx.x < 3 && smax[threadIdx.x] != 0u) atomicMax(cs + CS_G2MAX + threadIdx.x, smax[threadIdx.x]);
+  if (last && threadIdx.x < 3 && smax[threadIdx.x] != 0u) atomicMax(cs + CS_G2MAX + threadIdx.x, smax[threadIdx.x]);
   for (int k = threadIdx.x; k < K; k += 256)
     if (cks[k] != 0.f) atomicAdd(&ck[k], (double)cks[k]);
   dnoise = block_sum(dnoise, scratch);

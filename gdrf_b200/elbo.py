@@ -7,7 +7,10 @@ conditional, the reparameterised draw of ``mu``, both Normal terms, the Dirichle
 topic softmax, the theta-phi mixture and the multinomial log-likelihood -- and their gradients.
 
 Inputs are the *constrained* parameter values; autograd chains through the constraint transforms
-outside the op.  The value returned is ELBO / n_global for the observations handed in (this rank's
+outside the op.  ``eps`` may be ``[P, K, N]``: P draws of the guide per observation (``Trace_ELBO(num_particles=P,
+vectorize_particles=True)``, ``train_script.py:330-335``); value and gradient are then the mean over the particles,
+computed with ONE pass of the contractions (the marginal moments do not depend on the draw and the backward
+contractions are linear in the per-observation weights) and P passes of the per-observation chain.  The value returned is ELBO / n_global for the observations handed in (this rank's
 shard); the reference's loss (``poutine.scale(1/N)``, ``train_script.py:365``) is its negative.
 """
 from __future__ import annotations
@@ -32,7 +35,9 @@ def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.index or 0, 0)
+    """One workspace per (device, stream): the C ABI is re-entrant per (workspace, stream) (include/gdrf_b200.h), so two
+    modules driven on two streams of one device must not share scratch memory."""
+    key = (device.index or 0, int(torch.cuda.current_stream(device).cuda_stream))
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         _WORKSPACES.pop(key, None)
@@ -79,8 +84,9 @@ class _Call:
             raise ValueError("u_loc must be [K, M] and u_scale_tril [K, M, M]")
         if phi.shape != (K, V) or beta.shape != (K, V):
             raise ValueError("phi and beta must be [K, V]")
-        if eps.dim() != 2 or eps.shape[0] != K or eps.shape[1] < n_offset + N:
-            raise ValueError("eps must be [K, >= n_offset + N]")
+        if eps.dim() not in (2, 3) or eps.shape[-2] != K or eps.shape[-1] < n_offset + N:
+            raise ValueError("eps must be [K, >= n_offset + N] (or [particles, K, >= n_offset + N])")
+        n_particles = int(eps.shape[0]) if eps.dim() == 3 else 1
         ls = lengthscale.reshape(-1)
         if ls.numel() not in (1, D):
             raise ValueError("lengthscale must have 1 or D entries")
@@ -95,9 +101,9 @@ class _Call:
             raise ValueError("the RationalQuadratic kernel needs its scale_mixture parameter")
         if self.t["ws"].device != dev:
             raise ValueError("ws must live on the same device as xs")
-        self.shape = _lib.Shape(n_local=N, n_offset=int(n_offset), n_eps=int(eps.shape[1]), d=D, m=M, k=K, v=V,
+        self.shape = _lib.Shape(n_local=N, n_offset=int(n_offset), n_eps=int(eps.shape[-1]), d=D, m=M, k=K, v=V,
                                 kernel_id=int(kernel_id), ls_dim=int(ls.numel()), chunk_rows=int(chunk_rows),
-                                flags=int(flags))
+                                flags=int(flags), n_particles=n_particles)
         self.inputs = _lib.Inputs(**{k: (None if v is None else v.data_ptr()) for k, v in self.t.items()})
         self.ws_bytes = _lib.workspace_bytes(self.shape)
         self.workspace = _workspace(dev, self.ws_bytes)
@@ -126,11 +132,14 @@ class _Call:
         lib = _lib.load()
         if terms is None:
             terms = torch.empty(4, dtype=torch.float64, device=self.device)
-        flags = (self.shape.flags & ~_lib.FLAG_WANT_GRAD) | int(extra_flags)
+        flags = (self.shape.flags & ~(_lib.FLAG_WANT_GRAD | _lib.FLAG_TERMS_IN_GRAD)) | int(extra_flags)
         if want_grad:
             flags |= _lib.FLAG_WANT_GRAD
-            if grad is None:
-                grad = torch.empty(_lib.grad_elems(self.shape), dtype=torch.float32, device=self.device)
+            ge = _lib.grad_elems(self.shape)
+            if grad is None:      # 8 floats of tail: the terms ride behind the gradient (one all-reduce carries both)
+                grad = torch.empty(ge + _lib.TERMS_TAIL, dtype=torch.float32, device=self.device)
+            if grad.numel() >= ge + _lib.TERMS_TAIL:
+                flags |= _lib.FLAG_TERMS_IN_GRAD
         self.shape.flags = flags
         out = _lib.Outputs(terms=terms.data_ptr(), grad=grad.data_ptr() if grad is not None else None)
         _lib.check(lib.gdrf_elbo_step(ctypes.byref(self.shape), ctypes.byref(self.inputs), ctypes.byref(out),
@@ -140,13 +149,13 @@ class _Call:
 
 def split_grad(flat: torch.Tensor, K: int, M: int, V: int, D: int, ls_dim: int):
     """Views into the flat gradient of include/gdrf_b200.h:gdrf_outputs (``scale_mixture`` is present when the
-    buffer carries the RationalQuadratic kernel's extra entry)."""
+    buffer carries the RationalQuadratic kernel's extra entry; an 8-float tail holding the terms is ignored)."""
     o = 0
     out = {}
     base = K * M * M + K * M + K * V + M * D + 2 + ls_dim
     blocks = [("u_scale_tril", (K, M, M)), ("u_loc", (K, M)), ("phi", (K, V)), ("Z", (M, D)),
               ("variance", ()), ("lengthscale", (ls_dim,)), ("noise", ())]
-    if flat.numel() > base:
+    if flat.numel() in (base + 1, base + 1 + _lib.TERMS_TAIL):
         blocks.append(("scale_mixture", ()))
     for name, shape in blocks:
         n = 1
@@ -155,6 +164,21 @@ def split_grad(flat: torch.Tensor, K: int, M: int, V: int, D: int, ls_dim: int):
         out[name] = flat[o:o + n].view(shape)
         o += n
     return out
+
+
+def flat_gradient(g) -> torch.Tensor:
+    """The flat buffer behind the views returned by :func:`split_grad` / :func:`elbo_value_and_grads`, INCLUDING the
+    8-float tail that carries the four ELBO terms as (hi, lo) fp32 pairs: one ``all_reduce`` of this tensor sums the
+    parameter gradients and the loss of all ranks (one collective per step)."""
+    base = g["u_scale_tril"]
+    total = sum(v.numel() for v in g.values()) + _lib.TERMS_TAIL
+    return base.reshape(-1).as_strided((total,), (1,))
+
+
+def terms_from_flat(flat: torch.Tensor) -> torch.Tensor:
+    """fp64 [lp_mu, lq, ll, lp_phi] from the tail of a (possibly all-reduced) flat gradient buffer."""
+    t = flat[-_lib.TERMS_TAIL:].double().view(4, 2)
+    return t[:, 0] + t[:, 1]
 
 
 class GDRFElbo(torch.autograd.Function):
@@ -194,6 +218,7 @@ class GDRFElbo(torch.autograd.Function):
     def backward(ctx, grad_out):
         (flat,) = ctx.saved_tensors
         lib = _lib.load()
+        flat = flat[:flat.numel() - _lib.TERMS_TAIL]
         dst = torch.empty_like(flat)
         go = grad_out.detach().to(torch.float32).contiguous()
         _lib.check(lib.gdrf_elbo_backward(flat.data_ptr(), flat.numel(), go.data_ptr(), 1.0 / ctx.n_global,
@@ -281,7 +306,7 @@ def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, leng
     for c in calls[1:]:
         c.shape.flags = calls[0].shape.flags
     terms = torch.empty(4, dtype=torch.float64, device=dev)
-    grad = torch.empty(_lib.grad_elems(calls[0].shape), dtype=torch.float32, device=dev)
+    grad = torch.empty(_lib.grad_elems(calls[0].shape) + _lib.TERMS_TAIL, dtype=torch.float32, device=dev)
     for i, call in enumerate(calls):
         if i + 1 < len(calls):
             issue_copy(i + 1)

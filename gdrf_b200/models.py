@@ -257,12 +257,12 @@ class SparseMultinomialGDRF(nn.Module):
                                   self._maxjitter, n_global, n_offset, include_prior, flags, chunk_rows,
                                   self._scale_mixture)
 
-        if eps.dim() == 3:      # [P, K, N]: Trace_ELBO(num_particles=P) averages the particles' ELBOs
-            return torch.stack([one(e) for e in eps]).mean()
-        if self.num_particles > 1:
-            extra = [torch.randn(self._K, N, device=self.device, generator=self._eps_generator)
-                     for _ in range(self.num_particles - 1)]
-            return torch.stack([one(e) for e in [eps] + extra]).mean()
+        # [P, K, N] (or num_particles > 1): Trace_ELBO(num_particles=P, vectorize_particles=True) averages the particles'
+        # ELBOs (train_script.py:330-335); the op shares the contractions between them
+        if eps.dim() == 2 and self.num_particles > 1:
+            extra = torch.randn(self.num_particles - 1, self._K, eps.shape[-1], device=self.device,
+                                generator=self._eps_generator)
+            eps = torch.cat([eps.unsqueeze(0), extra])
         return one(eps)
 
     def model(self, xs, ws, subsample=False):

@@ -186,8 +186,9 @@ class FusedSVI:
         x = m._scaled(xs)
         N = x.shape[0]
         n_global = global_count(N, m.device, self.group) if n_global is None else int(n_global)
-        if eps is None:     # drawn for exactly these observations
-            eps = torch.randn(m.K, N, device=m.device, generator=m._eps_generator)
+        if eps is None:     # drawn for exactly these observations; num_particles draws each (scripts/mvco.py:136)
+            P = int(getattr(m, "num_particles", 1))
+            eps = torch.randn(*((P,) if P > 1 else ()), m.K, N, device=m.device, generator=m._eps_generator)
             n_offset = 0
         rank = dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
         terms, g, _ = elbo_value_and_grads(x, ws.to(m.device), c["Z"], c["variance"], c["lengthscale"], c["u_loc"],
@@ -195,10 +196,12 @@ class FusedSVI:
                                            kernel=m._kernel_kind, jitter=m._jitter, maxjitter=m._maxjitter,
                                            n_global=n_global, n_offset=n_offset, include_prior=(rank == 0),
                                            scale_mixture=c.get("scale_mixture"))
-        flat = g["u_scale_tril"].reshape(-1).as_strided((self.theta_u.numel(),), (1,))
+        from .elbo import flat_gradient, terms_from_flat
+        flat_all = flat_gradient(g)            # gradient | 8 floats carrying the four ELBO terms
+        flat = flat_all[:self.theta_u.numel()]
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(flat_all, op=dist.ReduceOp.SUM, group=self.group)      # the one collective of the step
+            terms = terms_from_flat(flat_all)
         self.t += 1
         st = torch.cuda.current_stream(self.theta_u.device).cuda_stream
         if self.clip_norm > 0.0:

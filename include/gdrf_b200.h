@@ -45,6 +45,8 @@ enum {
                                      (second and later sub-shards of one step streamed from host memory)       */
   GDRF_FLAG_PARTIAL = 128,        /* gdrf_elbo_step: more sub-shards follow; skip the per-step epilogue (Cholesky
                                      adjoint, prior, gradient assembly, terms)                                 */
+  GDRF_FLAG_TERMS_IN_GRAD = 1 << 17, /* out->grad has 8 more floats behind gdrf_grad_elems(): the four terms again, as
+                                     (hi, lo) fp32 pairs, so that one all-reduce of the flat buffer carries the loss */
   GDRF_FLAG_SINGLE_CTA = 32,      /* run the four large contractions on single CTAs (cta_group::1) instead of
                                      CTA pairs (cta_group::2); same results, used for A/B measurement         */
   GDRF_FLAG_FULL_WIDTH = 1 << 14, /* issue full 256-column MMAs in the diagonal blocks of the triangular operands too
@@ -77,13 +79,18 @@ typedef struct gdrf_shape {
   int32_t ls_dim;     /* 1 (isotropic lengthscale) or d                                                       */
   int32_t chunk_rows; /* observations streamed per pass, multiple of 256; 0 = library default                 */
   int32_t flags;      /* GDRF_FLAG_*                                                                          */
+  int32_t n_particles;/* draws of the guide per observation (Trace_ELBO(num_particles=P, vectorize_particles=True),
+                         train_script.py:330-335); 0 or 1 = one.  eps is then [n_particles, k, n_eps], and the terms /
+                         gradient are the MEAN over the particles.  The contractions run once: only the
+                         per-observation chain is repeated per particle.                                       */
 } gdrf_shape;
 
 /* Constrained parameter values and data, row-major, fp32 unless noted. */
 typedef struct gdrf_inputs {
   const float* xs;           /* [n_local, d]   observation locations, already scaled to the unit cube         */
   const int32_t* ws;         /* [n_local, v]   category counts (train_script.py:268: int32)                   */
-  const float* eps;          /* [k, n_eps]     fixed standard-normal draws of the guide's mu site             */
+  const float* eps;          /* [k, n_eps]     fixed standard-normal draws of the guide's mu site
+                                               ([n_particles, k, n_eps] with gdrf_shape::n_particles > 1)             */
   const float* z;            /* [m, d]         inducing points                                                */
   const float* variance;     /* [1]            kernel variance                                                */
   const float* lengthscale;  /* [ls_dim]       kernel lengthscale                                             */

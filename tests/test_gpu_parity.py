@@ -201,6 +201,35 @@ def test_chunk_streaming_and_sharding_are_exact_properties():
         assert O.rel_err(tot_g[k], g0[k]) < 1e-5, k
 
 
+def test_two_streams_on_one_device_do_not_share_scratch():
+    """The C ABI is re-entrant per (workspace, stream); the host side keeps one workspace per (device, stream).  Two
+    different problems evaluated concurrently on two streams give what each gives alone."""
+    a = O.make_problem(N=5000, D=2, K=4, V=32, grid=[12, 12], kernel="rbf", seed=141)
+    b = O.make_problem(N=4000, D=3, K=6, V=48, grid=[6, 5, 5], kernel="matern32", seed=142)
+    ta, ga, _ = _run(a)
+    tb, gb, _ = _run(b)
+    from gdrf_b200.elbo import _WORKSPACES, elbo_value_and_grads
+    dev = _dev()
+    c = lambda t: t.to(dev)
+    args = {k: tuple(c(getattr(p, f)) for f in ("xs", "ws", "Z", "variance", "lengthscale", "u_loc", "u_scale_tril",
+                                                 "noise", "phi", "beta", "eps")) for k, p in (("a", a), ("b", b))}
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    out = {}
+    for rep in range(3):       # interleave launches of the two problems on their streams
+        with torch.cuda.stream(s1):
+            out["a"] = elbo_value_and_grads(*args["a"], kernel=a.kernel, jitter=a.jitter, maxjitter=a.maxjitter)
+        with torch.cuda.stream(s2):
+            out["b"] = elbo_value_and_grads(*args["b"], kernel=b.kernel, jitter=b.jitter, maxjitter=b.maxjitter)
+    torch.cuda.synchronize()
+    assert len({k for k in _WORKSPACES if k[1] in (s1.cuda_stream, s2.cuda_stream)}) == 2
+    for key, (t0, g0) in (("a", (ta, ga)), ("b", (tb, gb))):
+        t1, g1, _ = out[key]
+        assert torch.allclose(t1.cpu(), t0, rtol=1e-12, atol=1e-6), key
+        for k in g0:
+            assert O.rel_err(g1[k].cpu().double(), g0[k]) < 1e-5, (key, k)
+
+
 def test_host_streamed_evaluation_equals_device_resident():
     """elbo_value_and_grads_from_host (pinned host observations, sub-shards copied on a second stream while the
     previous one computes, accumulators carried across calls) gives the device-resident result."""
@@ -405,6 +434,52 @@ def test_exponential_kernel_and_particles():
     assert abs(both.item() - 0.5 * (e0.item() + e1.item())) < 1e-5 * abs(both.item())
     both.backward()
     assert m.u_loc_unconstrained.grad is not None and torch.isfinite(m.u_loc_unconstrained.grad).all()
+
+
+def test_shared_contraction_particles_equal_the_mean_of_single_particle_runs():
+    """eps[P, K, N] (Trace_ELBO(num_particles=P, vectorize_particles=True), train_script.py:330-335; scripts/mvco.py:136
+    runs 10): terms and every gradient equal the mean over P single-particle evaluations -- of this op, and of the fp64
+    oracle -- while the contractions run once (one prologue, one whitening, one T = W S_k, one dW / dS / dKxz / C5) and
+    only the per-observation chain is repeated.  Also through the chunk streaming (several chunks x several particles)."""
+    import time
+    inp = O.make_problem(N=2600, D=1, K=8, V=174, grid=[300], kernel="matern32", seed=73)      # C2-like, M padded to 512
+    P = 5
+    eps = torch.randn(P, 8, 2600, generator=torch.Generator().manual_seed(11))
+    N = inp.xs.shape[0]
+    singles = [_run(inp, eps=eps[p]) for p in range(P)]
+    t_mean = sum(t for t, _, _ in singles) / P
+    g_mean = {k: sum(g[k] for _, g, _ in singles) / P for k in singles[0][1]}
+    for chunk_rows in (0, 1024):
+        t, g, _ = _run(inp, eps=eps, chunk_rows=chunk_rows)
+        assert torch.allclose(t, t_mean, rtol=1e-9, atol=1e-4), (t, t_mean)
+        for k in g:
+            assert O.rel_err(g[k], g_mean[k]) < 2e-5, (chunk_rows, k, O.rel_err(g[k], g_mean[k]))
+    # against the oracle: mean over particles of the fp64 / fp32 single-particle results
+    g64, g32, e64 = None, None, 0.0
+    for p in range(P):
+        ip = O.OracleInputs(**{**inp.__dict__, "eps": eps[p]})
+        o, a = O.loss_and_grads(ip.to(torch.float64), twice=False)
+        _, b = O.loss_and_grads(ip, twice=False)
+        e64 += o["elbo"].item() / P
+        g64 = {k: v / P for k, v in a.items()} if g64 is None else {k: g64[k] + a[k] / P for k in a}
+        g32 = {k: v.double() / P for k, v in b.items()} if g32 is None else {k: g32[k] + b[k].double() / P for k in b}
+    elbo = (t[0] + t[3] + t[2] - t[1]).item()
+    assert abs(elbo - e64) <= ELBO_TOL * abs(e64)
+    assert_parity(_three_way(g, N, g64, g32, O.GRAD_NAMES), "5 particles")
+    # cost: 10 particles at this shape are far from 10 single-particle steps
+    big = O.make_problem(N=30000, D=1, K=8, V=174, grid=[1000], kernel="matern32", seed=74)
+    e10 = torch.randn(10, 8, 30000, generator=torch.Generator().manual_seed(12))
+    def timed(e):
+        _run(big, eps=e)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            _run(big, eps=e)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 3
+    t1, t10 = timed(e10[0]), timed(e10)
+    print(f"C2 shape, N=30000: 1 particle {1e3 * t1:.1f} ms, 10 particles {1e3 * t10:.1f} ms ({t10 / t1:.2f}x)")
+    assert t10 < 3.0 * t1
 
 
 SWEEP = [
