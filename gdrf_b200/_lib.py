@@ -25,7 +25,7 @@ FLAG_PARTIAL = 128
 FLAG_REF_G = {i: 1 << (7 + i) for i in range(1, 7)}
 FLAG_REF_ALL = 0x3F << 8
 FLAG_FULL_WIDTH = 1 << 14
-FLAG_NO_SEGMENTS = 1 << 15
+FLAG_INTERLEAVED_MMAS = 1 << 15
 FLAG_SEGMENTED_FWD = 1 << 16
 FLAG_TERMS_IN_GRAD = 1 << 17
 TERMS_TAIL = 8

@@ -273,6 +273,11 @@ cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool u
   return launch_gemm2<P>(g, n_items, sms, st);
 }
 
+// the forward contractions (whitening, row norms) issue the correction products of a k-block before its hi * hi products
+// (gemm_tc.cuh, CorrFirst) in tiles of at most this many k-blocks: all of them, unless the A/B flag asks for the
+// interleaved order
+int corr_kn(const gdrf_shape* s) { return (s->flags & GDRF_FLAG_INTERLEAVED_MMAS) ? 0 : (1 << 30); }
+
 // forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
 int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
                   bool with_var, bool store_t, int sms, cudaStream_t st) {
@@ -292,7 +297,7 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
   {
     auto fill = [&](auto& g) {
       g.kxz = kxz; g.linv = linv; g.w = w; g.w16 = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.wsq = at<double>(ws, p.wsq);
-      g.RT = RT; g.MB = p.MB; g.segk = (s->flags & GDRF_FLAG_NO_SEGMENTS) ? 0 : 1;
+      g.RT = RT; g.MB = p.MB; g.corr_kn = corr_kn(s);
     };
     ProfScope ps(PK_G1, st);
     ++g_launches;
@@ -313,16 +318,25 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<0>::BN; g.ncp = (int)p.ncp;
       { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_gemm<G2<0>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, st)); }
     } else {                                 // fp16 2 x 2 planes (22-bit operands), 3 products
-      G2<2>::Params g{};
-      g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = st_f16_perm(ws, p);
-      g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
-      g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / G2<2>::BN; g.ncp = (int)p.ncp;
-      g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
-      g.segk = (s->flags & GDRF_FLAG_SEGMENTED_FWD) ? 1 : 0;
-      const bool pairs = (s->flags & (GDRF_FLAG_REF_G2 | GDRF_FLAG_SINGLE_CTA)) == 0;
-      g.ksplit = pairs ? topic_split(p.K, (RT + 1) / 2, sms / 2) : 0;
-      const int n_items = pairs ? ((RT + 1) / 2) * 2 * g.ksplit : RT;
-      { ProfScope ps(PK_G2F, st); ++g_launches; CU(launch_big<G2<2>>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+      auto run = [&](auto tag) -> int {
+        using P2 = decltype(tag);
+        typename P2::Params g{};
+        g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.st = st_f16_perm(ws, p);
+        g.tp = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * p.Mp);
+        g.q = at<double>(ws, p.q); g.store_t = store_t ? 1 : 0; g.RT = RT; g.MB = p.MB; g.K = p.K; g.NT = p.Mp / P2::BN; g.ncp = (int)p.ncp;
+        g.varn = (s->flags & GDRF_FLAG_FULL_WIDTH) ? 0 : 1;
+        g.segk = P2::SEGK;
+        g.corr_kn = corr_kn(s);
+        const bool pairs = (s->flags & (GDRF_FLAG_REF_G2 | GDRF_FLAG_SINGLE_CTA)) == 0;
+        g.ksplit = pairs ? topic_split(p.K, (RT + 1) / 2, sms / 2) : 0;
+        const int n_items = pairs ? ((RT + 1) / 2) * 2 * g.ksplit : RT;
+        ProfScope ps(PK_G2F, st);
+        ++g_launches;
+        CU(launch_big<P2>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G2) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st));
+        return 0;
+      };
+      if (s->flags & GDRF_FLAG_SEGMENTED_FWD) { if (int e = run(G2<3>{})) return e; }
+      else { if (int e = run(G2<2>{})) return e; }
     }
   }
   return 0;

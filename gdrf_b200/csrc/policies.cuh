@@ -44,19 +44,19 @@ __device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int
                  : "memory");
 }
 
-// sum of 32 squares in fp64 (four independent chains): the row norms feed the marginal variance, which the model uses
-// as a scale -- an fp32 partial sum here (3e-8 relative) is already visible in the gradients
+// sum of 32 squares: four independent fp32 partial sums of 8 terms, combined in fp64.  (All-fp64 was measured: the 32
+// F2F conversions per call run on the quarter-rate pipe and made the forward contraction 20 % slower, for 3e-8 of
+// relative accuracy that does not show behind the accumulation noise of T itself.)
 __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double a = v[j], b = v[8 + j], c = v[16 + j], d = v[24 + j];
-    s0 = fma(a, a, s0);
-    s1 = fma(b, b, s1);
-    s2 = fma(c, c, s2);
-    s3 = fma(d, d, s3);
+    s0 = fmaf(v[j], v[j], s0);
+    s1 = fmaf(v[8 + j], v[8 + j], s1);
+    s2 = fmaf(v[16 + j], v[16 + j], s2);
+    s3 = fmaf(v[24 + j], v[24 + j], s3);
   }
-  return (s0 + s1) + (s2 + s3);
+  return ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -64,19 +64,18 @@ __device__ __forceinline__ double sumsq32(const float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------
 template <int BN_>
 struct G1T {
-  static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter (segmented accumulation: 128 columns each)
-  static constexpr int SEGK = (BN_ == 256) ? 1 : 0;
+  static constexpr int EPI_WARPS = 4;
   static constexpr int PA = 3, PB = 3, BN = BN_;     // 128: one CTA per tile; 256: CTA pair (gemm_tc2_kernel)
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int FMT = FMT_BF16;
   static constexpr int CB = BN / 64, PCS = BN / 128;
   struct Params {
     PlaneMat kxz, linv, w, w16;   // w16: fp16 2-plane copy of W for the forward row-norm contraction
-    double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients); zeroed by the
-                   // caller, the column halves of a row add their partial sums
+    double* wsq;   // |W_n|^2, accumulated in fp64 (a 1e-6 error here is a 1e-3 error in the gradients)
     int RT, MB;
-    int segk;      // CTA pairs: segmented accumulation (gemm_tc.cuh, SegK)
+    int corr_kn;   // CTA pairs: tiles of at most this many k-blocks issue their correction products first (CorrFirst)
   };
+  __device__ static bool corr_first(const Params& p, int kn) { return kn <= p.corr_kn; }
   __device__ static int num_items(const Params& p) { return p.RT; }
   __device__ static int num_subs(const Params& p, int) { return p.MB / CB; }
   __device__ static int k_iters(const Params& p, int, int sub) { return min(p.MB, CB * (sub + 1)); }
@@ -109,7 +108,7 @@ struct G1T {
       acc += sumsq32(v);
     }
     __device__ void sub_end(const Params&, int, int, int) {}
-    __device__ void item_end(const Params& p, int item, int row) { atomicAdd(&p.wsq[item * 128 + row], acc); }
+    __device__ void item_end(const Params& p, int item, int row) { p.wsq[item * 128 + row] = acc; }
   };
 };
 using G1 = G1T<128>;
@@ -121,11 +120,12 @@ using G1 = G1T<128>;
 //   d ll / d mu is O(counts), so a 2^-17 relative error in q shows up as 1e-3 in the gradients.
 // MODE 0: bf16 3 x 3 planes / 6 products, 128-wide tiles (24-bit operands; any fp32 range)
 // MODE 2: fp16 2 x 2 planes / 3 products, 256-wide tiles (22-bit operands) -- the default
+// MODE 3: MODE 2 with segmented accumulation (GDRF_FLAG_SEGMENTED_FWD; gemm_tc.cuh, SegK)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 struct G2 {
   static constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter: the T store must keep up with short tiles
-  static constexpr int FMT = (MODE == 2) ? FMT_F16 : FMT_BF16;
+  static constexpr int FMT = (MODE >= 2) ? FMT_F16 : FMT_BF16;
   static constexpr int PA = (MODE == 0) ? 3 : 2, PB = (MODE == 0) ? 3 : 2, BN = (MODE == 0) ? 128 : 256;
   static constexpr bool A_MN = false, B_MN = false;
   static constexpr int CB = BN / 64;      // 64-column blocks per tile
@@ -138,6 +138,7 @@ struct G2 {
     int RT, MB, K, NT, ncp;   // NT = Mp / BN column tiles per topic
     int varn;          // CTA pairs: 1 = narrow MMAs in the diagonal blocks, 0 = full width (GDRF_FLAG_FULL_WIDTH, A/B)
     int segk;          // CTA pairs: 1 = segmented accumulation (gemm_tc.cuh, SegK), 0 = one TMEM accumulation per tile
+    int corr_kn;       // CTA pairs: tiles of at most this many k-blocks issue their correction products first (CorrFirst)
     // CTA pairs: items are (256-row pair tile, group of K / ksplit topics), two consecutive items = the two 128-row
     // halves of one pair tile.  A chunk with fewer than 74 pair tiles (the last chunk of a shard) then still fills
     // the machine: ksplit is chosen by the host so that ceil(pair tiles * ksplit / 74) / ksplit is smallest.
@@ -168,8 +169,9 @@ struct G2 {
   // k_pack_st), so the needed rows are the ones next to the middle: rank 0 stages the last N/2 rows of its block,
   // rank 1 the first N/2 of its, and the MMA covers accumulator columns [128 - N/2, 128 + N/2).  The k-blocks are
   // walked last-to-first so that the first MMA is full width; 15 % fewer MMA columns per tile row.
-  static constexpr int VARN = (MODE == 2) ? 1 : 0;
-  static constexpr int SEGK = (MODE == 2) ? 1 : 0;
+  static constexpr int VARN = (MODE >= 2) ? 1 : 0;
+  static constexpr int SEGK = (MODE == 3) ? 1 : 0;   // its own instantiation: the default kernel keeps its registers
+  __device__ static bool corr_first(const Params& p, int kn) { return kn <= p.corr_kn; }
   __device__ static int kblock(int kit, int kn) { return kn - 1 - kit; }
   __device__ static int ncols(const Params& p, int kb, int) {
     return (kb >= 4 || p.varn == 0) ? 256 : 64 * (kb + 1);
@@ -196,7 +198,7 @@ struct G2 {
   }
   // accumulator column -> column of the tile under that row order (identity for the other modes)
   __device__ static int tile_col(int c) {
-    if (MODE != 2) return c;
+    if (MODE < 2) return c;
     return c < 128 ? 64 * (3 - (c >> 5)) + (c & 31) : 64 * ((c - 128) >> 5) + 32 + (c & 31);
   }
   struct Epi {

@@ -52,15 +52,17 @@ enum {
   GDRF_FLAG_FULL_WIDTH = 1 << 14, /* issue full 256-column MMAs in the diagonal blocks of the triangular operands too
                                      (default: narrower MMAs there, 10-15 % fewer MMA columns); same results up to
                                      fp32 summation order, used for A/B measurement                           */
-  /* Segmented accumulation (csrc/gemm_tc.cuh, SegK): every 64-deep k-block of a tile gets a fresh TMEM accumulator, the
-     small correction products of the split are issued before the hi*hi products, and the k-blocks are summed in fp32
-     registers with round-to-nearest.  The tensor pipe's own fp32 accumulation costs about one ulp of the running sum per
-     MMA; the model uses the marginal variance as a *scale* (sparse_gdrf.py:403-405), which turns 2e-7 of relative noise
-     there into 2e-4 of gradient error.  The whitening W = Kxz L^-T (1 % of the work) is segmented by default; the forward
-     row-norm contraction T = W S_k only on request, because draining a TMEM accumulator per k-block is bound by the
-     TMEM read port (measured: gradients 1.8x closer to fp64 for +13 % step time).                                 */
-  GDRF_FLAG_NO_SEGMENTS = 1 << 15,   /* whitening without segmented accumulation (A/B measurement)               */
-  GDRF_FLAG_SEGMENTED_FWD = 1 << 16, /* forward row-norm contraction with segmented accumulation                  */
+  /* Accumulation order of the two forward contractions (whitening W = Kxz L^-T, row norms T = W S_k).  The tensor
+     pipe's fp32 accumulation costs about one ulp of the running sum per MMA, and the model uses the marginal variance as
+     a *scale* (sparse_gdrf.py:403-405), which turns 2e-7 of relative noise there into 2e-4 of gradient error.
+     Default: inside every 64-deep k-block the small correction products of the split are issued before the hi*hi
+     products (csrc/gemm_tc.cuh, CorrFirst) -- measured: noise of the marginal variance 2.1-2.4e-7 -> 1.3-1.8e-7, small
+     problems 3-7x closer to fp64, no cost.                                                                         */
+  GDRF_FLAG_INTERLEAVED_MMAS = 1 << 15,  /* (hi,hi), (hi,lo), (lo,hi) per 16-deep k-step, as in the backward
+                                            contractions (A/B measurement)                                          */
+  GDRF_FLAG_SEGMENTED_FWD = 1 << 16,     /* segmented accumulation (csrc/gemm_tc.cuh, SegK): a fresh TMEM accumulator
+                                            per k-block, summed in fp32 registers: noise 1.1-1.4e-7, but bound by the
+                                            TMEM read port -- forward contraction +45 %, step +9 %                   */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
   GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
   GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,

@@ -19,6 +19,7 @@ CASES = {
     "c3_shape": dict(N=8192, D=2, K=16, V=128, grid=[16, 16], kernel="rbf", seed=61),
     "c4_shape": dict(N=4096, D=3, K=32, V=512, grid=[16, 8, 8], kernel="rbf", seed=52),
     "c2_shape": dict(N=4096, D=1, K=8, V=174, grid=[1000], kernel="matern32", seed=71),
+    "c5_shape": dict(N=1024, D=3, K=64, V=1024, grid=[16, 16, 8], kernel="matern52", seed=82),
 }
 
 
@@ -27,9 +28,9 @@ def main():
     from gdrf_b200.elbo import marginal_moments
     out_path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     base = _lib.FLAG_CHOL_FP32_STATUS
-    variants = {"default (fp16x3, whitening segmented)": base,
-                "nothing segmented": base | _lib.FLAG_NO_SEGMENTS,
-                "whitening + forward segmented": base | _lib.FLAG_SEGMENTED_FWD,
+    variants = {"default (corrections first)": base,
+                "interleaved MMAs": base | _lib.FLAG_INTERLEAVED_MMAS,
+                "segmented accumulation": base | _lib.FLAG_SEGMENTED_FWD,
                 "bf16x6": base | _lib.FLAG_FWD_BF16,
                 "plain-FMA checker, fp16 planes": base | _lib.FLAG_REF_G[1] | _lib.FLAG_REF_G[2]}
     res = []
