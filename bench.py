@@ -1,6 +1,6 @@
 """bench.py -- ELBO + gradient throughput of the sparse multinomial GDRF (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C4|C3|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C4|C3|...] [--obs N]
 
 One "step" = one evaluation of the ELBO and its full gradient over the whole synthetic data set
 (SURVEY.md 8(d) inputs at BASELINE.json configs[3]: N=1M, D=3, K=32, V=512, M=1024=16x8x8, RBF), including
@@ -510,14 +510,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
-    ap.add_argument("--n", type=int, default=0, help="override the number of observations (debugging)")
+    ap.add_argument("--obs", type=int, default=0, help="override the number of observations (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip svi_step / other_configs / particles")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
-    if args.n:
-        cfg["N"] = args.n
+    if args.obs:
+        cfg["N"] = args.obs
     if args.impl == "reference":
         run_reference(args, args.config, cfg)
         return
@@ -538,7 +538,7 @@ def main():
     steps = max(1, args.steps)
     # C5 is BASELINE's 8-GPU weak-scaling stress config (1 M observations per GPU)
     scaling = "weak" if args.config == "C5" else "strong"
-    if args.config == "C5" and not args.n:
+    if args.config == "C5" and not args.obs:
         cfg["N"] = 1_000_000 * world
     N, D, K, V = cfg["N"], cfg["D"], cfg["K"], cfg["V"]
     b = Bench(args.config, cfg, dev, rank, world, int(os.environ.get("GDRF_BENCH_FLAGS", "0")))
@@ -558,18 +558,37 @@ def main():
     loss = -float(t[0] + t[3] + t[2] - t[1]) / N
 
     e2e = None if args.no_e2e else b.e2e(steps)
-    extras = not args.no_extras and not args.n
+    extras = not args.no_extras and not args.obs
     svi = b.svi_step(min(steps, 5), 2) if extras else None
+
+    roofline = roofline_block(prof, steps, b.n_local, ms_mine, M, K, b.flags, b._lib) if rank == 0 else None
+    n_local, flags = b.n_local, b.flags
+    del b
+    torch.cuda.empty_cache()
+
+    # BASELINE configs[4]: the C5 stress shape, weak scaling at 1 M observations per GPU on 8 GPUs (all ranks take part)
+    c5_weak = None
+    if extras and world == 8 and args.config == "C4":
+        from gdrf_b200.elbo import release_workspaces
+        release_workspaces()
+        torch.cuda.empty_cache()
+        c5 = dict(CONFIGS["C5"])
+        c5["N"] = 1_000_000 * world
+        b5 = Bench("C5", c5, dev, rank, world)
+        ms5, _, (t5, _) = b5.timed(b5.step, 2, 3)
+        t5 = t5.cpu()
+        c5_weak = {"workload": f"C5: N={c5['N']} D=3 K=64 V=1024 M=2048 matern52, 1 M observations per GPU x {world} GPUs",
+                   "scaling": "weak", "value": c5["N"] / (ms5 * 1e-3), "unit": "observations/s", "ms_per_step": ms5,
+                   "steps": 2, "warmup": 3, "loss": -float(t5[0] + t5[3] + t5[2] - t5[1]) / c5["N"],
+                   "all_reduce_bytes": 4 * (64 * 2048 * 2048 + 64 * 2048 + 64 * 1024 + 2048 * 3 + 3 + 8)}
+        del b5
+        release_workspaces()
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    roofline = roofline_block(prof, steps, b.n_local, ms_mine, M, K, b.flags, b._lib)
-    n_local, flags = b.n_local, b.flags
-    del b
-    torch.cuda.empty_cache()
 
     other, particles = None, None
     if extras and world == 1 and args.config == "C4":
@@ -609,7 +628,7 @@ def main():
                        "api": "gdrf_b200.elbo.elbo_value_and_grads (public); one all-reduce of gradient + terms"},
             "loss": loss, "wall_s_timed": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "svi_step": svi, "other_configs": other,
-            "particles": particles,
+            "particles": particles, "c5_weak_scaling": c5_weak,
             "alg_tflops_step": algorithmic_flops_per_obs(M, K, V) * N / (ms_per_step * 1e-3) / 1e12}
     print(json.dumps(line), flush=True)
     if world > 1:
