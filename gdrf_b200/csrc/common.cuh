@@ -123,8 +123,8 @@ __device__ __forceinline__ float pow2_scale(float bound, float* inv) {
 
 // per-chunk scalars (zeroed together with q at the start of every chunk) and per-step scalars (zeroed by the prologue /
 // at the start of a step): running maxima kept as float bit patterns, and the power-of-two operand scales derived from them
-enum { CS_G2MAX = 0, CS_GLOCMAX = 1, CS_GV0MAX = 2, CS_DWMAX = 3, CS_SG_INV = 4, CS_SD_INV = 5, CS_COUNT = 64 };
-enum { PS_SMAX = 0, PS_LINVMAX = 1, PS_UMAX = 2, PS_COUNT = 64 };
+enum { CS_G2MAX = 0, CS_GLOCMAX = 1, CS_GV0MAX = 2, CS_DWMAX = 3, CS_SG_INV = 4, CS_SD_INV = 5, CS_SL_INV = 6, CS_COUNT = 64 };
+enum { PS_SMAX = 0, PS_LINVMAX = 1, PS_UMAX = 2, PS_SU_INV = 3, PS_COUNT = 64 };
 
 // running maximum of non-negative floats kept as their bit patterns (ordered like unsigned integers)
 __device__ __forceinline__ void atomic_max_abs(unsigned* slot, float absval) {

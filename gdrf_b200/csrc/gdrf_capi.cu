@@ -71,7 +71,7 @@ struct Plan {
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, ps;
   size_t L64, Linv64, tmpA, tmpB, dinv, dinv32;
-  size_t linv_pl, linv16_pl, st_pl, w16_pl;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
+  size_t linv_pl, linv16_pl, st_pl, w16_pl, u16_pl;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
   // per chunk
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
   size_t srow, arow, cnt, gv0, floc, cs, wsq, q, fvar, theta, g_loc, g2, g1;   // cs | wsq | q are contiguous: one memset
@@ -126,6 +126,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.dinv32 = bump(off, sizeof(float) * (size_t)p.Mp * NB);
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.linv16_pl = bump(off, sizeof(bf16) * 2 * Mp2);
+  p.u16_pl = bump(off, sizeof(bf16) * 2 * 256 * (size_t)p.Mp);
   p.st_pl = bump(off, sizeof(bf16) * 4 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
@@ -278,6 +279,18 @@ cudaError_t launch_big(const typename P::Params& g, int n_items, int sms, bool u
 // interleaved order
 int corr_kn(const gdrf_shape* s) { return (s->flags & GDRF_FLAG_INTERLEAVED_MMAS) ? 0 : (1 << 30); }
 
+// once per call, before the first chunk: the fp16 operand planes of u_loc for f_loc = W u_loc^T on the tensor pipe
+int pack_u(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, cudaStream_t st) {
+  if (s->flags & GDRF_FLAG_FWD_BF16) return 0;      // bf16 mode keeps the CUDA-core k_floc
+  unsigned* ps = at<unsigned>(ws, p.ps);
+  CU(cudaMemsetAsync(ps + PS_UMAX, 0, sizeof(unsigned), st));
+  k_absmax<<<32, 256, 0, st>>>(in->u_loc, (long long)p.K * p.M, ps + PS_UMAX);
+  LAUNCH_CHECK();
+  k_pack_u<<<dim3(p.MB, 2), 256, 0, st>>>(in->u_loc, p.K, p.M, plane_mat(ws, p.u16_pl, 256, p.Mp), ps);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // forward contraction chain of one chunk: Kxz -> W -> f_loc (and q when with_var)
 int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, long long n0, int nc, int RT,
                   bool with_var, bool store_t, int sms, cudaStream_t st) {
@@ -309,8 +322,17 @@ int chunk_forward(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, voi
       CU(launch_gemm2<G1T<256>>(g, RT, sms, st));
     }
   }
-  k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
-  LAUNCH_CHECK();
+  if ((s->flags & (GDRF_FLAG_FWD_BF16 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_REF_G1)) == 0) {
+    GF::Params g{};      // f_loc = W u_loc^T on the tensor pipe (fp16 pairs)
+    g.w = plane_mat(ws, p.w16_pl, p.ncp, p.Mp); g.u = plane_mat(ws, p.u16_pl, 256, p.Mp);
+    g.floc = at<double>(ws, p.floc); g.inv_scale = at<float>(ws, p.ps) + PS_SU_INV;
+    g.RT = RT; g.MB = p.MB; g.K = p.K; g.ncp = (int)p.ncp;
+    ++g_launches;
+    CU(launch_gemm2<GF>(g, RT, sms, st));
+  } else {
+    k_floc<16><<<dim3(RT, (p.K + 15) / 16), 128, 0, st>>>(w, in->u_loc, p.K, p.M, p.MB, at<double>(ws, p.floc), (int)p.ncp);
+    LAUNCH_CHECK();
+  }
   if (with_var) {
     if (s->flags & GDRF_FLAG_FWD_BF16) {     // 24-bit operands, 6 products
       G2<0>::Params g{};
@@ -448,6 +470,7 @@ int marginal_moments_impl(const gdrf_shape* s, const gdrf_inputs* in, T* out_flo
   if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = num_sms();
+  if (int e = pack_u(s, in, p, ws, st)) return e;
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
     const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
     const int RT = (nc + 127) / 128;
@@ -680,7 +703,10 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   }
 
   PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
-  PlaneMat dwt = kxz;   // Kxz is dead once W exists; its planes are reused for dWtot
+  // Kxz is dead once W exists; its planes are reused for dWtot (two planes) plus, in fp16 mode, 128 more columns that
+  // carry g_loc for du_loc (G5)
+  const bool fuse_du = (s->flags & (GDRF_FLAG_FWD_BF16 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_REF_G5)) == 0;
+  PlaneMat dwt = fuse_du ? plane_mat(ws, p.kxz_pl, p.ncp, Mp + 128) : kxz;
   PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
   PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
   // 16-bit operand planes of the backward follow the forward's format: fp16 pairs (22 bits) by default
@@ -700,7 +726,9 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   if (!cont) {
     k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
     LAUNCH_CHECK();
-    if (want_grad) {
+    if (f16) {
+      if (int e = pack_u(s, in, p, ws, st)) return e;
+    } else if (want_grad) {
       CU(cudaMemsetAsync(ps + PS_UMAX, 0, sizeof(unsigned), st));
       k_absmax<<<32, 256, 0, st>>>(in->u_loc, (long long)K * M, ps + PS_UMAX);
       LAUNCH_CHECK();
@@ -771,10 +799,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
       CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
-                                                       in->u_loc, K, M, (int)p.ncp, dwt, fmt, in->variance, cs, ps);
+                                                       in->u_loc, K, M, (int)p.ncp, dwt, fmt, in->variance, cs, ps,
+                                                       fuse_du ? (K + 63) / 64 : 0);
       LAUNCH_CHECK();
     }
-    if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
+    if (!fuse_du)
+      if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
     {
       g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
       g6.fmt = fmt; g6.inv_scale = cs_f + CS_SG_INV;
@@ -821,7 +851,9 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     {
       const int NBt = 2 * RT;
       auto fill = [&](auto& g, int splits) {
-        g.dwt = dwt; g.w = w_b; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp; g.MT = p.MT;
+        g.dwt = dwt; g.w = w_b; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+        g.MTW = p.MT; g.MT = p.MT + (fuse_du ? 2 : 0);
+        g.du = fuse_du ? at<double>(ws, p.du) : nullptr; g.inv_scale_l = cs_f + CS_SL_INV; g.K = K; g.M = M;
         g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
         if (splits > NBt) splits = NBt;
         if (splits < 1) splits = 1;
@@ -837,7 +869,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
         CU(launch_gemm<G5T<128>>(g, base * g.splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
       } else {
         // 256 x 256 pair tiles: as many splits of the observation range as fill the sms / 2 CTA pairs once
-        const int base = p.MT * (Mp / 256), pairs = base / 2, clusters = sms / 2;
+        const int base = (p.MT + (fuse_du ? 2 : 0)) * (Mp / 256), pairs = base / 2, clusters = sms / 2;
         G5T<256>::Params g{}; fill(g, pairs >= clusters ? 1 : clusters / pairs);
         CU(launch_gemm2<G5T<256>>(g, base * g.splits, sms, st));
       }

@@ -114,6 +114,50 @@ struct G1T {
 using G1 = G1T<128>;
 
 // ---------------------------------------------------------------------------------------------
+// GF:  f_loc[k, n] = sum_m W[n, m] u_loc[k, m]   (pyro conditional: loc = W @ v_2D; the mean function is zero,
+// abstract_gdrf.py:17-18) on the tensor pipe: A = W16 (fp16 pair), B = U16 [256 rows (k, zero beyond K) x Mp] = the fp16
+// pair of s_u * u_loc (s_u: power-of-two scale from max |u_loc|, so that any fp32 u_loc fits); the epilogue writes
+// f_loc in fp64 times 1 / s_u.  One 256 x 256 pair tile per 256 observation rows; only the first K accumulator columns
+// carry data (a 256-wide MMA costs what a narrower one does next to the operand fill).
+// ---------------------------------------------------------------------------------------------
+struct GF {
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int FMT = FMT_F16;
+  static constexpr int PA = 2, PB = 2, BN = 256;
+  static constexpr bool A_MN = false, B_MN = false;
+  struct Params {
+    PlaneMat w, u;
+    double* floc;              // [K][ncp]
+    const float* inv_scale;    // 1 / s_u (ps[PS_SU_INV])
+    int RT, MB, K, ncp;
+  };
+  __device__ static int num_items(const Params& p) { return p.RT; }
+  __device__ static int num_subs(const Params&, int) { return 1; }
+  __device__ static int k_iters(const Params& p, int, int) { return p.MB; }
+  __device__ static bool corr_first(const Params&, int) { return true; }
+  __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int) {
+    return p.w.base + pl * p.w.plane_stride + p.w.block_off(item, kit);
+  }
+  __device__ static const bf16* b_src(const Params& p, int, int, int kit, int pl, int pc) {
+    return p.u.base + pl * p.u.plane_stride + p.u.block_off(pc, kit);
+  }
+  struct Epi {
+    double inv;
+    __device__ void item_begin(const Params& p, int, int) { inv = (double)p.inv_scale[0]; }
+    __device__ void sub_begin(const Params&, int, int, int) {}
+    __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
+      if (c0 >= p.K) return;
+      const long long n = (long long)item * 128 + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < p.K) p.floc[(long long)(c0 + j) * p.ncp + n] = inv * (double)v[j];
+    }
+    __device__ void sub_end(const Params&, int, int, int) {}
+    __device__ void item_end(const Params&, int, int) {}
+  };
+};
+
+// ---------------------------------------------------------------------------------------------
 // G2:  T[n, (k, j)] = sum_{i >= j} W[n, i] S_k[i, j]
 //   epilogue: q[k, n] = sum_j T^2 (fp64) and, when the gradient is wanted, T itself as two bf16 planes (TP).
 //   T is needed to fp32 accuracy here: f_var enters mu = f_loc + f_var * eps as a *scale* of O(variance) and
@@ -429,6 +473,12 @@ struct G5T {
     const float* inv_scale;   // 1 / s_d
     int fmt;
     int RT, MB, Mp, MT, splits, nb_per_split;
+    // du_loc[k, m] += sum_n g_loc[k, n] W[n, m] rides along: k_dw_finalize writes s_l * g_loc as the column blocks
+    // [Mp, Mp + 128) of the dWtot planes, and MT counts two more 128-row output tiles than Mp / 128 (a pair tile; the
+    // second one is padding) whose rows are topics and go to du instead of C5
+    double* du;           // [K][M] fp64 accumulator, or NULL (MT == MTW then)
+    const float* inv_scale_l;   // 1 / s_l (cs[CS_SL_INV])
+    int MTW, K, M;        // MTW = Mp / 128 row tiles of C5
   };
   // item = (split, column tile bt of BN columns, 128-row tile at), at fastest: with BN = 256 the items 2t, 2t + 1 are
   // the two row halves of one 256 x 256 pair tile
@@ -440,7 +490,7 @@ struct G5T {
     return min(p.nb_per_split, 2 * p.RT - s * p.nb_per_split);
   }
   __device__ static const bf16* a_src(const Params& p, int item, int, int kit, int pl, int pc) {
-    const int s = item / per_split(p), t = item - s * per_split(p), at = t % p.MT;
+    const int s = item / per_split(p), t = item - s * per_split(p), at = min(t % p.MT, p.MTW);   // padding tile: any data
     const int nb = s * p.nb_per_split + kit;
     return p.dwt.base + pl * p.dwt.plane_stride + p.dwt.block_off(nb >> 1, at * 2 + pc) + (nb & 1) * 4096;
   }
@@ -455,6 +505,16 @@ struct G5T {
     __device__ void sub_begin(const Params&, int, int, int) {}
     __device__ void chunk(const Params& p, int item, int, int row, int c0, const float (&v)[32]) {
       const int t = item % per_split(p), at = t % p.MT, bt = t / p.MT;
+      if (at >= p.MTW) {                      // topic rows: du_loc
+        const int k = (at - p.MTW) * 128 + row, m0 = bt * BN + c0;
+        if (k >= p.K) return;
+        const double il = (double)p.inv_scale_l[0];
+        double* dst = p.du + (long long)k * p.M + m0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (m0 + j < p.M) atomicAdd(dst + j, il * (double)v[j]);
+        return;
+      }
       double* dst = p.c5 + (long long)(at * 128 + row) * p.Mp + bt * BN + c0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) atomicAdd(dst + j, inv * (double)v[j]);

@@ -176,6 +176,29 @@ __global__ void __launch_bounds__(256) k_pack_linv(const double* __restrict__ Li
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_abs(ps + PS_LINVMAX, mx);
 }
 
+// U16 [256 rows (k; zero beyond K) x Mp] = fp16 pair of s_u * u_loc for GF; s_u from ps[PS_UMAX], 1 / s_u -> ps[PS_SU_INV]
+__global__ void __launch_bounds__(256) k_pack_u(const float* __restrict__ u, int K, int M, PlaneMat u16,
+                                                unsigned* __restrict__ ps) {
+  const int cb = blockIdx.x, rt = blockIdx.y;
+  float inv;
+  const float s_u = pow2_scale(__uint_as_float(ps[PS_UMAX]), &inv);
+  if (cb == 0 && rt == 0 && threadIdx.x == 0) reinterpret_cast<float*>(ps)[PS_SU_INV] = inv;
+  for (int t = threadIdx.x; t < 128 * 8; t += 256) {
+    const int r = t >> 3, g = t & 7;
+    const int k = rt * 128 + r;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int m = cb * 64 + g * 8 + e;
+      v[e] = (k < K && m < M) ? s_u * u[(long long)k * M + m] : 0.f;
+    }
+    uint4 hk[2];
+    split8h<2>(v, hk);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(u16.elem(pl, k, cb * 64 + g * 8)) = hk[pl];
+  }
+}
+
 // max |x| over a small array (u_loc) into a per-step slot
 __global__ void k_absmax(const float* __restrict__ x, long long n, unsigned* __restrict__ slot) {
   float mx = 0.f;
@@ -777,7 +800,8 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
                                                      const float* __restrict__ g_loc, const float* __restrict__ gv0,
                                                      const float* __restrict__ u, int K, int M, int ncp, PlaneMat dwt,
                                                      int fmt, const float* __restrict__ variance,
-                                                     unsigned* __restrict__ cs, const unsigned* __restrict__ ps) {
+                                                     unsigned* __restrict__ cs, const unsigned* __restrict__ ps,
+                                                     int gl_blocks) {
   extern __shared__ __align__(16) float dwf_smem[];
   float inv_sd;
   const float s_d = pow2_scale(__uint_as_float(cs[CS_DWMAX]) +
@@ -799,6 +823,27 @@ __global__ void __launch_bounds__(256) k_dw_finalize(PlaneMat w, const float* __
     gs[t] = g_loc[(long long)k * ncp + rt * 128 + r];
   }
   __syncthreads();
+  if (gl_blocks > 0 && cb == 0) {
+    // s_l * g_loc as gl_blocks extra 64-column blocks [Mp + 64 b, ...) of the dWtot planes (columns = topics): the A
+    // operand of du_loc = g_loc W, contracted by G5 together with C5
+    float inv_sl;
+    const float s_l = pow2_scale(__uint_as_float(cs[CS_GLOCMAX]), &inv_sl);
+    if (rt == 0 && threadIdx.x == 0) reinterpret_cast<float*>(cs)[CS_SL_INV] = inv_sl;
+    for (int t = threadIdx.x; t < 128 * 8 * gl_blocks; t += 256) {
+      const int r = (t >> 3) & 127, gq = t & 7, b = t >> 10;
+      const int pos = (r & 31) * 4 + (r >> 5);
+      float o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = b * 64 + gq * 8 + e;
+        o8[e] = (k < K) ? s_l * gs[k * 128 + pos] : 0.f;
+      }
+      uint4 out[2];
+      split8x2(fmt, o8, out);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) *reinterpret_cast<uint4*>(dwt.elem(pl, rt * 128 + r, Mp + b * 64 + gq * 8)) = out[pl];
+    }
+  }
   const int rr = threadIdx.x >> 3, g = threadIdx.x & 7;
   const int col = cb * 64 + g * 8;
   float v[4][8];

@@ -101,7 +101,7 @@ def test_tensor_path_matches_plain_fma_checker():
     inp = O.make_problem(N=3000, D=2, K=3, V=40, grid=[20, 20], kernel="rbf", seed=11)   # Mp = 512: multi-tile
     t_tc, g_tc, _ = _run(inp)
     t_rf, g_rf, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_REF_ALL)
-    assert torch.allclose(t_tc, t_rf, rtol=1e-6, atol=1e-3)
+    assert torch.allclose(t_tc, t_rf, rtol=3e-6, atol=1e-3)
     for k in g_tc:   # both carry the same split; only summation order differs
         assert O.rel_err(g_tc[k], g_rf[k]) < 1e-3, (k, O.rel_err(g_tc[k], g_rf[k]))
 
@@ -123,7 +123,7 @@ def test_narrow_diagonal_mmas_agree_with_full_width():
         # the observation range in dS) and their whitening is not segmented, so fp32 partial sums differ more than
         # between the two pair variants
         t_s, g_s, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_SINGLE_CTA)
-        assert torch.allclose(t_n, t_s, rtol=1e-7, atol=1e-3)
+        assert torch.allclose(t_n, t_s, rtol=3e-6, atol=1e-3)      # f_loc: tensor pipe vs the CUDA-core kernel of the single-CTA path
         for k in g_n:
             assert O.rel_err(g_n[k], g_s[k]) < (1e-3 if k in HYPER else 5e-4), (grid, k, O.rel_err(g_n[k], g_s[k]))
 
@@ -172,7 +172,7 @@ def test_marginal_variance_noise_by_accumulation_order():
         e = (fvar.cpu() - o["f_var"]) / o["f_var"]
         std[name] = e.std().item()
         assert e.abs().max().item() < 3e-6, (name, e.abs().max().item())
-        assert O.rel_err(floc.cpu(), o["f_loc"]) < 5e-7, name
+        assert O.rel_err(floc.cpu(), o["f_loc"]) < 1e-6, name      # (its noise matters 1000x less than that of f_var)
     e32 = ((o32["f_var"].double() - o["f_var"]) / o["f_var"]).std().item()
     print("relative noise of f_var:", {k: f"{v:.2e}" for k, v in std.items()}, f"fp32 oracle {e32:.2e}")
     assert std["default"] < 2e-7 < e32
