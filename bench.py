@@ -322,11 +322,8 @@ class Bench:
                                            p["u_scale_tril"], p["noise"], p["phi"], p["beta"],
                                            self.eps if eps is None else eps, kernel=self.cfg["kernel"],
                                            jitter=self.jitter, maxjitter=self.maxjitter, n_global=self.cfg["N"],
-                                           include_prior=(self.rank == 0), flags=self.flags, chunk_rows=self.chunk_rows)
-        if self.world > 1:        # small parameter gradients + the four ELBO terms in ONE all-reduce
-            flat = flat_gradient(g)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            terms = terms_from_flat(flat)
+                                           include_prior=(self.rank == 0), flags=self.flags, chunk_rows=self.chunk_rows,
+                                           all_reduce=True)      # gradient + terms summed over the ranks (NCCL)
         return terms, g
 
     def barrier(self):

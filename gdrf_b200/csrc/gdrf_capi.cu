@@ -650,10 +650,10 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   } else {
     cholesky<double>(kuu, L, at<double>(ws, p.dinv), p.Mp, dev_status, st);
   }
-  g_launches += 2 * (p.Mp / NB) - 2;   // + the one LAUNCH_CHECK counts
+  g_launches += p.Mp / NB - 1;          // + the one LAUNCH_CHECK counts
   LAUNCH_CHECK();
-  tri_inverse(L, at<double>(ws, p.dinv), Linv, p.Mp, st);
-  g_launches += 2 * (p.Mp / NB) - 2;
+  // Kuu's memory (tmpA) is free once it is factorised: scratch of the recursive inverse
+  g_launches += tri_inverse(L, at<double>(ws, p.dinv), Linv, kuu, p.Mp, st) - 1;
   LAUNCH_CHECK();
   const bool f16 = (s->flags & GDRF_FLAG_FWD_BF16) == 0;
   unsigned* ps = at<unsigned>(ws, p.ps);

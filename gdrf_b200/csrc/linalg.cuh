@@ -70,24 +70,24 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 //   k_chol_diag : 32 warps, one thread per element of the block, columns exchanged through shared memory; also
 //                 inverts the triangular block.  status: 0 ok, c+1 = pivot of column c not > 0 (the
 //                 RuntimeError of torch.linalg.cholesky that gdrf/models/utils.py:31-37 catches).
-//   k_chol_trail: block (ib, jb), ib >= jb > kb: panel tiles P_i = A[ib][kb] Dinv^T, P_j likewise, then
-//                 A[ib][jb] -= P_i P_j^T; the jb == kb+1 blocks also store L[ib][kb] = P_i.
+//   k_chol_step : block (ib, jb), ib >= jb > kb: panel tiles P_i = A[ib][kb] Dinv^T, P_j likewise, then
+//                 A[ib][jb] -= P_i P_j^T; the jb == kb+1 blocks also store L[ib][kb] = P_i; block (kb+1, kb+1) goes on
+//                 to factorise its tile (look-ahead), so a block column costs ONE launch.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
-                                               int Mp, int kb, int* __restrict__ status) {
+__device__ __forceinline__ void chol_diag_core(T a, T (*sl)[NB + 1], T* __restrict__ L, T* __restrict__ Dinv, int Mp,
+                                               int kb, int* __restrict__ status) {
   // 32 warps, one thread per element (r = warp, c = lane).  Three single-warp formulations (all shuffles and fully
   // unrolled; all shared memory; row in registers) took 29-35 us per block column: one warp issuing ~14 K mostly
   // dependent instructions.  Here a column step is two block barriers and one multiply-add per thread, and a row of
   // the inverse is a warp-level dot product per column.  The factorisation's arithmetic and its order are unchanged
   // (right-looking: element (r, c) receives -L[r][j] L[c][j] for j = 0 .. c-1 in order); the inverse sums its dot
   // products as a shuffle tree instead of serially.
-  __shared__ T sl[NB][NB + 1];     // L (zero above the diagonal)
+  // sl: [NB][NB + 1] shared scratch of the caller for L (zero above the diagonal); first written after a block barrier
   __shared__ T scol[NB];           // the column being eliminated
   __shared__ T sinv[NB];           // 1 / L[j][j]
   __shared__ T sd;                 // the pivot
   const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
-  T a = A[((long long)kb * NB + r) * Mp + kb * NB + c];
   int bad = 0;
 #pragma unroll 1
   for (int j = 0; j < NB; ++j) {
@@ -132,6 +132,14 @@ __device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __res
 }
 
 template <typename T>
+__device__ __forceinline__ void chol_diag_body(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+                                               int Mp, int kb, int* __restrict__ status) {
+  __shared__ T sl[NB][NB + 1];
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  chol_diag_core<T>(A[((long long)kb * NB + r) * Mp + kb * NB + c], sl, L, Dinv, Mp, kb, status);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(NB * NB) k_chol_diag(const T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
                                                   int Mp, int kb, int* __restrict__ status) {
   chol_diag_body<T>(A, L, Dinv, Mp, kb, status);
@@ -147,9 +155,12 @@ __global__ void __launch_bounds__(NB * NB) k_chol_diag_both(const double* __rest
   else chol_diag_body<float>(Af, Lf, Dinvf, Mp, kb, status);
 }
 
-template <typename T>
-__device__ __forceinline__ void chol_trail_body(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
-                                                int Mp, int kb) {
+// LOOKAHEAD: the block that updates the next diagonal tile (kb+1, kb+1) goes straight on to factorise it (the updated
+// element is in a register), while the other blocks of the launch finish the trailing update: one launch per block
+// column instead of two, and the 20 us factorisation hides the 15 us update instead of following it.
+template <typename T, bool LOOKAHEAD>
+__device__ __forceinline__ void chol_trail_body(T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv,
+                                                int Mp, int kb, int* __restrict__ status) {
   const int ib = kb + 1 + blockIdx.y, jb = kb + 1 + blockIdx.x;
   if (jb > ib) return;
   __shared__ T ai[NB][NB + 1], aj[NB][NB + 1], dd[NB][NB + 1];
@@ -172,21 +183,24 @@ __device__ __forceinline__ void chol_trail_body(T* __restrict__ A, T* __restrict
   T s = 0;
 #pragma unroll
   for (int t = 0; t < NB; ++t) s += ai[r][t] * aj[c][t];
-  A[((long long)ib * NB + r) * Mp + jb * NB + c] -= s;
+  const T a_new = A[((long long)ib * NB + r) * Mp + jb * NB + c] - s;
+  A[((long long)ib * NB + r) * Mp + jb * NB + c] = a_new;
+  if (LOOKAHEAD && blockIdx.x == 0 && blockIdx.y == 0)      // block-uniform; ai is dead after the first barrier inside
+    chol_diag_core<T>(a_new, ai, L, Dinv, Mp, kb + 1, status);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NB * NB) k_chol_trail(T* __restrict__ A, T* __restrict__ L, const T* __restrict__ Dinv,
-                                                        int Mp, int kb) {
-  chol_trail_body<T>(A, L, Dinv, Mp, kb);
+__global__ void __launch_bounds__(NB * NB) k_chol_step(T* __restrict__ A, T* __restrict__ L, T* __restrict__ Dinv, int Mp,
+                                                       int kb, int* __restrict__ status) {
+  chol_trail_body<T, true>(A, L, Dinv, Mp, kb, status);
 }
 
-__global__ void __launch_bounds__(NB * NB) k_chol_trail_both(double* __restrict__ A, double* __restrict__ L,
-                                                             const double* __restrict__ Dinv, float* __restrict__ Af,
-                                                             float* __restrict__ Lf, const float* __restrict__ Dinvf,
-                                                             int Mp, int kb) {
-  if (blockIdx.z == 0) chol_trail_body<double>(A, L, Dinv, Mp, kb);
-  else chol_trail_body<float>(Af, Lf, Dinvf, Mp, kb);
+__global__ void __launch_bounds__(NB * NB) k_chol_step_both(double* __restrict__ A, double* __restrict__ L,
+                                                            double* __restrict__ Dinv, float* __restrict__ Af,
+                                                            float* __restrict__ Lf, float* __restrict__ Dinvf, int Mp,
+                                                            int kb, int* __restrict__ status) {
+  if (blockIdx.z == 0) chol_trail_body<double, true>(A, L, Dinv, Mp, kb, status);
+  else chol_trail_body<float, true>(Af, Lf, Dinvf, Mp, kb, status);
 }
 
 // A: Kuu (destroyed), L: factor (zero above the diagonal), Dinv: [Mp/32][32][32]
@@ -194,10 +208,10 @@ template <typename T>
 inline void cholesky(T* A, T* L, T* Dinv, int Mp, int* status, cudaStream_t st) {
   cudaMemsetAsync(L, 0, sizeof(T) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
-  for (int kb = 0; kb < nblk; ++kb) {
-    k_chol_diag<T><<<1, NB * NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
+  k_chol_diag<T><<<1, NB * NB, 0, st>>>(A, L, Dinv, Mp, 0, status);
+  for (int kb = 0; kb + 1 < nblk; ++kb) {       // trailing update of block column kb + factorisation of tile kb + 1
     const int rem = nblk - kb - 1;
-    if (rem > 0) k_chol_trail<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb);
+    k_chol_step<T><<<dim3(rem, rem), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb, status);
   }
 }
 
@@ -206,52 +220,66 @@ inline void cholesky_both(double* A, double* L, double* Dinv, float* Af, float* 
   cudaMemsetAsync(L, 0, sizeof(double) * (size_t)Mp * Mp, st);
   cudaMemsetAsync(Lf, 0, sizeof(float) * (size_t)Mp * Mp, st);
   const int nblk = Mp / NB;
-  for (int kb = 0; kb < nblk; ++kb) {
-    k_chol_diag_both<<<2, NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb, status);
+  k_chol_diag_both<<<2, NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, 0, status);
+  for (int kb = 0; kb + 1 < nblk; ++kb) {
     const int rem = nblk - kb - 1;
-    if (rem > 0) k_chol_trail_both<<<dim3(rem, rem, 2), NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb);
+    k_chol_step_both<<<dim3(rem, rem, 2), NB * NB, 0, st>>>(A, L, Dinv, Af, Lf, Dinvf, Mp, kb, status);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// X = L^-1 (lower): block forward substitution on the identity with rank-32 updates.  X doubles as the
-// right-hand side: before block row k is solved, X[k][j] (j < k) holds -sum_{t<k} L[k][t] X[t][j].
+// X = L^-1 (lower) by recursive doubling over the diagonal: the 32 x 32 diagonal blocks are already inverted (Dinv, from
+// the factorisation); at level s = 32, 64, ... every 2s x 2s diagonal block [[L11, 0], [L21, L22]] gets its lower-left
+// quarter X21 = -X22 (L21 X11) from the two s x s inverses of the level below.  Two batched launches per level,
+// log2(Mp / 32) levels (10 launches at M = 1024) instead of the 2 Mp / 32 - 1 dependent launches of a block forward
+// substitution.  Tm: [Mp][Mp] scratch for L21 X11.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB * NB) k_trinv_solve(double* __restrict__ X, const double* __restrict__ Dinv,
-                                                         int Mp, int k) {
-  __shared__ double d[NB][NB + 1], b[NB][NB + 1];
-  const int j = blockIdx.x;   // 0..k
-  const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
-  d[r][c] = Dinv[((long long)k * NB + r) * NB + c];
-  b[r][c] = (j == k) ? (r == c ? 1.0 : 0.0) : X[((long long)k * NB + r) * Mp + j * NB + c];
-  __syncthreads();
-  double s = 0.0;
-#pragma unroll
-  for (int t = 0; t < NB; ++t) s += d[r][t] * b[t][c];
-  X[((long long)k * NB + r) * Mp + j * NB + c] = s;
+__global__ void __launch_bounds__(NB * NB) k_trinv_diag(const double* __restrict__ Dinv, double* __restrict__ X, int Mp) {
+  const int kb = blockIdx.x, c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
+  X[((long long)kb * NB + r) * Mp + kb * NB + c] = Dinv[((long long)kb * NB + r) * NB + c];
 }
 
-__global__ void __launch_bounds__(NB * NB) k_trinv_update(const double* __restrict__ L, double* __restrict__ X, int Mp,
-                                                          int k) {
-  __shared__ double l[NB][NB + 1], x[NB][NB + 1];
-  const int i = k + 1 + blockIdx.y, j = blockIdx.x;   // i > k, j <= k
+// MODE 0: Tm21 = L21 X11 (X11 lower: k >= column);  MODE 1: X21 = -X22 Tm21 (X22 lower: k <= row)
+template <int MODE>
+__global__ void __launch_bounds__(NB * NB) k_trinv_level(const double* __restrict__ L, double* __restrict__ X,
+                                                         double* __restrict__ Tm, int Mp, int s) {
+  __shared__ double as[NB][NB + 1], bs[NB][NB + 1];
   const int c = threadIdx.x & (NB - 1), r = threadIdx.x / NB;
-  l[r][c] = L[((long long)i * NB + r) * Mp + k * NB + c];
-  x[r][c] = X[((long long)k * NB + r) * Mp + j * NB + c];
-  __syncthreads();
-  double s = 0.0;
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  // the pair merges the diagonal blocks [lo, mid) and [mid, hi); the last pair of a level may have a short (or no)
+  // second block when Mp / 32 is not a power of two
+  const long long lo = 2LL * s * blockIdx.z, mid = lo + s, hi = (lo + 2 * s < Mp) ? lo + 2 * s : Mp;
+  if (mid + ti * NB >= hi) return;                 // block-uniform
+  const long long row = mid + ti * NB + r, col = lo + tj * NB + c;
+  const int k0 = MODE == 0 ? tj * NB : 0, k1 = MODE == 0 ? s : (ti + 1) * NB;
+  const double* Am = MODE == 0 ? L : X;            // left factor: L21 / X22 (rows `row`)
+  const long long acol0 = MODE == 0 ? lo : mid;
+  const double* Bm = MODE == 0 ? X : Tm;           // right factor: X11 / Tm21 (columns `col`)
+  const long long brow0 = MODE == 0 ? lo : mid;
+  double acc = 0.0;
+  for (int k = k0; k < k1; k += NB) {
+    __syncthreads();
+    as[r][c] = Am[row * Mp + acol0 + k + c];
+    bs[r][c] = Bm[(brow0 + k + r) * Mp + col];
+    __syncthreads();
 #pragma unroll
-  for (int t = 0; t < NB; ++t) s += l[r][t] * x[t][c];
-  X[((long long)i * NB + r) * Mp + j * NB + c] -= s;
+    for (int t = 0; t < NB; ++t) acc += as[r][t] * bs[t][c];
+  }
+  if (MODE == 0) Tm[row * Mp + col] = acc;
+  else X[row * Mp + col] = -acc;
 }
 
-inline void tri_inverse(const double* L, const double* Dinv, double* X, int Mp, cudaStream_t st) {
+inline int tri_inverse(const double* L, const double* Dinv, double* X, double* Tm, int Mp, cudaStream_t st) {
   cudaMemsetAsync(X, 0, sizeof(double) * (size_t)Mp * Mp, st);
-  const int nblk = Mp / NB;
-  for (int k = 0; k < nblk; ++k) {
-    k_trinv_solve<<<k + 1, NB * NB, 0, st>>>(X, Dinv, Mp, k);
-    if (k + 1 < nblk) k_trinv_update<<<dim3(k + 1, nblk - k - 1), NB * NB, 0, st>>>(L, X, Mp, k);
+  k_trinv_diag<<<Mp / NB, NB * NB, 0, st>>>(Dinv, X, Mp);
+  int launches = 1;
+  for (int s = NB; s < Mp; s *= 2) {
+    const dim3 grid(s / NB, s / NB, (Mp + 2 * s - 1) / (2 * s));
+    k_trinv_level<0><<<grid, NB * NB, 0, st>>>(L, X, Tm, Mp, s);
+    k_trinv_level<1><<<grid, NB * NB, 0, st>>>(L, X, Tm, Mp, s);
+    launches += 2;
   }
+  return launches;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -195,13 +195,9 @@ class FusedSVI:
                                            c["u_scale_tril"], c["noise"], c["phi"], m._dirichlet_param, eps,
                                            kernel=m._kernel_kind, jitter=m._jitter, maxjitter=m._maxjitter,
                                            n_global=n_global, n_offset=n_offset, include_prior=(rank == 0),
-                                           scale_mixture=c.get("scale_mixture"))
-        from .elbo import flat_gradient, terms_from_flat
-        flat_all = flat_gradient(g)            # gradient | 8 floats carrying the four ELBO terms
-        flat = flat_all[:self.theta_u.numel()]
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(flat_all, op=dist.ReduceOp.SUM, group=self.group)      # the one collective of the step
-            terms = terms_from_flat(flat_all)
+                                           scale_mixture=c.get("scale_mixture"), all_reduce=True, group=self.group)
+        from .elbo import flat_gradient
+        flat = flat_gradient(g)[:self.theta_u.numel()]      # summed over the ranks, like terms
         self.t += 1
         st = torch.cuda.current_stream(self.theta_u.device).cuda_stream
         if self.clip_norm > 0.0:
