@@ -28,6 +28,7 @@ FLAG_FULL_WIDTH = 1 << 14
 FLAG_INTERLEAVED_MMAS = 1 << 15
 FLAG_SEGMENTED_FWD = 1 << 16
 FLAG_TERMS_IN_GRAD = 1 << 17
+FLAG_LIKELIHOOD_FMA = 1 << 18
 TERMS_TAIL = 8
 
 

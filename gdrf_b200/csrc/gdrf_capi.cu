@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "likelihood_tc.cuh"
 #include "linalg.cuh"
 #include "optimizer.cuh"
 #include "policies.cuh"
@@ -71,9 +72,9 @@ struct Plan {
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, ps;
   size_t L64, Linv64, tmpA, tmpB, dinv, dinv32;
-  size_t linv_pl, linv16_pl, st_pl, w16_pl, u16_pl;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
+  size_t linv_pl, linv16_pl, st_pl, w16_pl, u16_pl, phit_pl, lfact;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
   // per chunk
-  size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf;   // dwt aliases kxz; dkxz aliases dw
+  size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf, dphi_part;   // dwt aliases kxz; dkxz aliases dw
   size_t srow, arow, cnt, gv0, floc, cs, wsq, q, fvar, theta, g_loc, g2, g1;   // cs | wsq | q are contiguous: one memset
   size_t total;
   long long zero_bytes;   // [acc .. c5] contiguous region cleared every step
@@ -127,6 +128,8 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.linv16_pl = bump(off, sizeof(bf16) * 2 * Mp2);
   p.u16_pl = bump(off, sizeof(bf16) * 2 * 256 * (size_t)p.Mp);
+  p.phit_pl = bump(off, sizeof(bf16) * 3 * 64 * (size_t)round_up_ll(p.V, 128));
+  p.lfact = bump(off, sizeof(float) * LT_LFACT);
   p.st_pl = bump(off, sizeof(bf16) * 4 * (size_t)p.K * Mp2);
   const size_t nm = (size_t)p.ncp * p.Mp;
   p.kxz_pl = bump(off, sizeof(bf16) * 3 * nm);
@@ -135,6 +138,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tp_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.wg_pl = bump(off, sizeof(bf16) * 2 * nm * p.K);
   p.dwf = bump(off, sizeof(float) * nm);
+  p.dphi_part = bump(off, p.K <= 64 ? sizeof(float) * (size_t)(p.ncp / 128) * p.K * round_up_ll(p.V, 128) : 0);
   p.srow = bump(off, sizeof(float) * p.ncp);
   p.arow = bump(off, sizeof(float) * p.ncp);
   p.cnt = bump(off, sizeof(float) * p.ncp);
@@ -209,8 +213,26 @@ int launch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0
   return 0;
 }
 
-int dispatch_likelihood(const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms, cudaStream_t st,
-                        double inv_p) {
+// stage 4 on the tensor pipe (likelihood_tc.cuh) for K <= 64 topics; the CUDA-core kernel otherwise / on request
+bool likelihood_on_tensor_pipe(const gdrf_shape* s) { return s->k <= 64 && (s->flags & GDRF_FLAG_LIKELIHOOD_FMA) == 0; }
+
+PlaneMat phit_mat(void* ws, const Plan& p) { return plane_mat(ws, p.phit_pl, round_up_ll(p.V, 128), 64); }
+
+int dispatch_likelihood(const gdrf_shape* s, const Plan& p, int nc, const gdrf_inputs* in, long long n0, void* ws, int sms,
+                        cudaStream_t st, double inv_p) {
+  if (likelihood_on_tensor_pipe(s)) {
+    CU(cudaFuncSetAttribute(k_likelihood_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+    k_likelihood_tc<<<(nc + 127) / 128, LT_THREADS, LT_SMEM, st>>>(
+        nc, (int)p.ncp, p.K, p.V, in->ws + n0 * p.V, at<float>(ws, p.theta), at<float>(ws, p.srow), phit_mat(ws, p),
+        at<float>(ws, p.g1), at<float>(ws, p.arow), at<float>(ws, p.cnt), at<float>(ws, p.dphi_part),
+        at<float>(ws, p.lfact), at<double>(ws, p.acc), inv_p);
+    LAUNCH_CHECK();
+    const int Vp = (int)round_up_ll(p.V, 128);
+    k_reduce_dphi<<<dim3((unsigned)(((long long)p.K * Vp + 255) / 256), 8), 256, 0, st>>>(at<float>(ws, p.dphi_part), (nc + 127) / 128,
+                                                                            p.K, p.V, Vp, at<double>(ws, p.dphi), inv_p);
+    LAUNCH_CHECK();
+    return 0;
+  }
   const int kpw = (p.K + 15) / 16;
   const int vj_need = (p.V + 31) / 32;
 #define LK(KPW, VJ) return launch_likelihood<KPW, VJ>(p, nc, in, n0, ws, sms, st, inv_p)
@@ -726,6 +748,12 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   if (!cont) {
     k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
     LAUNCH_CHECK();
+    if (likelihood_on_tensor_pipe(s)) {
+      k_pack_phit<<<(int)(round_up_ll(p.V, 128) / 128), 256, 0, st>>>(in->phi, K, p.V, phit_mat(ws, p));
+      LAUNCH_CHECK();
+      k_lfact_table<<<LT_LFACT / 256, 256, 0, st>>>(at<float>(ws, p.lfact));
+      LAUNCH_CHECK();
+    }
     if (f16) {
       if (int e = pack_u(s, in, p, ws, st)) return e;
     } else if (want_grad) {
@@ -768,7 +796,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       GDRF_DISPATCH_KQ(K, GDRF_OBS_PREPARE);
 #undef GDRF_OBS_PREPARE
       LAUNCH_CHECK();
-      if (int e = dispatch_likelihood(p, nc, in, n0, ws, sms, st, inv_p)) return e;
+      if (int e = dispatch_likelihood(s, p, nc, in, n0, ws, sms, st, inv_p)) return e;
 #define GDRF_OBS_FINALIZE(KQ)                                                                                  \
   k_obs_finalize<KQ><<<RT * 4, 256, 0, st>>>(nc, (int)p.ncp, K, s->n_offset + n0, s->n_eps, at<float>(ws, p.theta), \
                                              at<float>(ws, p.srow), at<float>(ws, p.g1), at<float>(ws, p.arow),    \

@@ -63,6 +63,8 @@ enum {
   GDRF_FLAG_SEGMENTED_FWD = 1 << 16,     /* segmented accumulation (csrc/gemm_tc.cuh, SegK): a fresh TMEM accumulator
                                             per k-block, summed in fp32 registers: noise 1.1-1.4e-7, but bound by the
                                             TMEM read port -- forward contraction +45 %, step +9 %                   */
+  GDRF_FLAG_LIKELIHOOD_FMA = 1 << 18, /* mixture + multinomial likelihood on CUDA cores (k_likelihood) instead of the three
+                                     chained tcgen05 contractions of k_likelihood_tc (default for k <= 64); A/B + checker */
   /* test hooks: run contraction Gi (i = 1..6) through the plain-FMA checker kernel instead of tcgen05 */
   GDRF_FLAG_REF_G1 = 1 << 8, GDRF_FLAG_REF_G2 = 1 << 9, GDRF_FLAG_REF_G3 = 1 << 10,
   GDRF_FLAG_REF_G4 = 1 << 11, GDRF_FLAG_REF_G5 = 1 << 12, GDRF_FLAG_REF_G6 = 1 << 13,

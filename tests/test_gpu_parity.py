@@ -106,6 +106,26 @@ def test_tensor_path_matches_plain_fma_checker():
         assert O.rel_err(g_tc[k], g_rf[k]) < 1e-3, (k, O.rel_err(g_tc[k], g_rf[k]))
 
 
+def test_tensor_pipe_likelihood_matches_the_cuda_core_kernel():
+    """Stage 4 (mixture, multinomial log-likelihood, its backward) as three chained tcgen05 contractions per
+    128-observation tile (k_likelihood_tc: P in TMEM, r in shared memory) against the CUDA-core kernel it replaces
+    (GDRF_FLAG_LIKELIHOOD_FMA), on shapes with V not a multiple of 128 / 32 / 4, K = 1 ... 64, a partial last tile, rows
+    without counts and a one-category problem (the 1 - eps clamp)."""
+    from gdrf_b200 import _lib
+    for kw in (dict(N=1500, D=2, K=3, V=40, grid=[6, 6], kernel="rbf", seed=151),
+               dict(N=513, D=2, K=40, V=300, grid=[5, 5], kernel="rbf", seed=152),
+               dict(N=700, D=1, K=64, V=1024, grid=[40], kernel="matern32", seed=153),
+               dict(N=257, D=2, K=2, V=1, grid=[3, 4], kernel="matern32", seed=154),
+               dict(N=900, D=3, K=17, V=65, grid=[3, 3, 3], kernel="exponential", seed=155)):
+        inp = O.make_problem(**kw)
+        inp.ws[5] = 0
+        t_tc, g_tc, _ = _run(inp)
+        t_f, g_f, _ = _run(inp, flags=_lib.FLAG_CHOL_FP32_STATUS | _lib.FLAG_LIKELIHOOD_FMA)
+        assert torch.allclose(t_tc, t_f, rtol=2e-7, atol=2e-3), (kw, t_tc - t_f)
+        for k in g_tc:      # two fp32-accumulating evaluations of the same sums; the hyper-parameter ones cancel heavily
+            assert O.rel_err(g_tc[k], g_f[k]) < (2e-4 if k in HYPER else 2e-5), (kw, k, O.rel_err(g_tc[k], g_f[k]))
+
+
 def test_narrow_diagonal_mmas_agree_with_full_width():
     """The CTA-pair kernels shrink the MMA to the non-zero columns inside the diagonal blocks of S_k (column windows
     of 64 ... 256 around the middle of a permuted accumulator); GDRF_FLAG_FULL_WIDTH issues full 256-column MMAs over
