@@ -483,7 +483,8 @@ def c1_record(dev):
     return {"workload": f"C1: data/data_2d_artificial.csv N={N} D=2 K={K} V={args[1].shape[1]} M={M} rbf, train() defaults",
             "value": N / (ms * 1e-3), "unit": "observations/s", "ms_per_step": ms, "njitter": int(nj),
             "loss": -float(tt[0] + tt[3] + tt[2] - tt[1]) / N,
-            "note": "latency-bound: 6 jitter escalations (6 prologues + 6 status read-backs) per step, as jittercholesky does"}
+            "note": "latency-bound: the reference's jitter escalation (utils.py:27-40) lands on level 5 -- one full prologue at level 0, "
+                    "five fp32 status-only factorisations, one full prologue at level 5, a status read-back after each"}
 
 
 def particles_record(dev):

@@ -18,6 +18,7 @@ KERNEL_IDS = {"rbf": 0, "matern32": 1, "matern52": 2, "exponential": 3, "rationa
 FLAG_WANT_GRAD = 1
 FLAG_INCLUDE_PRIOR = 2
 FLAG_CHOL_FP32_STATUS = 4
+FLAG_STATUS_ONLY = 8
 FLAG_FWD_BF16 = 16
 FLAG_SINGLE_CTA = 32
 FLAG_CONTINUE = 64

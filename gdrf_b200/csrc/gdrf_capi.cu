@@ -659,6 +659,18 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
   double* L = at<double>(ws, p.L64);
   double* Linv = at<double>(ws, p.Linv64);
   double* kuu = at<double>(ws, p.tmpA);
+  if (s->flags & GDRF_FLAG_STATUS_ONLY) {
+    // only the question jittercholesky asks at this level -- does the reference's fp32 factorisation fail? -- is
+    // answered: the fp32 Kuu and its fp32 Cholesky, nothing else (no fp64 values, inverse or operand planes)
+    float* k32 = at<float>(ws, p.tmpB);
+    float* l32 = k32 + (size_t)p.Mp * p.Mp;
+    k_kuu<float><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, k32);
+    LAUNCH_CHECK();
+    cholesky<float>(k32, l32, at<float>(ws, p.dinv32), p.Mp, dev_status, st);
+    g_launches += p.Mp / NB - 1;
+    LAUNCH_CHECK();
+    return 0;
+  }
   k_kuu<double><<<g2d, 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter, kuu);
   LAUNCH_CHECK();
   if (s->flags & GDRF_FLAG_CHOL_FP32_STATUS) {

@@ -119,13 +119,24 @@ class _Call:
                                          self.workspace.data_ptr(), self.ws_bytes, self.stream, status.data_ptr()))
             return int(status.item())        # the one host read-back of the step (mirrors try/except)
 
-        for nj in range(int(maxjitter)):
+        probe = False      # after a first failure: probe the next levels with the fp32 status factorisation alone
+        nj = 0
+        while nj < int(maxjitter):
+            if probe and (self.shape.flags & _lib.FLAG_CHOL_FP32_STATUS):
+                self.shape.flags |= _lib.FLAG_STATUS_ONLY
+                st = run(nj)
+                self.shape.flags &= ~_lib.FLAG_STATUS_ONLY
+                if st > 0:
+                    nj += 1
+                    continue
             st = run(nj)
             if st == -1:                     # factorised, but an operand may leave the fp16 range: repack as bf16 planes
                 self.shape.flags |= _lib.FLAG_FWD_BF16
                 st = run(nj)
             if st == 0:
                 return nj
+            probe = True
+            nj += 1
         raise RuntimeError("reached max jitter, covariance is unstable")
 
     def step(self, want_grad: bool, terms=None, grad=None, extra_flags: int = 0):

@@ -36,6 +36,9 @@ enum {
   GDRF_FLAG_WANT_GRAD = 1,        /* gdrf_elbo_step also produces the flat gradient                         */
   GDRF_FLAG_INCLUDE_PRIOR = 2,    /* add the Dirichlet log-density of phi and its gradient (one rank only)   */
   GDRF_FLAG_CHOL_FP32_STATUS = 4, /* decide not-PD with an fp32 factorisation of the reference's fp32 Kuu    */
+  GDRF_FLAG_STATUS_ONLY = 8,      /* gdrf_prologue: only decide whether this jitter level fails (the fp32 factorisation of
+                                     the reference's fp32 Kuu); a caller escalating through failing levels runs the full
+                                     prologue once, at the level that succeeds                                  */
   GDRF_FLAG_FWD_BF16 = 16,        /* every 16-bit operand plane is bf16 (any fp32 range): the forward row-norm
                                      contraction runs on 3 bf16 planes / 6 products (24-bit operands) and the
                                      backward contractions on bf16 pairs (16-bit), instead of fp16 pairs / 3 products
@@ -126,7 +129,8 @@ int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
  * factorisation succeeded, 1 + the failing column when it did not, -1 when it succeeded but u_scale_tril, L^-1, the
  * kernel variance or the bound sqrt(variance m) max|u_scale_tril| on T = W S_k may leave the fp16 range (then call
  * gdrf_prologue again, and gdrf_elbo_step, with GDRF_FLAG_FWD_BF16; with that flag the status is never -1).
- * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39).          */
+ * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39); after a first failure
+ * it may probe the following levels with GDRF_FLAG_STATUS_ONLY and run the full prologue at the first that passes.  */
 int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
                   size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
 

@@ -29,10 +29,11 @@ DISTINCT = {                 # bytes: distinct reads + writes per launch
     "<G3>": 2 * 2 * NM * K + 2 * 2 * K * M * M * TRI + 4 * NM + 4 * K * N,    # T, ST16N, g2 -> dW
     "<G6>": 2 * 2 * NM * K * 2 + 4 * K * M * M * TRI * 2,                     # WG, T -> dS (read-modify-write)
     "G4T": 2 * 2 * NM + 2 * 2 * M * M * TRI + 4 * NM,                               # dWtot, Linv16 -> dKxz
-    "G5T": 2 * 2 * NM * 2 + 8 * M * M,                                              # dWtot, W16 -> C5 (fp64 atomics)
+    "G5T": 2 * 2 * NM * 2 + 8 * M * M + 2 * 2 * N * 128,                            # dWtot (+ g_loc), W16 -> C5, du_loc
     "k_scale_w": 3 * 2 * NM + 4 * K * N + 2 * 2 * NM * K,                           # W, g2 -> WG
-    "k_likelihood": 4 * N * V + 4 * K * N + 4 * K * V + 4 * K * N,                  # ws, theta, phi -> g1
-    "k_floc": 3 * 2 * NM + 8 * K * N, "k_du": 3 * 2 * NM + 4 * K * N,
+    "k_likelihood": 4 * N * V + 4 * K * N + 6 * 64 * V + 4 * K * N + 4 * (N // 128) * K * V,   # ws, theta, phi^T -> g1, dphi slabs
+    "<GF>": 2 * 2 * NM + 8 * K * N,                                                 # W16 -> f_loc
+    "k_reduce_dphi": 4 * (N // 128) * K * V + 8 * K * V,
     "k_dw_finalize": 3 * 2 * NM + 4 * NM + 2 * 2 * NM, "k_kxz_planes": 4 * D * N + 3 * 2 * NM,
     "k_kxz_backward": 4 * NM + 4 * D * N, "k_obs_prepare": (8 + 8 + 4 + 4 + 4) * K * N, "k_obs_finalize": (4 * 6) * K * N,
 }
