@@ -510,6 +510,8 @@ SWEEP = [
     (255, 4, 5, 37, [3, 3, 2, 2], "rbf"),       # D = 4, M = 36
     (1000, 3, 17, 65, [5, 3, 3], "exponential"),
     (513, 2, 40, 300, [9, 9], "rbf"),           # K > 32 (two topics per lane), V > 256
+    (900, 2, 80, 70, [7, 7], "matern32"),       # K > 64: the CUDA-core likelihood, two g_loc column blocks in G5
+    (2000, 2, 128, 40, [5, 5], "rbf"),          # K = 128: the largest topic count the library takes
     (2049, 1, 6, 31, [300], "matern52"),        # M = 300 -> padded to 512, N = 16 tiles + 1 row
     (700, 2, 4, 23, [6, 6], "rationalquadratic"),   # third kernel hyper-parameter (scale_mixture)
     (400, 3, 3, 12, [4, 3, 3], "rationalquadratic"),
