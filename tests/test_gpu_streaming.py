@@ -176,3 +176,37 @@ def test_pyro_adapter_path_under_the_shim(tmp_path):
     script.write_text(PYRO_ADAPTER)
     r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+
+@pytest.mark.gpu
+def test_reference_epoch_loop_sees_fused_training_without_write_back(tmp_path):
+    """The reference's epoch loop (train_script.py:467-500): svi.step, then model.perplexity / kernel_lengthscale /
+    kernel_variance, then torch.save({"model": deepcopy(model).half(), ...}) -- every epoch.  With FusedSVI the module's
+    parameters are views of the flat buffer it trains, so the evaluation calls and the checkpoint see the trained values
+    with no write_back(); with num_particles = 10 (scripts/mvco.py:136) the step draws ten particles."""
+    import copy
+    from gdrf_b200 import FusedSVI, Matern32, SparseMultinomialGDRF
+    from oracle import gdrf_oracle as O
+    src = O.make_problem(N=1200, D=1, K=4, V=30, grid=[40], kernel="matern32", seed=171)
+    m = SparseMultinomialGDRF(num_observation_categories=30, num_topic_categories=4, world=[(0.0, 1.0)],
+                              kernel=Matern32(1, variance=src.variance, lengthscale=src.lengthscale), dirichlet_param=0.01,
+                              n_points=40, inducing_init="grid", device="cuda:0", jitter=1e-4, maxjitter=15)
+    m.seed_eps(7)
+    m.num_particles = 10
+    xs, ws = src.xs.cuda(), src.ws.cuda()
+    svi = FusedSVI(m, lr=5e-2)
+    ppl, ls, losses = [], [], []
+    for epoch in range(6):
+        losses.append(svi.step(xs, ws))
+        ppl.append(float(m.perplexity(xs, ws)))                 # abstract_gdrf.py:137-139 through the module
+        ls.append(float(m.kernel_lengthscale))
+        path = tmp_path / "last.pt"
+        torch.save({"epoch": epoch, "model": copy.deepcopy(m).half()}, path)     # train_script.py:490-500
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert ppl[-1] < ppl[0] and len(set(ppl)) == len(ppl)       # the module evaluates what FusedSVI trained
+    assert len(set(ls)) == len(ls)
+    back = torch.load(path, weights_only=False)["model"].float()
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), back.named_parameters()):
+        assert n1 == n2 and torch.allclose(p1.detach().cpu(), p2.detach().cpu(), atol=3e-2, rtol=2e-2), n1
+    assert abs(float(back.cuda().perplexity(xs, ws)) - ppl[-1]) < 0.05 * ppl[-1]
