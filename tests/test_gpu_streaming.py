@@ -200,7 +200,7 @@ def test_reference_epoch_loop_sees_fused_training_without_write_back(tmp_path):
     for epoch in range(6):
         losses.append(svi.step(xs, ws))
         ppl.append(float(m.perplexity(xs, ws)))                 # abstract_gdrf.py:137-139 through the module
-        ls.append(float(m.kernel_lengthscale))
+        ls.append(float(np.asarray(m.kernel_lengthscale).reshape(-1)[0]))
         path = tmp_path / "last.pt"
         torch.save({"epoch": epoch, "model": copy.deepcopy(m).half()}, path)     # train_script.py:490-500
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
