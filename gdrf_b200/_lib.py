@@ -50,7 +50,7 @@ class Outputs(ctypes.Structure):
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
            "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_marginal_moments", "gdrf_perplexity_terms",
-           "gdrf_marginal_moments_f64",
+           "gdrf_marginal_moments_f64", "gdrf_jitter_probe",
            "gdrf_constrain", "gdrf_adam_step", "gdrf_clipped_adam_step", "gdrf_gather_rows", "gdrf_last_error",
            "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
@@ -82,7 +82,8 @@ def load() -> ctypes.CDLL:
                                            c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]
     lib.gdrf_gather_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.c_int32, ctypes.c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p]
-    for n in EXPORTS[:13]:
+    lib.gdrf_jitter_probe.argtypes = [P(Shape), P(Inputs), c_double, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]
+    for n in EXPORTS[:14]:
         getattr(lib, n).restype = c_int
     lib.gdrf_launch_count.restype = ctypes.c_longlong
     lib.gdrf_profile_enable.argtypes = [c_int]
@@ -110,6 +111,9 @@ def grad_elems(shape: Shape) -> int:
     out = c_int64(0)
     check(load().gdrf_grad_elems(ctypes.byref(shape), ctypes.byref(out)))
     return int(out.value)
+
+
+PROBE_MAX = 8      # GDRF_PROBE_MAX
 
 
 PROFILE_KINDS = ("G1", "G2_fwd", "scale_w", "G3", "G4", "G5", "G6")

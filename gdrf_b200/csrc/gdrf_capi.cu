@@ -71,7 +71,7 @@ struct Plan {
   int chunk_rows;
   // persistent
   size_t acc, ck, du, dphi, dz, c5, phisum, ps;
-  size_t L64, Linv64, tmpA, tmpB, dinv, dinv32;
+  size_t L64, Linv64, tmpA, tmpB, dinv, dinv32, probe;
   size_t linv_pl, linv16_pl, st_pl, w16_pl, u16_pl, phit_pl, lfact;   // st_pl: 4 planes -- bf16 mode: ST (3); fp16 mode: ST16 permuted (2) | ST16N (2)
   // per chunk
   size_t kxz_pl, w_pl, tp_pl, wg_pl, dwf, dphi_part;   // dwt aliases kxz; dkxz aliases dw
@@ -125,6 +125,7 @@ int make_plan(const gdrf_shape* s, Plan& p) {
   p.tmpB = bump(off, sizeof(double) * Mp2);
   p.dinv = bump(off, sizeof(double) * (size_t)p.Mp * NB);
   p.dinv32 = bump(off, sizeof(float) * (size_t)p.Mp * NB);
+  p.probe = bump(off, sizeof(float) * GDRF_PROBE_MAX * (2 * Mp2 + (size_t)p.Mp * NB));   // gdrf_jitter_probe
   p.linv_pl = bump(off, sizeof(bf16) * 3 * Mp2);
   p.linv16_pl = bump(off, sizeof(bf16) * 2 * Mp2);
   p.u16_pl = bump(off, sizeof(bf16) * 2 * 256 * (size_t)p.Mp);
@@ -708,6 +709,31 @@ int gdrf_prologue(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int
     k_merge_status<<<1, 1, 0, st>>>(ps, in->variance, p.M, dev_status);
     LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int gdrf_jitter_probe(const gdrf_shape* s, const gdrf_inputs* in, double jitter, int njitter_first, int count, void* ws,
+                      size_t ws_bytes, gdrf_stream_t stream, int* dev_status) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !ws || !dev_status) return fail(1, "null pointer argument%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  if (njitter_first < 0 || count < 1 || count > GDRF_PROBE_MAX) return fail(1, "njitter_first must be >= 0 and count in [1, GDRF_PROBE_MAX]%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Hyper hp = make_hyper(s, in);
+  const size_t Mp2 = (size_t)p.Mp * p.Mp;
+  float* k32 = at<float>(ws, p.probe);
+  float* l32 = k32 + GDRF_PROBE_MAX * Mp2;
+  float* d32 = l32 + GDRF_PROBE_MAX * Mp2;
+  CU(cudaMemsetAsync(dev_status, 0, sizeof(int) * count, st));
+  k_kuu_batch<<<dim3(ceil_div(p.Mp, 256), p.Mp, count), 256, 0, st>>>(in->z, p.M, p.Mp, hp, jitter, njitter_first, k32,
+                                                                     (long long)Mp2);
+  LAUNCH_CHECK();
+  cholesky_batch(k32, l32, d32, p.Mp, count, dev_status, st);
+  g_launches += p.Mp / NB - 1;
+  LAUNCH_CHECK();
   return 0;
 }
 

@@ -18,8 +18,8 @@ constexpr int NB = 32;   // block size of the blocked factorisations
 //               only to decide whether the reference's fp32 Cholesky would have failed.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, double jitter, int njitter,
-                      T* __restrict__ Kuu) {
+__device__ __forceinline__ void kuu_body(const float* __restrict__ Z, int M, int Mp, const Hyper& hp, double jitter,
+                                         int njitter, T* __restrict__ Kuu) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= Mp) return;
@@ -62,6 +62,11 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
     }
   }
   Kuu[(long long)i * Mp + j] = val;
+}
+template <typename T>
+__global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, double jitter, int njitter,
+                      T* __restrict__ Kuu) {
+  kuu_body<T>(Z, M, Mp, hp, jitter, njitter, Kuu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,6 +206,38 @@ __global__ void __launch_bounds__(NB * NB) k_chol_step_both(double* __restrict__
                                                             int kb, int* __restrict__ status) {
   if (blockIdx.z == 0) chol_trail_body<double, true>(A, L, Dinv, Mp, kb, status);
   else chol_trail_body<float, true>(Af, Lf, Dinvf, Mp, kb, status);
+}
+
+// Batched status probe (jittercholesky's "does this level fail?", utils.py:31-37, for SEVERAL jitter levels at once):
+// blockIdx.z / blockIdx.x selects the level; every level has its own fp32 Kuu, L, Dinv and status word, `stride`
+// (matrices), `dstride` (Dinv) elements apart.  The levels are independent, so the batch costs one launch chain -- the
+// chain is latency-bound on the 32 x 32 diagonal factorisations -- instead of one chain and one host read-back per level.
+__global__ void __launch_bounds__(NB * NB) k_chol_diag_batch(const float* __restrict__ A, float* __restrict__ L,
+                                                             float* __restrict__ Dinv, int Mp, int kb, long long stride,
+                                                             long long dstride, int* __restrict__ status) {
+  const long long b = blockIdx.x;
+  chol_diag_body<float>(A + b * stride, L + b * stride, Dinv + b * dstride, Mp, kb, status + b);
+}
+__global__ void __launch_bounds__(NB * NB) k_chol_step_batch(float* __restrict__ A, float* __restrict__ L,
+                                                             float* __restrict__ Dinv, int Mp, int kb, long long stride,
+                                                             long long dstride, int* __restrict__ status) {
+  const long long b = blockIdx.z;
+  chol_trail_body<float, true>(A + b * stride, L + b * stride, Dinv + b * dstride, Mp, kb, status + b);
+}
+// Kuu in the reference's fp32 arithmetic for `count` consecutive jitter levels nj0, nj0 + 1, ... (blockIdx.z)
+__global__ void k_kuu_batch(const float* __restrict__ Z, int M, int Mp, Hyper hp, double jitter, int nj0,
+                            float* __restrict__ Kuu, long long stride) {
+  kuu_body<float>(Z, M, Mp, hp, jitter, nj0 + (int)blockIdx.z, Kuu + (long long)blockIdx.z * stride);
+}
+inline void cholesky_batch(float* A, float* L, float* Dinv, int Mp, int count, int* status, cudaStream_t st) {
+  const long long stride = (long long)Mp * Mp, dstride = (long long)Mp * NB;
+  cudaMemsetAsync(L, 0, sizeof(float) * (size_t)stride * count, st);
+  const int nblk = Mp / NB;
+  k_chol_diag_batch<<<count, NB * NB, 0, st>>>(A, L, Dinv, Mp, 0, stride, dstride, status);
+  for (int kb = 0; kb + 1 < nblk; ++kb) {
+    const int rem = nblk - kb - 1;
+    k_chol_step_batch<<<dim3(rem, rem, count), NB * NB, 0, st>>>(A, L, Dinv, Mp, kb, stride, dstride, status);
+  }
 }
 
 // A: Kuu (destroyed), L: factor (zero above the diagonal), Dinv: [Mp/32][32][32]

@@ -134,6 +134,16 @@ int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
 int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
                   size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
 
+/* jittercholesky's question "does level njitter fail?" (utils.py:31-37: the try/except around the fp32
+ * torch.linalg.cholesky) answered for `count` <= GDRF_PROBE_MAX consecutive levels njitter_first, njitter_first + 1, ...
+ * in ONE launch chain: dev_status[i] (DEVICE int[count]) = 0 when the reference's fp32 factorisation of
+ * Kuu + (sum_{t <= njitter_first + i} jitter 10^t) I succeeds, 1 + the failing column otherwise.  The levels are
+ * independent and the chain is latency-bound, so the batch costs what one level does.  Writes only its own scratch in
+ * the workspace: a completed gdrf_prologue on the same workspace stays valid.                                    */
+#define GDRF_PROBE_MAX 8
+int gdrf_jitter_probe(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter_first, int count,
+                      void* workspace, size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
+
 /* One evaluation of the ELBO terms (and, with GDRF_FLAG_WANT_GRAD, of the full gradient) over this shard,
  * streamed in chunks of chunk_rows observations.  Requires a successful gdrf_prologue on the same
  * workspace with the same z / variance / lengthscale.  A shard may be fed in several calls (sub-shards with

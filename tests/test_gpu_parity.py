@@ -88,6 +88,34 @@ def test_c1_reference_defaults_escalate_jitter_like_the_reference():
     assert_parity(_check_against_golden(inp, d, terms, g, nj), "C1")
 
 
+def test_jitter_search_speculation_and_batched_probe_return_the_reference_level():
+    """The escalation search (elbo._Call.prologue): a cold search (level 0 fails -> one batched probe of the remaining
+    levels -> full prologue at the first that passes), the speculative repeat (probe of the levels below the last
+    level + full prologue there, one read-back) and a WRONG hint (the previous model landed on a higher / lower level)
+    all return the level the reference's jittercholesky walks to, with identical results."""
+    from gdrf_b200 import elbo as E
+    inp, d = load_golden("c1_artificial2d")
+    E._JITTER_HINTS.clear()
+    t0, g0, nj0 = _run(inp)                      # cold: general search
+    assert nj0 == 5 and list(E._JITTER_HINTS.values()) == [5]
+    t1, g1, nj1 = _run(inp)                      # speculation holds
+    same = lambda ta, ga: (torch.allclose(t0, ta, rtol=1e-9, atol=0) and      # atomics: summation order differs run to run
+                           all(O.rel_err(ga[k], g0[k]) < 1e-5 for k in g0))
+    assert nj1 == 5 and same(t1, g1)
+    key = next(iter(E._JITTER_HINTS))
+    for wrong in (2, 7):                         # hint too low (level 2 still fails) / too high (level 5 passes below it)
+        E._JITTER_HINTS[key] = wrong
+        t2, g2, nj2 = _run(O.OracleInputs(**{**inp.__dict__, "maxjitter": 15}))
+        assert nj2 == 5 and same(t2, g2)
+        assert E._JITTER_HINTS[key] == 5
+    # a well-conditioned model of the same shape key after an ill-conditioned one: the hint must not leak a level
+    easy = O.OracleInputs(**{**inp.__dict__, "jitter": 1e-2})
+    E._JITTER_HINTS[key] = 5
+    _, _, nj3 = _run(easy)
+    assert nj3 == 0 and E._JITTER_HINTS[key] == 0
+    E._JITTER_HINTS.clear()
+
+
 def test_max_jitter_raises_like_the_reference():
     inp, _ = load_golden("ragged")
     bad = O.OracleInputs(**{**inp.__dict__, "lengthscale": torch.tensor([5.0]), "jitter": 1e-12, "maxjitter": 2})
