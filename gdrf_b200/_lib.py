@@ -50,7 +50,7 @@ class Outputs(ctypes.Structure):
 
 EXPORTS = ("gdrf_workspace_bytes", "gdrf_grad_elems", "gdrf_prologue", "gdrf_elbo_step",
            "gdrf_elbo_backward", "gdrf_marginal_mean", "gdrf_marginal_moments", "gdrf_perplexity_terms",
-           "gdrf_marginal_moments_f64", "gdrf_jitter_probe",
+           "gdrf_marginal_moments_f64", "gdrf_jitter_probe", "gdrf_moments_vjp",
            "gdrf_constrain", "gdrf_adam_step", "gdrf_clipped_adam_step", "gdrf_gather_rows", "gdrf_last_error",
            "gdrf_build_info", "gdrf_launch_count", "gdrf_profile_enable", "gdrf_profile_read")
 
@@ -83,7 +83,8 @@ def load() -> ctypes.CDLL:
     lib.gdrf_gather_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, ctypes.c_int32, ctypes.c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gdrf_jitter_probe.argtypes = [P(Shape), P(Inputs), c_double, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]
-    for n in EXPORTS[:14]:
+    lib.gdrf_moments_vjp.argtypes = [P(Shape), P(Inputs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    for n in EXPORTS[:15]:
         getattr(lib, n).restype = c_int
     lib.gdrf_launch_count.restype = ctypes.c_longlong
     lib.gdrf_profile_enable.argtypes = [c_int]

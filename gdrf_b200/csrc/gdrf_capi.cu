@@ -737,6 +737,243 @@ int gdrf_jitter_probe(const gdrf_shape* s, const gdrf_inputs* in, double jitter,
   return 0;
 }
 
+// ---- shared by gdrf_elbo_step and gdrf_moments_vjp: everything that follows the per-observation weights ----
+struct StepCtx {
+  const gdrf_shape* s;
+  const gdrf_inputs* in;
+  Plan p;
+  void* ws;
+  float* grad;       // flat gradient buffer (dS accumulates here)
+  int sms;
+  cudaStream_t st;
+  Hyper hp;
+  bool fuse_du, f16;
+  int fmt;
+  PlaneMat kxz, dwt, w, linv, st_b, linv_b, w_b, tpm, wgm;
+  unsigned *cs, *ps;
+  const float* cs_f;
+  float* dwf;
+  double* acc;
+  G6::Params g6;
+};
+
+int make_step_ctx(const gdrf_shape* s, const gdrf_inputs* in, const Plan& p, void* ws, float* grad, cudaStream_t st,
+                  bool want_grad, StepCtx& c) {
+  c.s = s; c.in = in; c.p = p; c.ws = ws; c.grad = grad; c.st = st;
+  c.sms = num_sms();
+  c.hp = make_hyper(s, in);
+  const int Mp = p.Mp;
+  c.kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
+  // Kxz is dead once W exists; its planes are reused for dWtot (two planes) plus, in fp16 mode, 128 more columns that
+  // carry g_loc for du_loc (G5)
+  c.fuse_du = (s->flags & (GDRF_FLAG_FWD_BF16 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_REF_G5)) == 0;
+  c.dwt = c.fuse_du ? plane_mat(ws, p.kxz_pl, p.ncp, Mp + 128) : c.kxz;
+  c.w = plane_mat(ws, p.w_pl, p.ncp, Mp);
+  c.linv = plane_mat(ws, p.linv_pl, Mp, Mp);
+  // 16-bit operand planes of the backward follow the forward's format: fp16 pairs (22 bits) by default
+  c.f16 = (s->flags & GDRF_FLAG_FWD_BF16) == 0;
+  c.fmt = c.f16 ? FMT_F16 : FMT_BF16;
+  c.st_b = c.f16 ? st_f16_nat(ws, p) : st_bf16(ws, p);                       // B of dW (G3)
+  c.linv_b = c.f16 ? plane_mat(ws, p.linv16_pl, Mp, Mp) : c.linv;            // B of dKxz (G4)
+  c.w_b = c.f16 ? plane_mat(ws, p.w16_pl, p.ncp, Mp) : c.w;                  // B of C5 (G5)
+  c.cs = at<unsigned>(ws, p.cs);
+  c.ps = at<unsigned>(ws, p.ps);
+  c.cs_f = at<float>(ws, p.cs);
+  c.tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)p.K * Mp);
+  c.wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)p.K * Mp);
+  c.dwf = at<float>(ws, p.dwf);
+  c.acc = at<double>(ws, p.acc);
+  // tiles of dS on / below the diagonal (i tile of 128 rows, j tile of 256 columns)
+  c.g6 = G6::Params{};
+  if (want_grad) {
+    int nt = 0;
+    // pair order: entries 2t, 2t+1 are the 128-row tiles (2 a2, b), (2 a2 + 1, b) of one 256 x 256 pair tile
+    for (int b = 0; b < p.JT; ++b)
+      for (int a2 = b; a2 < p.JT; ++a2)
+        if (256 * a2 < p.M && 256 * b < p.M)
+          for (int h = 0; h < 2; ++h) {
+            if (nt >= G6::MAX_TILES) return fail(1, "too many dS tiles%s");
+            c.g6.ta[nt] = (unsigned char)(2 * a2 + h);
+            c.g6.tb[nt] = (unsigned char)b;
+            ++nt;
+          }
+    c.g6.ntile = nt;
+  }
+  return 0;
+}
+
+// once per call, before the first chunk, when a gradient is wanted: what the backward operand scales need of u_loc
+int prepare_u(StepCtx& c, bool want_grad) {
+  if (c.f16) return pack_u(c.s, c.in, c.p, c.ws, c.st);
+  if (want_grad) {
+    CU(cudaMemsetAsync(c.ps + PS_UMAX, 0, sizeof(unsigned), c.st));
+    k_absmax<<<32, 256, 0, c.st>>>(c.in->u_loc, (long long)c.p.K * c.p.M, c.ps + PS_UMAX);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// Backward of one chunk from the per-observation weights (g_loc = d/d f_loc, g2 = 2 d/d f_var, gv0 = the share of
+// d/d f_var that reaches var0 = max(variance - |W_n|^2, 0), and their chunk maxima in cs[]) to dS, du_loc, C5, dZ,
+// d lengthscale, d variance (the Kxz part).  xs_chunk: the inputs the chunk's forward ran on.
+int chunk_backward(StepCtx& c, const float* xs_chunk, int nc, int RT) {
+  const gdrf_shape* s = c.s;
+  const gdrf_inputs* in = c.in;
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  cudaStream_t st = c.st;
+  const int sms = c.sms, K = p.K, M = p.M, Mp = p.Mp, fmt = c.fmt;
+  const bool fuse_du = c.fuse_du;
+  const Hyper& hp = c.hp;
+  unsigned *cs = c.cs, *ps = c.ps;
+  const float* cs_f = c.cs_f;
+  float* dwf = c.dwf;
+  double* acc = c.acc;
+  PlaneMat &w = c.w, &wgm = c.wgm, &tpm = c.tpm, &st_b = c.st_b, &dwt = c.dwt, &linv_b = c.linv_b, &w_b = c.w_b;
+  G6::Params& g6 = c.g6;
+  {
+    ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
+    k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm, fmt, in->variance, cs);
+    LAUNCH_CHECK();
+  }
+  {
+    G3::Params g{};
+    g.tp = tpm; g.st = st_b; g.g2 = at<float>(ws, p.g2); g.dw = dwf; g.cs = cs; g.fmt = fmt;
+    g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
+    g.varn = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_FULL_WIDTH)) ? 0 : 1;
+    g.isplit = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA)) ? 0 : 1;
+    const int n_items = g.isplit ? ((RT + 1) / 2) * 2 * p.JT : RT;
+    { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+  }
+  {
+    const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
+    CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
+                                                     in->u_loc, K, M, (int)p.ncp, dwt, fmt, in->variance, cs, ps,
+                                                     fuse_du ? (K + 63) / 64 : 0);
+    LAUNCH_CHECK();
+  }
+  if (!fuse_du)
+    if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
+  {
+    g6.wg = wgm; g6.tp = tpm; g6.ds = c.grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
+    g6.fmt = fmt; g6.inv_scale = cs_f + CS_SG_INV;
+    // (topic, tile) items in units of CTA pairs: as many whole rounds of the sms / 2 pairs as fit run unsplit; the
+    // items of the last, partial round are cut along the observations so that this round is full as well
+    const int base = K * g6.ntile, pairs = base / 2, clusters = sms / 2, NBt = 2 * RT;
+    int whole_pairs = (pairs / clusters) * clusters, sp;
+    if (pairs - whole_pairs == 0) sp = 1;
+    else sp = clusters / (pairs - whole_pairs);
+    if (sp < 1) sp = 1;
+    if (sp > 8 && whole_pairs > 0) sp = 8;
+    if (sp > NBt) sp = NBt;
+    const int per = (NBt + sp - 1) / sp;
+    sp = (NBt + per - 1) / per;
+    if (sp == 1) whole_pairs = pairs;
+    g6.n_whole = 2 * whole_pairs; g6.tail_sp = sp; g6.tail_per = per;
+    const int n_items6 = g6.n_whole + (base - g6.n_whole) * sp;
+    { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, n_items6, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
+  }
+  {
+    auto fill = [&](auto& g) {
+      g.dwt = dwt; g.linv = linv_b; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+      g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
+    };
+    ProfScope ps(PK_G4, st);
+    ++g_launches;
+    if ((s->flags & (GDRF_FLAG_REF_G4 | GDRF_FLAG_SINGLE_CTA)) != 0) {
+      G4T<128>::Params g{}; fill(g);
+      CU(launch_gemm<G4T<128>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st));
+    } else {
+      G4T<256>::Params g{}; fill(g);
+      CU(launch_gemm2<G4T<256>>(g, RT, sms, st));
+    }
+  }
+  {
+    const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
+#define GDRF_KXZ_BACKWARD(DT, KID)                                                                  \
+k_kxz_backward<DT, KID><<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(      \
+    dwf, Mp, xs_chunk, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc)
+    GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_BACKWARD);
+#undef GDRF_KXZ_BACKWARD
+    LAUNCH_CHECK();
+  }
+  {
+    const int NBt = 2 * RT;
+    auto fill = [&](auto& g, int splits) {
+      g.dwt = dwt; g.w = w_b; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp;
+      g.MTW = p.MT; g.MT = p.MT + (fuse_du ? 2 : 0);
+      g.du = fuse_du ? at<double>(ws, p.du) : nullptr; g.inv_scale_l = cs_f + CS_SL_INV; g.K = K; g.M = M;
+      g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
+      if (splits > NBt) splits = NBt;
+      if (splits < 1) splits = 1;
+      const int per = (NBt + splits - 1) / splits;
+      g.splits = (NBt + per - 1) / per;
+      g.nb_per_split = per;
+    };
+    ProfScope ps(PK_G5, st);
+    ++g_launches;
+    if ((s->flags & (GDRF_FLAG_REF_G5 | GDRF_FLAG_SINGLE_CTA)) != 0) {
+      const int base = p.MT * p.MT;
+      G5T<128>::Params g{}; fill(g, base >= 2 * sms ? 1 : (2 * sms + base - 1) / base);
+      CU(launch_gemm<G5T<128>>(g, base * g.splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
+    } else {
+      // 256 x 256 pair tiles: as many splits of the observation range as fill the sms / 2 CTA pairs once
+      const int base = (p.MT + (fuse_du ? 2 : 0)) * (Mp / 256), pairs = base / 2, clusters = sms / 2;
+      G5T<256>::Params g{}; fill(g, pairs >= clusters ? 1 : clusters / pairs);
+      CU(launch_gemm2<G5T<256>>(g, base * g.splits, sms, st));
+    }
+  }
+  return 0;
+}
+
+// Per-step tail of the gradient: Cholesky adjoint of C5 -> Kuu adjoint -> (Z, lengthscale, variance), the Dirichlet
+// prior, and the assembly of the small gradients behind dS in the flat buffer.
+int step_epilogue(StepCtx& c, bool want_grad) {
+  const gdrf_shape* s = c.s;
+  const gdrf_inputs* in = c.in;
+  const Plan& p = c.p;
+  void* ws = c.ws;
+  cudaStream_t st = c.st;
+  const int K = p.K, M = p.M, Mp = p.Mp;
+  const Hyper& hp = c.hp;
+  double* acc = c.acc;
+  if (want_grad) {
+    // Cholesky adjoint (Murray 2016; torch cholesky_backward):  G_L = -tril(L^-T C5),
+    // Phi = tril(L^T G_L) with halved diagonal, G_K = L^-T Phi L^-1, symmetrised inside k_kuu_backward.
+    double* L = at<double>(ws, p.L64);
+    double* Linv = at<double>(ws, p.Linv64);
+    double* tA = at<double>(ws, p.tmpA);
+    double* tB = at<double>(ws, p.tmpB);
+    const dim3 g2d(ceil_div(Mp, 256), Mp);
+    // every factor is triangular: (L^-T X)[i, j] sums over k >= i, a lower X over k >= j, X L^-1 over k >= j
+    dgemm<true, false, 1, true>(Linv, at<double>(ws, p.c5), tA, Mp, st);     // lower part of L^-T C5
+    k_tril_op<<<g2d, 256, 0, st>>>(tA, Mp, 0);
+    dgemm<true, false, 1, true>(L, tA, tB, Mp, st);                          // lower part of L^T G_L
+    k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
+    dgemm<true, false, 3, false>(Linv, tB, tA, Mp, st);                      // L^-T Phi, Phi lower
+    dgemm<false, false, 2, false>(tA, Linv, tB, Mp, st);                     // (...) L^-1
+    g_launches += 5;   // 4 fp64 products + 2 tril ops, one counted by LAUNCH_CHECK
+    LAUNCH_CHECK();
+    k_kuu_backward<<<M, 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
+    LAUNCH_CHECK();
+  }
+  const int include_prior = (s->flags & GDRF_FLAG_INCLUDE_PRIOR) ? 1 : 0;
+  if (include_prior) {
+    k_prior<<<K, 128, 0, st>>>(in->phi, in->beta, K, p.V, acc);
+    LAUNCH_CHECK();
+  }
+  if (want_grad) {
+    const int has_alpha = s->kernel_id == KERNEL_RQ ? 1 : 0;
+    const long long small = (long long)K * M + (long long)K * p.V + (long long)M * p.D + 2 + s->ls_dim + has_alpha;
+    k_assemble<<<(int)((small + 255) / 256), 256, 0, st>>>(K, M, p.V, p.D, s->ls_dim, has_alpha, include_prior, in->phi, in->beta,
+                                                           acc, at<double>(ws, p.ck), at<double>(ws, p.du),
+                                                           at<double>(ws, p.dphi), at<double>(ws, p.dz), c.grad);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_outputs* out, void* ws, size_t ws_bytes,
                    gdrf_stream_t stream) {
   Plan p;
@@ -750,8 +987,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   if (s->n_offset < 0 || s->n_offset + s->n_local > s->n_eps) return fail(1, "eps window out of range%s");
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = num_sms();
-  const Hyper hp = make_hyper(s, in);
-  const int K = p.K, M = p.M, Mp = p.Mp;
+  const int K = p.K, M = p.M;
 
   const int P = s->n_particles > 1 ? s->n_particles : 1;
   const double inv_p = 1.0 / P;
@@ -761,27 +997,11 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
     CU(cudaMemsetAsync(at<char>(ws, p.acc), 0, (size_t)p.zero_bytes, st));
     if (want_grad) CU(cudaMemsetAsync(out->grad, 0, sizeof(float) * (size_t)K * M * M, st));
   }
-
-  PlaneMat kxz = plane_mat(ws, p.kxz_pl, p.ncp, Mp);
-  // Kxz is dead once W exists; its planes are reused for dWtot (two planes) plus, in fp16 mode, 128 more columns that
-  // carry g_loc for du_loc (G5)
-  const bool fuse_du = (s->flags & (GDRF_FLAG_FWD_BF16 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_REF_G5)) == 0;
-  PlaneMat dwt = fuse_du ? plane_mat(ws, p.kxz_pl, p.ncp, Mp + 128) : kxz;
-  PlaneMat w = plane_mat(ws, p.w_pl, p.ncp, Mp);
-  PlaneMat linv = plane_mat(ws, p.linv_pl, Mp, Mp);
-  // 16-bit operand planes of the backward follow the forward's format: fp16 pairs (22 bits) by default
-  const bool f16 = (s->flags & GDRF_FLAG_FWD_BF16) == 0;
-  const int fmt = f16 ? FMT_F16 : FMT_BF16;
-  PlaneMat st_b = f16 ? st_f16_nat(ws, p) : st_bf16(ws, p);                       // B of dW (G3)
-  PlaneMat linv_b = f16 ? plane_mat(ws, p.linv16_pl, Mp, Mp) : linv;              // B of dKxz (G4)
-  PlaneMat w_b = f16 ? plane_mat(ws, p.w16_pl, p.ncp, Mp) : w;                    // B of C5 (G5)
-  unsigned* cs = at<unsigned>(ws, p.cs);
-  unsigned* ps = at<unsigned>(ws, p.ps);
-  const float* cs_f = at<float>(ws, p.cs);
-  PlaneMat tpm = plane_mat(ws, p.tp_pl, p.ncp, (long long)K * Mp);
-  PlaneMat wgm = plane_mat(ws, p.wg_pl, p.ncp, (long long)K * Mp);
-  float* dwf = at<float>(ws, p.dwf);
-  double* acc = at<double>(ws, p.acc);
+  StepCtx c;
+  if (int e = make_step_ctx(s, in, p, ws, out->grad, st, want_grad, c)) return e;
+  const Hyper& hp = c.hp;
+  unsigned* cs = c.cs;
+  double* acc = c.acc;
 
   if (!cont) {
     k_phisum<<<K, 128, 0, st>>>(in->phi, K, p.V, at<float>(ws, p.phisum));
@@ -792,30 +1012,7 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       k_lfact_table<<<LT_LFACT / 256, 256, 0, st>>>(at<float>(ws, p.lfact));
       LAUNCH_CHECK();
     }
-    if (f16) {
-      if (int e = pack_u(s, in, p, ws, st)) return e;
-    } else if (want_grad) {
-      CU(cudaMemsetAsync(ps + PS_UMAX, 0, sizeof(unsigned), st));
-      k_absmax<<<32, 256, 0, st>>>(in->u_loc, (long long)K * M, ps + PS_UMAX);
-      LAUNCH_CHECK();
-    }
-  }
-
-  // tiles of dS on / below the diagonal (i tile of 128 rows, j tile of 256 columns)
-  G6::Params g6{};
-  if (want_grad) {
-    int nt = 0;
-    // pair order: entries 2t, 2t+1 are the 128-row tiles (2 a2, b), (2 a2 + 1, b) of one 256 x 256 pair tile
-    for (int b = 0; b < p.JT; ++b)
-      for (int a2 = b; a2 < p.JT; ++a2)
-        if (256 * a2 < M && 256 * b < M)
-          for (int h = 0; h < 2; ++h) {
-            if (nt >= G6::MAX_TILES) return fail(1, "too many dS tiles%s");
-            g6.ta[nt] = (unsigned char)(2 * a2 + h);
-            g6.tb[nt] = (unsigned char)b;
-            ++nt;
-          }
-    g6.ntile = nt;
+    if (int e = prepare_u(c, want_grad)) return e;
   }
 
   for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
@@ -847,135 +1044,11 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
       LAUNCH_CHECK();
     }
     if (!want_grad) continue;
-    {
-      ProfScope ps(PK_G2B, st);   // slot reused: the row-weighted copies of W
-      k_scale_w<<<dim3(p.MB, RT), 256, 0, st>>>(w, at<float>(ws, p.g2), K, p.MB, (int)p.ncp, wgm, fmt, in->variance, cs);
-      LAUNCH_CHECK();
-    }
-    {
-      G3::Params g{};
-      g.tp = tpm; g.st = st_b; g.g2 = at<float>(ws, p.g2); g.dw = dwf; g.cs = cs; g.fmt = fmt;
-      g.RT = RT; g.MB = p.MB; g.K = K; g.JT = p.JT; g.Mp = Mp; g.ncp = (int)p.ncp;
-      g.varn = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA | GDRF_FLAG_FULL_WIDTH)) ? 0 : 1;
-      g.isplit = (s->flags & (GDRF_FLAG_REF_G3 | GDRF_FLAG_SINGLE_CTA)) ? 0 : 1;
-      const int n_items = g.isplit ? ((RT + 1) / 2) * 2 * p.JT : RT;
-      { ProfScope ps(PK_G3, st); ++g_launches; CU(launch_big<G3>(g, n_items, sms, (s->flags & GDRF_FLAG_REF_G3) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
-    }
-    {
-      const size_t smem = sizeof(float) * (size_t)K * (72 + 128);
-      CU(cudaFuncSetAttribute(k_dw_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_dw_finalize<<<dim3(p.MB, RT), 256, smem, st>>>(w, dwf, Mp, at<float>(ws, p.g_loc), at<float>(ws, p.gv0),
-                                                       in->u_loc, K, M, (int)p.ncp, dwt, fmt, in->variance, cs, ps,
-                                                       fuse_du ? (K + 63) / 64 : 0);
-      LAUNCH_CHECK();
-    }
-    if (!fuse_du)
-      if (int e = launch_du(p, w, RT, ws, sms, st)) return e;
-    {
-      g6.wg = wgm; g6.tp = tpm; g6.ds = out->grad; g6.RT = RT; g6.MB = p.MB; g6.K = K; g6.M = M;
-      g6.fmt = fmt; g6.inv_scale = cs_f + CS_SG_INV;
-      // (topic, tile) items in units of CTA pairs: as many whole rounds of the sms / 2 pairs as fit run unsplit; the
-      // items of the last, partial round are cut along the observations so that this round is full as well
-      const int base = K * g6.ntile, pairs = base / 2, clusters = sms / 2, NBt = 2 * RT;
-      int whole_pairs = (pairs / clusters) * clusters, sp;
-      if (pairs - whole_pairs == 0) sp = 1;
-      else sp = clusters / (pairs - whole_pairs);
-      if (sp < 1) sp = 1;
-      if (sp > 8 && whole_pairs > 0) sp = 8;
-      if (sp > NBt) sp = NBt;
-      const int per = (NBt + sp - 1) / sp;
-      sp = (NBt + per - 1) / per;
-      if (sp == 1) whole_pairs = pairs;
-      g6.n_whole = 2 * whole_pairs; g6.tail_sp = sp; g6.tail_per = per;
-      const int n_items6 = g6.n_whole + (base - g6.n_whole) * sp;
-      { ProfScope ps(PK_G6, st); ++g_launches; CU(launch_big<G6>(g6, n_items6, sms, (s->flags & GDRF_FLAG_REF_G6) != 0, (s->flags & GDRF_FLAG_SINGLE_CTA) != 0, st)); }
-    }
-    {
-      auto fill = [&](auto& g) {
-        g.dwt = dwt; g.linv = linv_b; g.dkxz = dwf; g.RT = RT; g.MB = p.MB; g.Mp = Mp;
-        g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
-      };
-      ProfScope ps(PK_G4, st);
-      ++g_launches;
-      if ((s->flags & (GDRF_FLAG_REF_G4 | GDRF_FLAG_SINGLE_CTA)) != 0) {
-        G4T<128>::Params g{}; fill(g);
-        CU(launch_gemm<G4T<128>>(g, RT, sms, (s->flags & GDRF_FLAG_REF_G4) != 0, st));
-      } else {
-        G4T<256>::Params g{}; fill(g);
-        CU(launch_gemm2<G4T<256>>(g, RT, sms, st));
-      }
-    }
-    {
-      const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
-#define GDRF_KXZ_BACKWARD(DT, KID)                                                                  \
-  k_kxz_backward<DT, KID><<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(      \
-      dwf, Mp, in->xs + n0 * p.D, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc)
-      GDRF_DISPATCH_DK(p.D, hp.kid, GDRF_KXZ_BACKWARD);
-#undef GDRF_KXZ_BACKWARD
-      LAUNCH_CHECK();
-    }
-    {
-      const int NBt = 2 * RT;
-      auto fill = [&](auto& g, int splits) {
-        g.dwt = dwt; g.w = w_b; g.c5 = at<double>(ws, p.c5); g.RT = RT; g.MB = p.MB; g.Mp = Mp;
-        g.MTW = p.MT; g.MT = p.MT + (fuse_du ? 2 : 0);
-        g.du = fuse_du ? at<double>(ws, p.du) : nullptr; g.inv_scale_l = cs_f + CS_SL_INV; g.K = K; g.M = M;
-        g.fmt = fmt; g.inv_scale = cs_f + CS_SD_INV;
-        if (splits > NBt) splits = NBt;
-        if (splits < 1) splits = 1;
-        const int per = (NBt + splits - 1) / splits;
-        g.splits = (NBt + per - 1) / per;
-        g.nb_per_split = per;
-      };
-      ProfScope ps(PK_G5, st);
-      ++g_launches;
-      if ((s->flags & (GDRF_FLAG_REF_G5 | GDRF_FLAG_SINGLE_CTA)) != 0) {
-        const int base = p.MT * p.MT;
-        G5T<128>::Params g{}; fill(g, base >= 2 * sms ? 1 : (2 * sms + base - 1) / base);
-        CU(launch_gemm<G5T<128>>(g, base * g.splits, sms, (s->flags & GDRF_FLAG_REF_G5) != 0, st));
-      } else {
-        // 256 x 256 pair tiles: as many splits of the observation range as fill the sms / 2 CTA pairs once
-        const int base = (p.MT + (fuse_du ? 2 : 0)) * (Mp / 256), pairs = base / 2, clusters = sms / 2;
-        G5T<256>::Params g{}; fill(g, pairs >= clusters ? 1 : clusters / pairs);
-        CU(launch_gemm2<G5T<256>>(g, base * g.splits, sms, st));
-      }
-    }
+    if (int e = chunk_backward(c, in->xs + n0 * p.D, nc, RT)) return e;
   }
 
   if (partial) return 0;
-  if (want_grad) {
-    // Cholesky adjoint (Murray 2016; torch cholesky_backward):  G_L = -tril(L^-T C5),
-    // Phi = tril(L^T G_L) with halved diagonal, G_K = L^-T Phi L^-1, symmetrised inside k_kuu_backward.
-    double* L = at<double>(ws, p.L64);
-    double* Linv = at<double>(ws, p.Linv64);
-    double* tA = at<double>(ws, p.tmpA);
-    double* tB = at<double>(ws, p.tmpB);
-    const dim3 g2d(ceil_div(Mp, 256), Mp);
-    // every factor is triangular: (L^-T X)[i, j] sums over k >= i, a lower X over k >= j, X L^-1 over k >= j
-    dgemm<true, false, 1, true>(Linv, at<double>(ws, p.c5), tA, Mp, st);     // lower part of L^-T C5
-    k_tril_op<<<g2d, 256, 0, st>>>(tA, Mp, 0);
-    dgemm<true, false, 1, true>(L, tA, tB, Mp, st);                          // lower part of L^T G_L
-    k_tril_op<<<g2d, 256, 0, st>>>(tB, Mp, 1);
-    dgemm<true, false, 3, false>(Linv, tB, tA, Mp, st);                      // L^-T Phi, Phi lower
-    dgemm<false, false, 2, false>(tA, Linv, tB, Mp, st);                     // (...) L^-1
-    g_launches += 5;   // 4 fp64 products + 2 tril ops, one counted by LAUNCH_CHECK
-    LAUNCH_CHECK();
-    k_kuu_backward<<<M, 128, 0, st>>>(tB, Mp, in->z, M, hp, at<double>(ws, p.dz), acc);
-    LAUNCH_CHECK();
-  }
-  const int include_prior = (s->flags & GDRF_FLAG_INCLUDE_PRIOR) ? 1 : 0;
-  if (include_prior) {
-    k_prior<<<K, 128, 0, st>>>(in->phi, in->beta, K, p.V, acc);
-    LAUNCH_CHECK();
-  }
-  if (want_grad) {
-    const int has_alpha = s->kernel_id == KERNEL_RQ ? 1 : 0;
-    const long long small = (long long)K * M + (long long)K * p.V + (long long)M * p.D + 2 + s->ls_dim + has_alpha;
-    k_assemble<<<(int)((small + 255) / 256), 256, 0, st>>>(K, M, p.V, p.D, s->ls_dim, has_alpha, include_prior, in->phi, in->beta,
-                                                           acc, at<double>(ws, p.ck), at<double>(ws, p.du),
-                                                           at<double>(ws, p.dphi), at<double>(ws, p.dz), out->grad);
-    LAUNCH_CHECK();
-  }
+  if (int e = step_epilogue(c, want_grad)) return e;
   float* tail = nullptr;
   if (want_grad && (s->flags & GDRF_FLAG_TERMS_IN_GRAD)) {
     int64_t ge = 0;
@@ -985,6 +1058,37 @@ int gdrf_elbo_step(const gdrf_shape* s, const gdrf_inputs* in, const gdrf_output
   k_copy_terms<<<1, 32, 0, st>>>(acc, out->terms, tail);
   LAUNCH_CHECK();
   return 0;
+}
+
+int gdrf_moments_vjp(const gdrf_shape* s, const gdrf_inputs* in, const float* up_floc, const float* up_fvar, float* grad,
+                     void* ws, size_t ws_bytes, gdrf_stream_t stream) {
+  Plan p;
+  if (int e = make_plan(s, p)) return e;
+  if (int e = check_device()) return e;
+  if (!in || !ws || !up_floc || !grad) return fail(1, "null pointer argument%s");
+  if (!in->u_scale_tril) return fail(1, "gdrf_moments_vjp needs u_scale_tril (packed by gdrf_prologue)%s");
+  if (s->kernel_id == KERNEL_RQ && !in->scale_mixture) return fail(1, "the RationalQuadratic kernel needs in->scale_mixture%s");
+  if (ws_bytes < p.total) return fail(1, "workspace too small%s (need %lld bytes)", "", (long long)p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = p.K, M = p.M;
+  CU(cudaMemsetAsync(at<char>(ws, p.acc), 0, (size_t)p.zero_bytes, st));
+  CU(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)K * M * M, st));
+  gdrf_shape sh = *s;                       // no prior, no terms
+  sh.flags = (s->flags | GDRF_FLAG_WANT_GRAD) & ~(GDRF_FLAG_INCLUDE_PRIOR | GDRF_FLAG_TERMS_IN_GRAD | GDRF_FLAG_CONTINUE | GDRF_FLAG_PARTIAL);
+  StepCtx c;
+  if (int e = make_step_ctx(&sh, in, p, ws, grad, st, true, c)) return e;
+  if (int e = prepare_u(c, true)) return e;
+  for (long long n0 = 0; n0 < s->n_local; n0 += p.chunk_rows) {
+    const int nc = (int)((s->n_local - n0 < p.chunk_rows) ? (s->n_local - n0) : p.chunk_rows);
+    const int RT = (nc + 127) / 128;
+    if (int e = chunk_forward(&sh, in, p, ws, n0, nc, RT, true, true, c.sms, st)) return e;
+    k_vjp_weights<<<RT * 4, 256, 0, st>>>(nc, (int)p.ncp, K, n0, s->n_local, up_floc, up_fvar, at<double>(ws, p.wsq), c.hp,
+                                          at<float>(ws, p.g_loc), at<float>(ws, p.g2), at<float>(ws, p.gv0), c.acc,
+                                          RT * 128, c.cs);
+    LAUNCH_CHECK();
+    if (int e = chunk_backward(c, in->xs + n0 * p.D, nc, RT)) return e;
+  }
+  return step_epilogue(c, true);
 }
 
 int gdrf_elbo_backward(const float* grad, int64_t elems, const float* scale_dev, float scale_host, float* dst,

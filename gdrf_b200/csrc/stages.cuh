@@ -674,6 +674,63 @@ __global__ void __launch_bounds__(256) k_obs_finalize(int nc, int ncp, int K, lo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward weights of one chunk from UPSTREAM gradients of the marginal moments (gdrf_moments_vjp: the vector-Jacobian
+// product of SparseGDRF.forward, sparse_gdrf.py:277-319) instead of from the ELBO's per-observation chain:
+//   g_loc = d/d f_loc,  g2 = 2 d/d f_var,  gv0_n = sum_k d/d f_var[k, n] where var0 = max(variance - |W_n|^2, 0) is open
+// (f_var = var0 + q), the direct d/d variance, and the chunk maxima that size the fp16 operand scales.  Same layout and
+// thread map as k_obs_finalize (8 lanes per observation); padding rows are zeroed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vjp_weights(int nc, int ncp, int K, long long n0, long long n_stride,
+                                                     const float* __restrict__ up_loc, const float* __restrict__ up_var,
+                                                     const double* __restrict__ wsq, Hyper hp,
+                                                     float* __restrict__ g_loc, float* __restrict__ g2,
+                                                     float* __restrict__ gv0, double* __restrict__ acc, int npad,
+                                                     unsigned* __restrict__ cs) {
+  __shared__ double scratch[32];
+  __shared__ unsigned smax[3];
+  if (threadIdx.x < 3) smax[threadIdx.x] = 0u;
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int n = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool live = n < nc;
+  float mx_g2 = 0.f, mx_gl = 0.f, gsum = 0.f;
+  if (n < npad)
+    for (int k = sub; k < K; k += 8) {
+      const long long o = (long long)k * ncp + n, u = (long long)k * n_stride + n0 + n;
+      const float gl = live ? up_loc[u] : 0.f;
+      const float gv = (live && up_var) ? up_var[u] : 0.f;
+      g_loc[o] = gl;
+      g2[o] = 2.f * gv;
+      gsum += gv;
+      mx_g2 = fmaxf(mx_g2, fabsf(2.f * gv));
+      mx_gl = fmaxf(mx_gl, fabsf(gl));
+    }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+  double dvar = 0.0;
+  if (sub == 0 && n < npad) {
+    float g0 = 0.f;
+    if (live && ((double)hp.variance[0] - wsq[n]) >= 0.0) g0 = gsum;
+    dvar = (double)g0;
+    gv0[n] = g0;
+    if (g0 != 0.f) atomicMax(&smax[2], __float_as_uint(fabsf(g0)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx_g2 = fmaxf(mx_g2, __shfl_xor_sync(0xffffffffu, mx_g2, o));
+    mx_gl = fmaxf(mx_gl, __shfl_xor_sync(0xffffffffu, mx_gl, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx_g2 > 0.f) atomicMax(&smax[0], __float_as_uint(mx_g2));
+    if (mx_gl > 0.f) atomicMax(&smax[1], __float_as_uint(mx_gl));
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && smax[threadIdx.x] != 0u) atomicMax(cs + CS_G2MAX + threadIdx.x, smax[threadIdx.x]);
+  dvar = block_sum(dvar, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[ACC_DVAR], dvar);
+}
+
+// ---------------------------------------------------------------------------------------------
 // du_loc[k, m] += sum_n g_loc[k, n] W[n, m]     (adjoint of f_loc = W u_loc^T)
 // One CTA per (64-column block, slab of row tiles).  Each 128-row tile of W is rebuilt from its planes into shared
 // memory; a thread owns a 4-column x 8-topic register tile and a slice of the rows (4 rows per step: one 16-byte

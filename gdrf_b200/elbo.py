@@ -35,6 +35,17 @@ def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
     return _COPY_STREAMS[key]
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """Second compute stream (the speculative jitter probe runs on it next to the full prologue), one per device."""
+    key = device.index or 0
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """One workspace per (device, stream): the C ABI is re-entrant per (workspace, stream) (include/gdrf_b200.h), so two
     modules driven on two streams of one device must not share scratch memory."""
@@ -114,11 +125,11 @@ class _Call:
         _lib.check(_lib.load().gdrf_prologue(ctypes.byref(self.shape), ctypes.byref(self.inputs), float(jitter), nj,
                                              self.workspace.data_ptr(), self.ws_bytes, self.stream, status.data_ptr()))
 
-    def _probe(self, jitter: float, first: int, count: int, status: torch.Tensor) -> None:
+    def _probe(self, jitter: float, first: int, count: int, status: torch.Tensor, stream=None) -> None:
         """fp32 'does the reference's factorisation fail?' for levels first .. first+count-1 in one launch chain."""
         _lib.check(_lib.load().gdrf_jitter_probe(ctypes.byref(self.shape), ctypes.byref(self.inputs), float(jitter),
-                                                 first, count, self.workspace.data_ptr(), self.ws_bytes, self.stream,
-                                                 status.data_ptr()))
+                                                 first, count, self.workspace.data_ptr(), self.ws_bytes,
+                                                 self.stream if stream is None else stream, status.data_ptr()))
 
     def prologue(self, jitter: float, maxjitter: int) -> int:
         """jittercholesky (utils.py:27-40): the first level njitter < maxjitter whose factorisation succeeds.
@@ -147,8 +158,14 @@ class _Call:
         known = {}                           # level -> fp32 status already probed
         hint = _JITTER_HINTS.get(key, 0)
         if fp32_mode and 0 < hint < maxjitter and hint <= _lib.PROBE_MAX:
-            self._probe(jitter, 0, hint, status[1:])
+            # the probe (its own scratch region of the workspace) runs on a side stream next to the full prologue: both
+            # are latency-bound chains of small launches
+            main = torch.cuda.current_stream(self.device)
+            side = _side_stream(self.device)
+            side.wait_stream(main)
+            self._probe(jitter, 0, hint, status[1:], stream=side.cuda_stream)
             self._full_prologue(jitter, hint, status)
+            main.wait_stream(side)
             st = status[:1 + hint].tolist()  # one read-back for the probe and the prologue
             known = {lvl: st[1 + lvl] for lvl in range(hint)}
             if all(v > 0 for v in known.values()):
@@ -427,6 +444,84 @@ def marginal_moments(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: 
     _lib.check(fn(ctypes.byref(call.shape), ctypes.byref(call.inputs), floc.data_ptr(), fvar.data_ptr(),
                   call.workspace.data_ptr(), call.ws_bytes, call.stream))
     return floc, fvar
+
+
+class MarginalMoments(torch.autograd.Function):
+    """(f_loc, f_var) = MarginalMoments.apply(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel_id, jitter,
+    maxjitter, flags, chunk_rows, scale_mixture, f64) -- the sparse-GP marginal of ``SparseGDRF.forward`` /
+    ``gp.util.conditional(..., full_cov=False, whiten=True)`` (sparse_gdrf.py:277-319, :334-344), differentiable with
+    respect to the constrained Z, variance, lengthscale, u_loc, u_scale_tril (and scale_mixture) the way torch autograd
+    differentiates the reference's: the backward is ``gdrf_moments_vjp`` (the contractions of ``gdrf_elbo_step``'s
+    backward, fed with the upstream gradients instead of the ELBO's per-observation weights)."""
+
+    @staticmethod
+    def forward(ctx, xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel_id: int, jitter: float, maxjitter: int,
+                flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0, scale_mixture=None, f64: bool = False):
+        K, M = u_loc.shape
+        N = xs.shape[0]
+        dev = xs.device
+        call = _moments_call(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel_id, flags, chunk_rows, scale_mixture)
+        ctx.njitter = call.prologue(jitter, maxjitter)
+        dtype = torch.float64 if f64 else torch.float32
+        floc = torch.empty(K, N, dtype=dtype, device=dev)
+        fvar = torch.empty(K, N, dtype=dtype, device=dev)
+        fn = _lib.load().gdrf_marginal_moments_f64 if f64 else _lib.load().gdrf_marginal_moments
+        _lib.check(fn(ctypes.byref(call.shape), ctypes.byref(call.inputs), floc.data_ptr(), fvar.data_ptr(),
+                      call.workspace.data_ptr(), call.ws_bytes, call.stream))
+        ctx.save_for_backward(xs, Z, variance, lengthscale, u_loc, u_scale_tril,
+                              *( [scale_mixture] if scale_mixture is not None else []))
+        ctx.has_sm = scale_mixture is not None
+        ctx.args = (int(kernel_id), float(jitter), int(maxjitter), int(call.shape.flags), int(chunk_rows))
+        return floc, fvar
+
+    @staticmethod
+    def backward(ctx, g_floc, g_fvar):
+        saved = ctx.saved_tensors
+        xs, Z, variance, lengthscale, u_loc, u_scale_tril = saved[:6]
+        sm = saved[6] if ctx.has_sm else None
+        kernel_id, jitter, maxjitter, flags, chunk_rows = ctx.args
+        K, M = u_loc.shape
+        call = _moments_call(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel_id,
+                             flags & ~_lib.FLAG_FWD_BF16, chunk_rows, sm)
+        call.prologue(jitter, maxjitter)      # same parameters: lands on the level of the forward
+        up_loc = torch.zeros(K, xs.shape[0], dtype=torch.float32, device=xs.device) if g_floc is None \
+            else g_floc.detach().to(torch.float32).contiguous()
+        up_var = None if g_fvar is None else g_fvar.detach().to(torch.float32).contiguous()
+        grad = torch.empty(_lib.grad_elems(call.shape), dtype=torch.float32, device=xs.device)
+        _lib.check(_lib.load().gdrf_moments_vjp(ctypes.byref(call.shape), ctypes.byref(call.inputs), up_loc.data_ptr(),
+                                                None if up_var is None else up_var.data_ptr(), grad.data_ptr(),
+                                                call.workspace.data_ptr(), call.ws_bytes, call.stream))
+        g = split_grad(grad, K, M, 1, xs.shape[1], call.shape.ls_dim)
+        need = ctx.needs_input_grad
+        outs = [None,
+                g["Z"].to(Z.dtype) if need[1] else None,
+                g["variance"].reshape(variance.shape).to(variance.dtype) if need[2] else None,
+                g["lengthscale"].reshape(lengthscale.shape).to(lengthscale.dtype) if need[3] else None,
+                g["u_loc"].to(u_loc.dtype) if need[4] else None,
+                g["u_scale_tril"].to(u_scale_tril.dtype) if need[5] else None,
+                None, None, None, None, None,
+                g["scale_mixture"].reshape(sm.shape).to(sm.dtype) if (sm is not None and need[11]) else None,
+                None]
+        return tuple(outs)
+
+
+def _moments_call(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel_id, flags, chunk_rows, scale_mixture):
+    """A _Call for the moments-only entry points: the observation-side inputs they do not read are one-column dummies."""
+    K = u_loc.shape[0]
+    N = xs.shape[0]
+    dev = xs.device
+    return _Call(xs, torch.zeros(N, 1, dtype=torch.int32, device=dev), Z, variance, lengthscale, u_loc, u_scale_tril,
+                 torch.ones((), device=dev), torch.ones(K, 1, device=dev), torch.ones(K, 1, device=dev),
+                 torch.empty(K, N, device=dev),
+                 kernel_id, 0, flags, chunk_rows, scale_mixture)
+
+
+def marginal_moments_diff(xs, Z, variance, lengthscale, u_loc, u_scale_tril, kernel: str = "rbf", jitter: float = 1e-8,
+                          maxjitter: int = 5, flags: int = _lib.FLAG_CHOL_FP32_STATUS, chunk_rows: int = 0,
+                          scale_mixture=None, dtype=torch.float32):
+    """:func:`marginal_moments` as a differentiable op (see :class:`MarginalMoments`)."""
+    return MarginalMoments.apply(xs, Z, variance, lengthscale, u_loc, u_scale_tril, _lib.KERNEL_IDS[kernel], jitter,
+                                 maxjitter, flags, chunk_rows, scale_mixture, dtype == torch.float64)
 
 
 def perplexity_from_mean(floc: torch.Tensor, ws: torch.Tensor, phi: torch.Tensor) -> torch.Tensor:

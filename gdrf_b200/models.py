@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .elbo import GDRFElbo, marginal_mean, marginal_moments, perplexity_from_mean
+from .elbo import GDRFElbo, MarginalMoments, marginal_mean, marginal_moments, perplexity_from_mean
 from .kernels import kernel_kind
 
 try:  # optional: the reference's inference driver
@@ -72,7 +72,7 @@ class SparseMultinomialGDRF(nn.Module):
                  inducing_init: str = "random", mean_function: Callable = None, link_function: Callable = None,
                  noise: Optional[float] = None, device: str = "cpu", whiten: bool = True, jitter: float = 1e-8,
                  maxjitter: int = 5, randomize_wt_matrix: bool = False, randomize_metric=None,
-                 randomize_iters: int = 100, **kwargs):
+                 randomize_iters: int = 100, reference_double_scale: bool = False, **kwargs):
         super().__init__()
         if mean_function is not None or link_function is not None:
             raise NotImplementedError("only the default zero mean and softmax link are accelerated")
@@ -88,6 +88,9 @@ class SparseMultinomialGDRF(nn.Module):
         self._n_dims = len(world)
         self._unit_world = all(float(b[0]) == 0.0 and float(b[1]) == 1.0 for b in world)
         self._warned_world = False
+        # opt-in (not a reference keyword): reproduce the reference guide's second scale() for a non-unit world
+        # (sparse_gdrf.py:380) -- see elbo()
+        self._reference_double_scale = bool(reference_double_scale)
         self._kernel = kernel.to(self.device)
         self._kernel_kind = kernel_kind(kernel)
         if isinstance(dirichlet_param, float):
@@ -236,12 +239,15 @@ class SparseMultinomialGDRF(nn.Module):
         xs = xs.to(self.device)
         self._check_Xnew_shape(xs)
         x = xs.float() if scaled else self._scaled(xs)
-        if not scaled and not self._unit_world and not self._warned_world:
+        double_scale = self._reference_double_scale and not scaled and not self._unit_world
+        if not scaled and not self._unit_world and not self._warned_world and not double_scale:
             # sparse_gdrf.py:380: the reference's guide applies scale() a second time on top of scale_decorator, so
             # for a world other than [0,1]^D its guide and model condition on different inputs.  train() always
-            # hands over unit-cube data (train_script.py:263-271); here xs is scaled once for both.
+            # hands over unit-cube data (train_script.py:263-271); here xs is scaled once for both unless the module
+            # was built with reference_double_scale=True.
             warnings.warn("world is not the unit cube: the reference's guide rescales xs twice "
-                          "(sparse_gdrf.py:380); gdrf_b200 scales once for model and guide")
+                          "(sparse_gdrf.py:380); gdrf_b200 scales once for model and guide "
+                          "(reference_double_scale=True reproduces the reference)")
             self._warned_world = True
         N = x.shape[0]
         if eps is None:     # drawn here for exactly these observations: the window into eps starts at 0
@@ -250,7 +256,7 @@ class SparseMultinomialGDRF(nn.Module):
         n_global = N if n_global is None else int(n_global)
         ws = ws.to(self.device)
 
-        def one(e):
+        def one(e, x=x):
             return GDRFElbo.apply(x, ws, self._inducing_points, self._kernel.variance, self._kernel.lengthscale,
                                   self.u_loc, self.u_scale_tril, self.noise, self._word_topic_matrix_map,
                                   self._dirichlet_param, e, _lib.KERNEL_IDS[self._kernel_kind], self._jitter,
@@ -263,7 +269,30 @@ class SparseMultinomialGDRF(nn.Module):
             extra = torch.randn(self.num_particles - 1, self._K, eps.shape[-1], device=self.device,
                                 generator=self._eps_generator)
             eps = torch.cat([eps.unsqueeze(0), extra])
-        return one(eps)
+        if not double_scale:
+            return one(eps)
+        # The reference on a non-unit world: the guide draws mu from the marginal at scale(scale(xs)) and scores it
+        # there (lq); the model scores the same mu under the marginal at scale(xs) (lp_mu); the likelihood and the prior
+        # only see mu and phi.  So ELBO_ref = ELBO(all terms at the guide's inputs) + lp_mu(mu | model's moments)
+        # - lp_mu(mu | guide's moments): the fused op evaluates the first term, and the correction is an elementwise
+        # function of the two sets of marginal moments (fp64, [K, N]), differentiated through gdrf_moments_vjp.
+        x_guide = self.scale(x)
+        kid = _lib.KERNEL_IDS[self._kernel_kind]
+        base = one(eps, x_guide)
+        gp_args = (self._inducing_points, self._kernel.variance, self._kernel.lengthscale, self.u_loc, self.u_scale_tril,
+                   kid, self._jitter, self._maxjitter, flags, chunk_rows, self._scale_mixture, True)
+        fl_g, fv_g = MarginalMoments.apply(x_guide, *gp_args)
+        fl_m, fv_m = MarginalMoments.apply(x, *gp_args)
+        e = eps[..., n_offset:n_offset + N].double()
+        mu = fl_g + fv_g * e
+        noise = self.noise.double()
+
+        def lp(fl, fv):        # Normal(fl, fv + noise).log_prob(mu) without its constant; the variance is the scale
+            sp = fv + noise
+            return (-torch.log(sp) - 0.5 * ((mu - fl) / sp) ** 2).sum(dim=(-2, -1))
+
+        delta = (lp(fl_m, fv_m) - lp(fl_g, fv_g)).mean()          # mean over the particles
+        return base + (delta / float(n_global)).to(base.dtype)
 
     def model(self, xs, ws, subsample=False):
         """sparse_gdrf.py:322-373.  Under Pyro: one factor carrying N * (ELBO / N); the enclosing
@@ -309,10 +338,15 @@ class SparseMultinomialGDRF(nn.Module):
             raise NotImplementedError("full_cov=True is not accelerated")
         Xnew = Xnew.to(self.device)
         self._check_Xnew_shape(Xnew)
+        x = self._scaled(Xnew)
+        params = (self._inducing_points, self._kernel.variance, self._kernel.lengthscale, self.u_loc, self.u_scale_tril)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # differentiable like the reference's (torch autograd through gp.util.conditional): gdrf_moments_vjp
+            return MarginalMoments.apply(x, *params, _lib.KERNEL_IDS[self._kernel_kind], self._jitter, self._maxjitter,
+                                         _lib.FLAG_CHOL_FP32_STATUS, 0, self._scale_mixture, False)
         with torch.no_grad():
-            return marginal_moments(self._scaled(Xnew), self._inducing_points, self._kernel.variance,
-                                    self._kernel.lengthscale, self.u_loc, self.u_scale_tril, self._kernel_kind,
-                                    self._jitter, self._maxjitter, scale_mixture=self._scale_mixture)
+            return marginal_moments(x, *params, self._kernel_kind, self._jitter, self._maxjitter,
+                                    scale_mixture=self._scale_mixture)
 
     def artifacts(self, xs, ws, all: bool = False):
         ret = {"kernel variance": self.kernel_variance, "kernel lengthscale": self.kernel_lengthscale}

@@ -182,6 +182,9 @@ class FusedSVI:
     def step(self, xs, ws, subsample=False, eps=None, n_global=None, n_offset=0) -> float:
         from .elbo import elbo_value_and_grads
         m = self.m
+        if getattr(m, "_reference_double_scale", False) and not m._unit_world:
+            raise NotImplementedError("reference_double_scale on a non-unit world runs through SparseMultinomialGDRF.elbo "
+                                      "(gdrf_b200.svi.SVI / torch optimisers), not the fused step")
         c = self.constrain()
         x = m._scaled(xs)
         N = x.shape[0]

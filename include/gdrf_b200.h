@@ -168,6 +168,17 @@ int gdrf_marginal_mean(const gdrf_shape* shape, const gdrf_inputs* in, float* ou
 int gdrf_marginal_moments(const gdrf_shape* shape, const gdrf_inputs* in, float* out_floc, float* out_fvar,
                           void* workspace, size_t workspace_bytes, gdrf_stream_t stream);
 
+/* Vector-Jacobian product of gdrf_marginal_moments: given the upstream gradients up_floc, up_fvar ([k, n_local] fp32 each;
+ * up_fvar may be NULL = zero) of a scalar with respect to (f_loc, f_var), writes that scalar's gradient with respect to
+ * the constrained u_scale_tril, u_loc, Z, variance, lengthscale (and scale_mixture) into `grad`, laid out like
+ * gdrf_outputs.grad (the phi and noise entries are zero).  This is what torch autograd computes when the reference
+ * differentiates through SparseGDRF.forward / gp.util.conditional (sparse_gdrf.py:277-319, :334-344): the forward
+ * contractions of a chunk are re-run (T is kept), the upstream gradients take the place of the ELBO's per-observation
+ * weights, and the backward contractions, the Cholesky adjoint and the kernel adjoints are the ones gdrf_elbo_step
+ * runs.  Requires gdrf_prologue (with u_scale_tril) on the same workspace.                                       */
+int gdrf_moments_vjp(const gdrf_shape* shape, const gdrf_inputs* in, const float* up_floc, const float* up_fvar,
+                     float* grad, void* workspace, size_t workspace_bytes, gdrf_stream_t stream);
+
 /* The same moments as the library holds them internally (fp64 per-observation chain): [k, n_local] fp64.  The
  * reference's outputs are fp32; this variant exists so that a caller (and the parity tests) can see the marginal
  * variance -- which the model uses as a *scale*, sparse_gdrf.py:403-405 -- below fp32 resolution.               */

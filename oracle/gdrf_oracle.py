@@ -162,13 +162,18 @@ class OracleInputs:
     maxjitter: int = 5
     n_global: Optional[int] = None   # the 1/N of poutine.scale; defaults to len(xs)
     scale_mixture: Optional[torch.Tensor] = None   # RationalQuadratic only
+    # what the GUIDE conditions on when it differs from the model's xs: the reference's guide applies scale() a second
+    # time (sparse_gdrf.py:380), so on a world other than the unit cube it sees scale(scale(xs)) while the model sees
+    # scale(xs).  None: the same inputs (the unit-cube data of train(), train_script.py:263-271).
+    xs_guide: Optional[torch.Tensor] = None
 
     def to(self, dtype: torch.dtype) -> "OracleInputs":
         f = lambda t: t.detach().to(dtype)
         return OracleInputs(f(self.xs), self.ws, f(self.Z), f(self.variance), f(self.lengthscale),
                             f(self.u_loc), f(self.u_scale_tril), f(self.noise), f(self.phi),
                             f(self.beta), f(self.eps), self.kernel, self.jitter, self.maxjitter,
-                            self.n_global, None if self.scale_mixture is None else f(self.scale_mixture))
+                            self.n_global, None if self.scale_mixture is None else f(self.scale_mixture),
+                            None if self.xs_guide is None else f(self.xs_guide))
 
 
 GRAD_NAMES = ("Z", "variance", "lengthscale", "u_loc", "u_scale_tril", "noise", "phi")
@@ -178,7 +183,8 @@ def param_names(inp: "OracleInputs"):
     return GRAD_NAMES + (("scale_mixture",) if inp.scale_mixture is not None else ())
 
 
-def _one_conditional(inp: OracleInputs, p: Dict[str, torch.Tensor], force_njitter=None):
+def _one_conditional(inp: OracleInputs, p: Dict[str, torch.Tensor], force_njitter=None, xs=None):
+    xs = inp.xs if xs is None else xs
     sm = p.get("scale_mixture", inp.scale_mixture)
     Kuu = kernel_matrix(inp.kernel, p["Z"], p["Z"], p["variance"], p["lengthscale"], sm).contiguous()
     M = Kuu.size(0)
@@ -188,10 +194,10 @@ def _one_conditional(inp: OracleInputs, p: Dict[str, torch.Tensor], force_njitte
         nj = force_njitter
         Kj = Kuu + effective_jitter(inp.jitter, nj) * torch.eye(M, dtype=Kuu.dtype)
         Luu = torch.linalg.cholesky(Kj)
-    f_loc, f_var = conditional_whitened(inp.kernel, inp.xs, p["Z"], p["variance"], p["lengthscale"],
+    f_loc, f_var = conditional_whitened(inp.kernel, xs, p["Z"], p["variance"], p["lengthscale"],
                                         p["u_loc"], p["u_scale_tril"], Luu, **({} if sm is None else {"scale_mixture": sm}))
     # zero mean function (abstract_gdrf.py:17-18) broadcast-added
-    f_loc = f_loc + torch.zeros(inp.xs.shape[:-1], dtype=f_loc.dtype)
+    f_loc = f_loc + torch.zeros(xs.shape[:-1], dtype=f_loc.dtype)
     return f_loc, f_var, nj
 
 
@@ -206,14 +212,14 @@ def elbo_terms(inp: OracleInputs, params: Optional[Dict[str, torch.Tensor]] = No
     p = params if params is not None else {k: getattr(inp, k) for k in param_names(inp)}
     N = inp.xs.size(0)
     # ---- guide (sparse_gdrf.py:375-409) ----
-    f_loc_g, f_var_g, nj = _one_conditional(inp, p, force_njitter)
+    f_loc_g, f_var_g, nj = _one_conditional(inp, p, force_njitter, xs=inp.xs_guide)
     mu = f_loc_g + f_var_g * inp.eps                      # Normal(f_loc, f_var).rsample()
     q_mu = torch.distributions.Normal(f_loc_g, f_var_g)
     lq = q_mu.log_prob(mu).sum()
     # Delta(phi).to_event(1): log-prob 0, value = the parameter
     phi = p["phi"]
     # ---- model (sparse_gdrf.py:323-373) replayed against the guide's mu / phi ----
-    if twice:
+    if twice or inp.xs_guide is not None:
         f_loc_m, f_var_m, _ = _one_conditional(inp, p, nj if force_njitter is None else force_njitter)
     else:
         f_loc_m, f_var_m = f_loc_g, f_var_g

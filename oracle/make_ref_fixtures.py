@@ -58,6 +58,9 @@ CASES = {
     "ref_m52_3d_ard": ("Matern52", 3, 3, 2, 15, 160, False, True, 1e-4, 15),
     "ref_exp2d": ("Exponential", 2, 4, 3, 10, 150, False, False, 1e-6, 5),
     "ref_rq2d": ("RationalQuadratic", 2, 4, 3, 11, 180, False, False, 1e-5, 15),
+    # an 11th entry is the world: on anything but the unit cube the reference's guide conditions on scale(scale(xs))
+    # (sparse_gdrf.py:380) and its model on scale(xs) -- the drop-in's reference_double_scale=True reproduces this
+    "ref_world2d": ("RBF", 2, 5, 3, 12, 220, False, False, 1e-4, 15, [(-1.0, 1.0), (0.0, 2.0)]),
 }
 
 
@@ -66,15 +69,18 @@ def run_case(models, name, spec, svi_steps=3):
     import pyro.contrib.gp as gp
     from pyro import poutine
     from pyro.infer import SVI, Trace_ELBO
-    kname, D, n_points, K, V, N, fixed, ard, jitter, maxjitter = spec
+    kname, D, n_points, K, V, N, fixed, ard, jitter, maxjitter = spec[:10]
+    world = spec[10] if len(spec) > 10 else [(0.0, 1.0)] * D
     seed = sum(map(ord, name))
     torch.manual_seed(seed)
     pyro.clear_param_store()
     xs, ws = make_data(N, D, V, seed)
+    lo = torch.tensor([b[0] for b in world])
+    xs = lo + xs * (torch.tensor([b[1] for b in world]) - lo)       # observations anywhere in the world
     ls = torch.tensor([0.35, 0.5, 0.7][:D]) if ard else torch.tensor(0.4)
     kernel = getattr(gp.kernels, kname)(D, variance=torch.tensor(1.3), lengthscale=ls)
     m = models.SparseMultinomialGDRF(
-        num_observation_categories=V, num_topic_categories=K, world=[(0.0, 1.0)] * D, kernel=kernel,
+        num_observation_categories=V, num_topic_categories=K, world=world, kernel=kernel,
         dirichlet_param=0.1, n_points=n_points, fixed_inducing_points=fixed, inducing_init="grid", device="cpu",
         jitter=jitter, maxjitter=maxjitter, xs=xs, ws=ws)
     ctor_init = {k: v.detach().clone() for k, v in m.named_parameters()}      # what the reference's constructor set
@@ -106,6 +112,7 @@ def run_case(models, name, spec, svi_steps=3):
            "lp_phi": np.float64(model_trace.nodes["phi"]["fn"].log_prob(model_trace.nodes["phi"]["value"]).sum().item()),
            "ll": np.float64(model_trace.nodes["w"]["fn"].log_prob(model_trace.nodes["w"]["value"]).sum().item()),
            "beta": m._dirichlet_param.numpy(),
+           "world": np.array(world, dtype=np.float64),
            "spec": np.array([kname, D, n_points, K, V, N, int(fixed), int(ard), jitter, maxjitter], dtype=object).astype(str)}
     if fixed:
         out["Z_fixed"] = m._inducing_points.detach().numpy()
@@ -138,5 +145,7 @@ def run_case(models, name, spec, svi_steps=3):
 
 if __name__ == "__main__":
     models = import_reference_models()
+    only = sys.argv[1:]                      # python oracle/make_ref_fixtures.py [case ...]
     for name, spec in CASES.items():
-        run_case(models, name, spec)
+        if not only or name in only:
+            run_case(models, name, spec)

@@ -30,7 +30,7 @@ def load_golden(name):
     return inp, d
 
 
-REF_CASES = ["ref_rbf2d", "ref_m32_1d_fixed", "ref_m52_3d_ard", "ref_exp2d", "ref_rq2d"]
+REF_CASES = ["ref_rbf2d", "ref_m32_1d_fixed", "ref_m52_3d_ard", "ref_exp2d", "ref_rq2d", "ref_world2d"]
 REF_KERNELS = {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52", "Exponential": "exponential",
                "RationalQuadratic": "rationalquadratic"}
 
@@ -42,6 +42,10 @@ def load_ref_fixture(name):
     s = [str(x) for x in d["spec"]]
     spec = dict(kernel=REF_KERNELS[s[0]], kernel_class=s[0], D=int(s[1]), n_points=int(s[2]), K=int(s[3]), V=int(s[4]),
                 N=int(s[5]), fixed=bool(int(s[6])), ard=bool(int(s[7])), jitter=float(s[8]), maxjitter=int(s[9]))
+    # the world the reference model was built on ([0, 1]^D in the older fixtures, which do not store it); xs is in
+    # world coordinates
+    spec["world"] = ([tuple(map(float, b)) for b in d["world"]] if "world" in d.files else [(0.0, 1.0)] * spec["D"])
+    spec["unit_world"] = all(b == (0.0, 1.0) for b in spec["world"])
     u = {k[len("param/"):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("param/")}
     return spec, u, d
 
@@ -64,7 +68,13 @@ def ref_constrained(spec, u, d, dtype=torch.float64):
 
 def ref_oracle_inputs(spec, params, d, eps, dtype=torch.float64):
     det = {k: v.detach() for k, v in params.items()}
-    return OracleInputs(xs=torch.from_numpy(d["xs"]).to(dtype), ws=torch.from_numpy(d["ws"]).int(), Z=det["Z"],
+    # scale_decorator (topic_model.py:122-144) maps xs into the unit cube for model and guide; the guide then applies
+    # scale() once more (sparse_gdrf.py:380) -- a no-op only on the unit world
+    lo = torch.tensor([b[0] for b in spec["world"]], dtype=dtype)
+    delta = torch.tensor([b[1] - b[0] for b in spec["world"]], dtype=dtype)
+    xs1 = (torch.from_numpy(d["xs"]).to(dtype) - lo) / delta
+    xs_guide = None if spec["unit_world"] else (xs1 - lo) / delta
+    return OracleInputs(xs=xs1, xs_guide=xs_guide, ws=torch.from_numpy(d["ws"]).int(), Z=det["Z"],
                         variance=det["variance"], lengthscale=det["lengthscale"], u_loc=det["u_loc"],
                         u_scale_tril=det["u_scale_tril"], noise=det["noise"], phi=det["phi"],
                         beta=torch.from_numpy(d["beta"]).to(dtype), eps=torch.as_tensor(eps).to(dtype),

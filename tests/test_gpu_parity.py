@@ -116,6 +116,43 @@ def test_jitter_search_speculation_and_batched_probe_return_the_reference_level(
     E._JITTER_HINTS.clear()
 
 
+def test_marginal_moments_vjp_matches_autograd_of_the_oracle():
+    """gdrf_moments_vjp (MarginalMoments.backward): the gradient of a random linear functional of (f_loc, f_var) with
+    respect to Z, variance, lengthscale, u_loc, u_scale_tril against torch autograd through the oracle's
+    conditional (what the reference gets when it differentiates through SparseGDRF.forward, sparse_gdrf.py:277-319),
+    in fp64 and fp32, under the parity gate; chunked and unchunked; ARD Matern-5/2 and RBF."""
+    from gdrf_b200.elbo import marginal_moments_diff
+    names = ("Z", "variance", "lengthscale", "u_loc", "u_scale_tril")
+    for kw, chunk_rows in ((dict(N=1500, D=2, K=3, V=8, grid=[8, 8], kernel="rbf", seed=21), 0),
+                           (dict(N=1100, D=3, K=5, V=8, grid=[4, 4, 4], kernel="matern52", seed=22, ard=True), 512)):
+        inp = O.make_problem(**kw)
+        K, N = inp.u_loc.shape[0], inp.xs.shape[0]
+        g = torch.Generator().manual_seed(kw["seed"])
+        a, b = torch.randn(K, N, generator=g), 1e-2 * torch.randn(K, N, generator=g)
+
+        def oracle(dtype):
+            i = inp.to(dtype)
+            p = {k: getattr(i, k).clone().requires_grad_(True) for k in names}
+            fl, fv, _ = O._one_conditional(i, p)
+            return fl.detach(), fv.detach(), torch.autograd.grad((a.to(dtype) * fl).sum() + (b.to(dtype) * fv).sum(),
+                                                                 [p[k] for k in names])
+        fl64, fv64, g64 = oracle(torch.float64)
+        _, _, g32 = oracle(torch.float32)
+        leaves = {k: getattr(inp, k).to(_dev()).clone().requires_grad_(True) for k in names}
+        fl, fv = marginal_moments_diff(inp.xs.to(_dev()), leaves["Z"], leaves["variance"], leaves["lengthscale"],
+                                       leaves["u_loc"], leaves["u_scale_tril"], kernel=inp.kernel, jitter=inp.jitter,
+                                       maxjitter=inp.maxjitter, chunk_rows=chunk_rows)
+        assert O.rel_err(fl.detach().cpu(), fl64) < 1e-5 and O.rel_err(fv.detach().cpu(), fv64) < 1e-5
+        ((a.to(_dev()) * fl).sum() + (b.to(_dev()) * fv).sum()).backward()
+        rows = {}
+        for k, r64, r32 in zip(names, g64, g32):
+            mine = leaves[k].grad.cpu().double()
+            if k == "u_scale_tril":
+                mine, r64, r32 = mine.tril(), r64.tril(), r32.tril()
+            rows[k] = (O.rel_err(mine, r64), O.rel_err(r32, r64), O.rel_err(mine, r32))
+        assert_parity(rows, f"moments vjp {kw['kernel']}")
+
+
 def test_max_jitter_raises_like_the_reference():
     inp, _ = load_golden("ragged")
     bad = O.OracleInputs(**{**inp.__dict__, "lengthscale": torch.tensor([5.0]), "jitter": 1e-12, "maxjitter": 2})
