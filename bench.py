@@ -374,12 +374,13 @@ class Bench:
         H2D on a second stream while the previous one computes, the four terms read back to the host every step.  The
         134 MB gradient stays on the device (it feeds an on-device optimiser: FusedSVI)."""
         import torch.distributed as dist
-        from gdrf_b200.elbo import elbo_value_and_grads_from_host, flat_gradient, terms_from_flat
+        from gdrf_b200.elbo import DEFAULT_CHUNK_ROWS, elbo_value_and_grads_from_host, sub_shard_rows
         torch, p, cfg = self.torch, self.prm, self.cfg
         hx, hw, he = (t_.cpu().pin_memory() for t_ in (self.xs, self.ws, self.eps))
         h_terms = torch.empty(4, dtype=torch.float64).pin_memory()
-        n_sub = max(2, min(8, self.n_local // 60000))
-        per = ((self.n_local + n_sub - 1) // n_sub + 255) // 256 * 256
+        # one chunk per sub-shard: the first copy (41 MB at C4), the only one not hidden by compute, fits under the prologue
+        n_sub = max(2, -(-self.n_local // DEFAULT_CHUNK_ROWS))
+        per = sub_shard_rows(self.n_local, n_sub)
         D, K, V = cfg["D"], cfg["K"], cfg["V"]
         staging = [dict(xs=torch.empty(per, D, dtype=torch.float32, device=self.dev),
                         ws=torch.empty(per, V, dtype=torch.int32, device=self.dev),
@@ -389,11 +390,8 @@ class Bench:
             tm, g_, _ = elbo_value_and_grads_from_host(
                 hx, hw, he, p["Z"], p["variance"], p["lengthscale"], p["u_loc"], p["u_scale_tril"], p["noise"],
                 p["phi"], p["beta"], kernel=cfg["kernel"], jitter=self.jitter, maxjitter=self.maxjitter,
-                n_global=cfg["N"], include_prior=(self.rank == 0), flags=self.flags, n_sub=n_sub, staging=staging)
-            if self.world > 1:
-                flat = flat_gradient(g_)
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                tm = terms_from_flat(flat)
+                n_global=cfg["N"], include_prior=(self.rank == 0), flags=self.flags, n_sub=n_sub, staging=staging,
+                all_reduce=True)         # gradient + terms summed over the ranks (NCCL), dS under the per-step epilogue
             h_terms.copy_(tm, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return h_terms

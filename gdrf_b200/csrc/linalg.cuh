@@ -82,58 +82,60 @@ __global__ void k_kuu(const float* __restrict__ Z, int M, int Mp, Hyper hp, doub
 template <typename T>
 __device__ __forceinline__ void chol_diag_core(T a, T (*sl)[NB + 1], T* __restrict__ L, T* __restrict__ Dinv, int Mp,
                                                int kb, int* __restrict__ status) {
-  // 32 warps, one thread per element (r = warp, c = lane).  Three single-warp formulations (all shuffles and fully
-  // unrolled; all shared memory; row in registers) took 29-35 us per block column: one warp issuing ~14 K mostly
-  // dependent instructions.  Here a column step is two block barriers and one multiply-add per thread, and a row of
-  // the inverse is a warp-level dot product per column.  The factorisation's arithmetic and its order are unchanged
-  // (right-looking: element (r, c) receives -L[r][j] L[c][j] for j = 0 .. c-1 in order); the inverse sums its dot
-  // products as a shuffle tree instead of serially.
+  // 32 warps, one thread per element (input and output map: r = warp, c = lane).  Three single-warp formulations (all
+  // shuffles and fully unrolled; all shared memory; row in registers) took 29-35 us per block column: one warp issuing
+  // ~14 K mostly dependent instructions.  Here a column step is one block barrier and one multiply-add per thread, and a
+  // column of the inverse is one warp's forward substitution.  The factorisation's arithmetic and its order are
+  // unchanged (right-looking: element (r, c) receives -L[r][j] L[c][j] for j = 0 .. c-1 in order).
   // sl: [NB][NB + 1] shared scratch of the caller for L (zero above the diagonal); first written after a block barrier
-  __shared__ T scol[NB];           // the column being eliminated
+  __shared__ T scol[2][NB];        // the column being eliminated (double-buffered: one block barrier per column)
   __shared__ T sinv[NB];           // 1 / L[j][j]
-  __shared__ T sd;                 // the pivot
   const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
-  int bad = 0;
+  // The elimination runs on the TRANSPOSED thread map (thread = element (row = lane, column = warp)): column j then
+  // lives in ONE warp, which alone takes the pivot's reciprocal square root (every thread doing so -- 32 warps x ~40 fp64
+  // instructions per column on a 64-lane fp64 pipe -- was what a column step cost: ~1200 clk), scales its column and
+  // publishes it; the other warps wait at the single barrier of the step and apply the rank-1 update.
+  __syncthreads();                 // the caller may still be reading sl (chol_trail_body's ai)
+  sl[r][c] = a;
+  __syncthreads();
+  const int rr = c, cc = r;        // lane, warp
+  T at = sl[rr][cc];
 #pragma unroll 1
   for (int j = 0; j < NB; ++j) {
-    if (r == j && c == j) sd = a;
-    __syncthreads();
-    T d = sd;
-    if (!(d > T(0))) {
-      if (bad == 0) bad = kb * NB + j + 1;
-      d = T(1);
-    }
-    // one reciprocal square root per column instead of two square roots and a division (each a long dependent
-    // chain in fp64); a Newton step puts sqrt(d) = d * inv back within an ulp
-    const T inv = rsqrt(d);
-    T sq = d * inv;
-    sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
-    if (c == j) {
-      T lj = T(0);
-      if (r == j) lj = sq;
-      else if (r > j) lj = a * inv;
-      a = lj;
-      scol[r] = lj;
-      if (r == j) sinv[j] = inv;
+    if (cc == j) {                 // warp-uniform
+      T d = __shfl_sync(0xffffffffu, at, j);
+      if (!(d > T(0))) {
+        if (rr == 0) atomicCAS(status, 0, kb * NB + j + 1);
+        d = T(1);
+      }
+      // one reciprocal square root per column instead of two square roots and a division (each a long dependent
+      // chain in fp64); a Newton step puts sqrt(d) = d * inv back within an ulp
+      const T inv = rsqrt(d);
+      T sq = d * inv;
+      sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
+      const T lj = (rr == j) ? sq : (rr > j ? at * inv : T(0));
+      at = lj;
+      scol[j & 1][rr] = lj;
+      if (rr == j) sinv[j] = inv;
     }
     __syncthreads();
-    if (c > j && r >= c) a -= scol[r] * scol[c];
+    if (cc > j && rr >= cc) at -= scol[j & 1][rr] * scol[j & 1][cc];
   }
-  sl[r][c] = (c <= r) ? a : T(0);
+  __syncthreads();                 // sl was read by everyone long ago; scol/sinv complete
+  sl[rr][cc] = (cc <= rr) ? at : T(0);
   __syncthreads();
   L[((long long)kb * NB + r) * Mp + kb * NB + c] = sl[r][c];
-  // row r of the inverse: x L = e_r, back-substituted over the columns from the right; lane t holds x[t]
-  T x = T(0);
+  // the inverse X = L^-1, one column per warp on the transposed map: forward substitution L x = e_cc in its
+  // right-looking form -- lane i publishes x_i = b_i / L[i][i] with one shuffle and every lane below it updates its
+  // right-hand side b -= L[rr][i] x_i (a shuffle and a multiply-add per step instead of a five-level shuffle tree)
+  T b = (rr == cc) ? T(1) : T(0), x = T(0);
 #pragma unroll 1
-  for (int j = r; j >= 0; --j) {
-    T part = (c > j) ? x * sl[c][j] : T(0);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const T xj = (((r == j) ? T(1) : T(0)) - part) * sinv[j];
-    if (c == j) x = xj;
+  for (int i = cc; i < NB; ++i) {
+    const T xi = __shfl_sync(0xffffffffu, b, i) * sinv[i];
+    if (rr == i) x = xi;
+    if (rr > i) b -= sl[rr][i] * xi;
   }
-  Dinv[((long long)kb * NB + r) * NB + c] = x;
-  if (threadIdx.x == 0 && bad != 0) atomicCAS(status, 0, bad);
+  Dinv[((long long)kb * NB + rr) * NB + cc] = x;
 }
 
 template <typename T>

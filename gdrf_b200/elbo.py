@@ -23,6 +23,7 @@ import torch
 from . import _lib
 
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+DEFAULT_CHUNK_ROWS = 148 * 128     # the library's chunk (csrc/gdrf_capi.cu: DEFAULT_SMS * 128 observation rows)
 _COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 _JITTER_HINTS: Dict[Tuple[int, int, int, int], int] = {}   # (device, M, D, kernel) -> jitter level of the last prologue
 
@@ -338,38 +339,53 @@ def elbo_value_and_grads(xs, ws, Z, variance, lengthscale, u_loc, u_scale_tril, 
     return terms, g, nj
 
 
+def sub_shard_rows(N: int, n_sub: int) -> int:
+    """Rows per sub-shard of :func:`elbo_value_and_grads_from_host` (the size its staging buffers need): N / n_sub
+    rounded up to 256, and to whole chunks of 148 * 128 observations once that is at least half a chunk."""
+    n_sub = max(1, min(int(n_sub), (N + 255) // 256))
+    per = ((N + n_sub - 1) // n_sub + 255) // 256 * 256
+    if 2 * per > DEFAULT_CHUNK_ROWS:
+        per = (per + DEFAULT_CHUNK_ROWS - 1) // DEFAULT_CHUNK_ROWS * DEFAULT_CHUNK_ROWS
+    return per
+
+
 def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, lengthscale, u_loc, u_scale_tril, noise,
                                    phi, beta, kernel: str = "rbf", jitter: float = 1e-8, maxjitter: int = 5,
                                    n_global=None, n_offset: int = 0, include_prior: bool = True,
                                    flags: int = _lib.FLAG_CHOL_FP32_STATUS, n_sub: int = 8, staging=None,
-                                   scale_mixture=None):
+                                   scale_mixture=None, all_reduce: bool = False, group=None):
     """Same result as :func:`elbo_value_and_grads`, with the observations (``xs_host`` [N, D] fp32, ``ws_host``
     [N, V] int32, ``eps_host`` [K, >= n_offset + N] fp32) living in pinned HOST memory.  The shard is cut into
     ``n_sub`` sub-shards; while sub-shard i is being evaluated on the compute stream, sub-shard i+1 is copied
     host-to-device on a second stream into the other half of a double buffer (GDRF_FLAG_CONTINUE /
-    GDRF_FLAG_PARTIAL carry the accumulators across the calls).  Parameters are device tensors.
+    GDRF_FLAG_PARTIAL carry the accumulators across the calls).  Sub-shards of at least half a chunk are rounded up to
+    whole chunks of 148 * 128 observations, so that only the last one ends in a short chunk; with one chunk per sub-shard
+    the first copy (the only one nothing hides but the prologue) is 41 MB at the C4 shape.  Parameters are device tensors.
+    ``all_reduce=True``: as in :func:`elbo_value_and_grads` (d/d u_scale_tril is reduced under the per-step epilogue).
     Returns (terms, grads dict, njitter)."""
+    import torch.distributed as dist
     dev = Z.device
     N, D = xs_host.shape
     V = ws_host.shape[1]
     K, M = u_loc.shape
     fl = int(flags) | (_lib.FLAG_INCLUDE_PRIOR if include_prior else 0)
-    n_sub = max(1, min(int(n_sub), (N + 255) // 256))
-    per = ((N + n_sub - 1) // n_sub + 255) // 256 * 256
+    per = sub_shard_rows(N, n_sub)
     bounds = [(lo, min(N, lo + per)) for lo in range(0, max(N, 1), per)]
     rows = per if N > 0 else 1
+    if staging is not None and staging[0]["xs"].shape[0] < rows:
+        raise ValueError(f"staging buffers hold {staging[0]['xs'].shape[0]} rows, the sub-shards have {rows}")
     if staging is None:
         staging = [dict(xs=torch.empty(rows, D, dtype=torch.float32, device=dev),
                         ws=torch.empty(rows, V, dtype=torch.int32, device=dev),
                         eps=torch.empty(K, rows, dtype=torch.float32, device=dev)) for _ in range(2)]
     compute = torch.cuda.current_stream(dev)
     copy_stream = _copy_stream(dev)
-    calls = []
-    for i, (lo, hi) in enumerate(bounds):
+    def make_call(i):      # built while the previous sub-shard computes: the host stays ahead of the device
+        lo, hi = bounds[i]
         st_ = staging[i % 2]
-        n = hi - lo
-        calls.append(_Call(st_["xs"][:n], st_["ws"][:n], Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi, beta,
-                           st_["eps"], _lib.KERNEL_IDS[kernel], 0, fl, 0, scale_mixture))
+        return _Call(st_["xs"][:hi - lo], st_["ws"][:hi - lo], Z, variance, lengthscale, u_loc, u_scale_tril, noise, phi,
+                     beta, st_["eps"], _lib.KERNEL_IDS[kernel], 0, fl, 0, scale_mixture)
+
     free_ev = [torch.cuda.Event(), torch.cuda.Event()]
     copied_ev = [torch.cuda.Event() for _ in bounds]
 
@@ -389,20 +405,34 @@ def elbo_value_and_grads_from_host(xs_host, ws_host, eps_host, Z, variance, leng
             copied_ev[i].record(copy_stream)
 
     issue_copy(0)
-    nj = calls[0].prologue(jitter, maxjitter)
-    for c in calls[1:]:
-        c.shape.flags = calls[0].shape.flags
+    call = make_call(0)
+    nj = call.prologue(jitter, maxjitter)
+    step_flags = call.shape.flags
     terms = torch.empty(4, dtype=torch.float64, device=dev)
-    grad = torch.empty(_lib.grad_elems(calls[0].shape) + _lib.TERMS_TAIL, dtype=torch.float32, device=dev)
-    for i, call in enumerate(calls):
-        if i + 1 < len(calls):
+    grad = torch.empty(_lib.grad_elems(call.shape) + _lib.TERMS_TAIL, dtype=torch.float32, device=dev)
+    reduce_ = all_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    for i in range(len(bounds)):
+        if i + 1 < len(bounds):
             issue_copy(i + 1)
         compute.wait_event(copied_ev[i])
-        extra = (_lib.FLAG_CONTINUE if i > 0 else 0) | (_lib.FLAG_PARTIAL if i + 1 < len(calls) else 0)
-        call.shape.flags &= ~(_lib.FLAG_CONTINUE | _lib.FLAG_PARTIAL)
+        extra = (_lib.FLAG_CONTINUE if i > 0 else 0) | (_lib.FLAG_PARTIAL if (i + 1 < len(bounds) or reduce_) else 0)
+        call.shape.flags = step_flags & ~(_lib.FLAG_CONTINUE | _lib.FLAG_PARTIAL)
         call.step(True, terms=terms, grad=grad, extra_flags=extra)
         free_ev[i % 2].record(compute)
-    g = split_grad(grad, K, M, V, D, calls[0].shape.ls_dim)
+        last = call
+        if i + 1 < len(bounds):
+            call = make_call(i + 1)
+    if reduce_:       # dS is complete: its all-reduce runs under the per-step epilogue (elbo_value_and_grads)
+        big = dist.all_reduce(grad[:K * M * M], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        n_local = last.shape.n_local
+        last.shape.n_local = 0
+        last.shape.flags &= ~(_lib.FLAG_CONTINUE | _lib.FLAG_PARTIAL)
+        last.step(True, terms=terms, grad=grad, extra_flags=_lib.FLAG_CONTINUE)
+        last.shape.n_local = n_local
+        dist.all_reduce(grad[K * M * M:], op=dist.ReduceOp.SUM, group=group)
+        big.wait()
+        terms = terms_from_flat(grad)
+    g = split_grad(grad, K, M, V, D, last.shape.ls_dim)
     return terms, g, nj
 
 
