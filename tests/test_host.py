@@ -70,6 +70,30 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     m = _cpu_model()
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.elbo(torch.rand(10, 2), torch.ones(10, 7, dtype=torch.int32))
+    # the entry points added in round 2 refuse as loudly: the batched jitter probe and the moments' VJP
+    rc = _lib.load().gdrf_jitter_probe(ctypes.byref(s), ctypes.byref(inp), 1e-6, 0, 4, buf, 10 ** 12, None,
+                                       ctypes.byref(status))
+    assert rc != 0
+    rc = _lib.load().gdrf_moments_vjp(ctypes.byref(s), ctypes.byref(inp), buf, buf, buf, buf, 10 ** 12, None)
+    assert rc != 0
+    with pytest.raises(RuntimeError, match="no CPU path"):      # a differentiable forward() has no eager fallback either
+        m.forward(torch.rand(10, 2) * torch.tensor([2.0, 1.0]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _cpu_model(reference_double_scale=True).elbo(torch.rand(10, 2), torch.ones(10, 7, dtype=torch.int32))
+
+
+def test_host_pipeline_sub_shards_are_whole_chunks():
+    """elbo_value_and_grads_from_host cuts a shard into sub-shards of whole 148 * 128-observation chunks once a sub-shard
+    is at least half a chunk (only the last one then ends in a short chunk), and into 256-row multiples below that."""
+    from gdrf_b200.elbo import DEFAULT_CHUNK_ROWS, sub_shard_rows
+    assert DEFAULT_CHUNK_ROWS == 148 * 128
+    assert sub_shard_rows(1_000_000, 53) == DEFAULT_CHUNK_ROWS            # C4 on one GPU: one chunk per sub-shard
+    assert sub_shard_rows(125_000, 7) == DEFAULT_CHUNK_ROWS              # ... and on eight
+    assert sub_shard_rows(1_000_000, 8) == 7 * DEFAULT_CHUNK_ROWS
+    assert sub_shard_rows(2900, 3) == 1024 and sub_shard_rows(2900, 1) == 3072 and sub_shard_rows(100, 8) == 256
+    for n, k in ((1_000_000, 53), (125_000, 7), (2900, 3), (1, 4)):
+        per = sub_shard_rows(n, k)
+        assert per % 256 == 0 and per * k >= n
 
 
 def _cpu_model(**kw):
