@@ -151,8 +151,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-PROFILE_SUMMARY = os.path.join(ROOT, "profiles", "r02_gemm_ncu_summary.json")
-PROFILE_FALLBACK = os.path.join(ROOT, "profiles", "r01j_gemm_ncu_summary.json")
+PROFILE_SUMMARY = os.path.join(ROOT, "profiles", "r02b_gemm_ncu_summary.json")
+PROFILE_FALLBACK = os.path.join(ROOT, "profiles", "r02_gemm_ncu_summary.json")
 
 
 def roofline_block(prof, steps, n_local, ms_step_rank0, M, K, flags, _lib):

@@ -6,7 +6,10 @@ TAG=$1
 mkdir -p gpurun_out
 CMD="python bench.py --obs 75776 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/${TAG}_plain.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 190 --csv --log-file gpurun_out/${TAG}_launches_n75776.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
+# one whole step: everything between two M x M prologues (k_kuu<double> opens a prologue); -s skips the warm-up steps
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 260 --csv --log-file gpurun_out/${TAG}_launches_n75776.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
+# the prologue alone (C4 / C1 / M = 2048 shapes, tools/time_prologue.py), launch by launch
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:k_chol|k_trinv|k_kuu|k_pack|k_merge" -c 50 --csv --log-file gpurun_out/${TAG}_prologue_launches.csv python tools/time_prologue.py > gpurun_out/${TAG}_ncu0.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc2|k_scale_w|k_likelihood|k_reduce_dphi|k_dw_finalize|k_kxz_planes|k_kxz_backward|k_obs_" -s 180 -c 15 -o gpurun_out/${TAG}_chunk -f $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 ncu -i gpurun_out/${TAG}_chunk.ncu-rep --page raw --csv > gpurun_out/${TAG}_chunk_ncu_raw.csv
 python tools/ncu_summary.py gpurun_out/${TAG}_chunk_ncu_raw.csv > gpurun_out/${TAG}_gemm_ncu_summary.json
