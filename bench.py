@@ -162,8 +162,13 @@ def roofline_block(prof, steps, n_local, ms_step_rank0, M, K, flags, _lib):
     if os.path.exists(peaks_path):
         peaks = json.load(open(peaks_path))
         peak_tf, peak_src = float(peaks.get("bf16_tflops_sustained", 1384.6)), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        burst_tf = float(peaks.get("bf16_tflops", peak_tf))
     else:
         peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+        burst_tf = peak_tf
+    # plausibility bound on issued MMA flops: 1.3 x the measured peak, taking the BURST figure -- a short kernel on a cool
+    # box (small configurations, the 8-GPU shards) legitimately runs above the power-capped sustained number
+    issued_limit = 1.3 * max(burst_tf, peak_tf) / peak_tf
     tri = 2.0 * (M * M / 2.0) * K                 # triangular-aware flops per observation of one W*S_k contraction
     alg = {"G1": 2.0 * M * M / 2, "G2_fwd": tri, "scale_w": 0.0, "G3": tri, "G4": 2.0 * M * M / 2, "G5": 2.0 * M * M,
            "G6": tri}
@@ -215,8 +220,8 @@ def roofline_block(prof, steps, n_local, ms_step_rank0, M, K, flags, _lib):
     problems = []
     if total_ms > 1.02 * ms_step_rank0:
         problems.append(f"profiled kernels sum to {total_ms:.1f} ms/step > step {ms_step_rank0:.1f} ms")
-    if any(e.get("issued_frac", 0) > 1.3 for e in per_kernel.values()):
-        problems.append("issued_frac > 1.3 of the measured bf16 peak")
+    if any(e.get("issued_frac", 0) > issued_limit for e in per_kernel.values()):
+        problems.append(f"issued_frac > {issued_limit:.2f} (1.3 x the measured burst bf16 peak)")
     if any(abs(e["launches_per_step"] - round(e["launches_per_step"])) > 1e-6 for e in per_kernel.values()):
         problems.append("launch records are not a whole number per step")
     if problems:      # a roofline that does not follow from the records is not printed
