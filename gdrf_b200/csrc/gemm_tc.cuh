@@ -143,7 +143,7 @@ struct FmtOf<P, std::void_t<decltype(std::declval<typename P::Params>().fmt)>> {
 
 // (plane_a, plane_b) products kept by the issue loops: all pairs with pa + pb <= max(PA, PB) - 1
 
-// warps: 0 = bulk-copy producer, 1 = MMA issuer / TMEM owner, 2.. = epilogue (P::EPI_WARPS of them, 4 or 8)
+// warps: 0 = bulk-copy producer, 1 = MMA issuer / TMEM owner, 2.. = epilogue (P::EPI_WARPS of them: 4, 8 or 16)
 template <class P>
 constexpr int gemm_threads() { return 64 + 32 * P::EPI_WARPS; }
 constexpr int GEMM_SMEM_BUDGET = 216 * 1024;
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(gemm_threads<P>(), 1) gemm_tc_kernel(const __g
     }
   } else {
     // ------------------------------ epilogue (warps 2..) ------------------------------
-    // a warp may only read the TMEM lane quarter warp%4; with 8 epilogue warps the second four take the upper
-    // half of the accumulator columns
+    // a warp may only read the TMEM lane quarter warp%4; with 8 (16) epilogue warps every further group of four warps
+    // takes the next half (quarter) of the accumulator columns
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;       // accumulator row owned by this thread
     constexpr int NCH = (P::BN / 32) / (P::EPI_WARPS / 4);

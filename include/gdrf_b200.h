@@ -130,7 +130,8 @@ int gdrf_grad_elems(const gdrf_shape* shape, int64_t* out_elems);
  * kernel variance or the bound sqrt(variance m) max|u_scale_tril| on T = W S_k may leave the fp16 range (then call
  * gdrf_prologue again, and gdrf_elbo_step, with GDRF_FLAG_FWD_BF16; with that flag the status is never -1).
  * The caller loops njitter = 0, 1, ... < maxjitter exactly like jittercholesky (utils.py:31-39); after a first failure
- * it may probe the following levels with GDRF_FLAG_STATUS_ONLY and run the full prologue at the first that passes.  */
+ * it may ask gdrf_jitter_probe for the following levels (several at once; or one at a time with GDRF_FLAG_STATUS_ONLY)
+ * and run the full prologue at the first that passes.                                                           */
 int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter, void* workspace,
                   size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
 
