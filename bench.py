@@ -401,10 +401,11 @@ class Bench:
             torch.cuda.current_stream().synchronize()
             return h_terms
 
-        ms, _, _ = self.timed(one, steps, 1)
+        ms, _, ht = self.timed(one, steps, 1)
         h2d = hx.numel() * 4 + hw.numel() * 4 + he.numel() * 4
         return {"value": cfg["N"] / (ms * 1e-3), "unit": "observations/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 32, "ms_per_step": ms,
+                "loss": -float(ht[0] + ht[3] + ht[2] - ht[1]) / cfg["N"],      # the terms read back on the last step
                 "note": "host buffers -> C ABI; the four ELBO terms come back to the host, the gradient stays on the "
                         "device for the on-device optimiser"}
 
@@ -617,6 +618,12 @@ def main():
         cpu_baseline = cpu_reference_rate(cfg, min(rows, N), 2, 1)
         cpu_baseline.pop("ms_per_step", None)
 
+    # the full-size result through two code paths with different chunk boundaries (device-resident shard in chunks of
+    # 18 944 vs host-streamed sub-shards; at N > 1 both are sums over the ranks): the ELBO is additive over observations
+    checks = None
+    if e2e is not None and e2e.get("loss") is not None:
+        checks = {"e2e_vs_device_resident_loss_rel_diff": abs(e2e["loss"] - loss) / abs(loss),
+                  "note": "same 1/N-scaled loss from the device-resident and the host-streamed evaluation of the full data set"}
     line = {"metric": METRIC, "value": value, "unit": "observations/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None,
@@ -629,7 +636,7 @@ def main():
                        "api": "gdrf_b200.elbo.elbo_value_and_grads (public); one all-reduce of gradient + terms"},
             "loss": loss, "wall_s_timed": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "svi_step": svi, "other_configs": other,
-            "particles": particles, "c5_weak_scaling": c5_weak,
+            "particles": particles, "c5_weak_scaling": c5_weak, "checks": checks,
             "alg_tflops_step": algorithmic_flops_per_obs(M, K, V) * N / (ms_per_step * 1e-3) / 1e12}
     print(json.dumps(line), flush=True)
     if world > 1:

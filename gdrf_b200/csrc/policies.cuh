@@ -25,18 +25,26 @@ __device__ __forceinline__ void store8(bf16* dst, const uint4& pk) { *reinterpre
 // The 128-byte swizzle only permutes 16-byte chunks with XOR (row & 7), so the two chunks of a 32-byte sector stay
 // in the same sector (possibly swapped): a full-sector store needs no read-for-fill in L2 (a pair of 16-byte stores
 // cost a DRAM read per written sector -- measured 2.3 GB per launch on the T store).
-// STREAM: evict-first hint for multi-GB outputs that are not re-read before they fall out of L2 anyway (the T
-// planes); without it they push the re-used B operand (ST) out of L2.
-template <bool STREAM = false>
-__device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int col, const uint4& lo, const uint4& hi) {
+// `policy` != 0: an L2 cache-policy operand (evict_first, l2_evict_first_policy()) for multi-GB outputs that are not
+// re-read before they fall out of L2 anyway (the T planes): without it they push the operand the same kernel re-reads
+// (the W tile of a CTA pair, once per topic) out of L2.  Measured on the forward contraction (ncu, one chunk): DRAM
+// reads 0.19 GB with the T store switched off, 3.37 GB with `st.global.cs` (the streaming hint does not reach L2's
+// replacement), 2.55 GB with the cache-policy operand; the step 309.9 -> 307.2 ms.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void store16(const PlaneMat& m, int plane, int r, int col, const uint4& lo, const uint4& hi,
+                                        uint64_t policy = 0) {
   bf16* p = m.elem(plane, r, col);                       // address of the chunk holding columns col .. col+7
   const bool swapped = (r & 1) != 0;                     // chunk index parity flips with row parity
   bf16* sector = swapped ? p - 8 : p;
   const uint4& a = swapped ? hi : lo;
   const uint4& b = swapped ? lo : hi;
-  if (STREAM)
-    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y),
-                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+  if (policy != 0)
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(sector), "r"(a.x),
+                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(policy)
                  : "memory");
   else
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(sector), "r"(a.x), "r"(a.y), "r"(a.z),
@@ -252,10 +260,12 @@ struct G2 {
   struct Epi {
     double qacc;
     int rt, s0;
+    uint64_t pol;
     __device__ void item_begin(const Params& p, int item, int) {
       qacc = 0.0;
       rt = row_tile(p, item);
       s0 = sub0(p, item);
+      pol = l2_evict_first_policy();
     }
     __device__ void sub_begin(const Params& p, int, int sub, int) {
       if (sub % p.NT == 0) qacc = 0.0;
@@ -271,7 +281,7 @@ struct G2 {
           split8x2(FMT, &v[g * 8], pa);
           split8x2(FMT, &v[g * 8 + 8], pb);
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) store16<true>(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl]);
+          for (int pl = 0; pl < 2; ++pl) store16(p.tp, pl, r, col0 + g * 8, pa[pl], pb[pl], pol);
         }
       }
     }

@@ -19,9 +19,14 @@ def load_golden(name):
     jitter, maxjitter = float(d["jitter"]), int(d["maxjitter"])
     if "u_scale_tril" in d.files:
         S = t("u_scale_tril").float()
-    else:  # C1: constructor init, sparse_gdrf.py:100-110
-        K = t("u_loc").shape[0]
-        L, _ = jittercholesky(kernel_matrix(kernel, Z, Z, var, ls), Z.shape[0], jitter, maxjitter)
+    else:  # C1: constructor init, sparse_gdrf.py:100-110 -- one fp32 factor shared by the K topics
+        K, M = t("u_loc").shape
+        if "u_scale_tril_shared_tril" in d.files:      # as computed when the fixture was made (not reproducible across
+            L = torch.zeros(M, M)                      # hosts: an fp32 Cholesky at the edge of positive definiteness)
+            il = np.tril_indices(M)
+            L[il[0], il[1]] = t("u_scale_tril_shared_tril").float()
+        else:
+            L, _ = jittercholesky(kernel_matrix(kernel, Z, Z, var, ls), M, jitter, maxjitter)
         S = L.expand(K, *L.shape).contiguous()
     inp = OracleInputs(xs=t("xs").float(), ws=t("ws").int(), Z=Z, variance=var, lengthscale=ls,
                        u_loc=t("u_loc").float(), u_scale_tril=S, noise=t("noise").float(),
