@@ -1,4 +1,7 @@
-# A/B of the L2 cache-hint flags on one box: bash tools/ab_l2.sh 0 524288 1572864   (GDRF_BENCH_FLAGS values)
+# A/B of GDRF_BENCH_FLAGS values on one box, with the DRAM bytes of the big contractions from an ncu metrics pass:
+#   bash tools/ab_l2.sh 0 524288 1572864
+# (used for the L2 cache-hint experiments of round 2 on builds that carried the hints behind flag bits 19 / 20:
+#  profiles/r02b_ab_l2_*.txt; the store-side hint that worked is now unconditional, the flag bits are gone)
 mkdir -p gpurun_out
 bash tools/ab_flags.sh "$@" "$@"
 for f in "$@"; do
