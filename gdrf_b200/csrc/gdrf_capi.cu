@@ -890,7 +890,11 @@ int chunk_backward(StepCtx& c, const float* xs_chunk, int nc, int RT) {
     }
   }
   {
-    const int rows_per_cta = 128;   // one 128 x 128 block per CTA: ~8 CTAs per SM hide the serial row loop
+    // one 128-column x rows_per_cta block per CTA, a serial row loop per thread: ~8 CTAs per SM hide its latency.  With
+    // few inducing points (M = 256: two column blocks) 128 rows per CTA left two CTAs per SM and the kernel at 55 us per
+    // chunk whatever M; fewer rows per CTA then
+    int rows_per_cta = 128;
+    while (rows_per_cta > 32 && (long long)p.MT * ((nc + rows_per_cta - 1) / rows_per_cta) < 6LL * sms) rows_per_cta >>= 1;
 #define GDRF_KXZ_BACKWARD(DT, KID)                                                                  \
 k_kxz_backward<DT, KID><<<dim3(p.MT, (nc + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(      \
     dwf, Mp, xs_chunk, nc, in->z, M, hp, rows_per_cta, at<double>(ws, p.dz), acc)
