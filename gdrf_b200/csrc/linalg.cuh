@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(NB * NB) k_chol_step_both(double* __restrict__
 
 // Batched status probe (jittercholesky's "does this level fail?", utils.py:31-37, for SEVERAL jitter levels at once):
 // blockIdx.z / blockIdx.x selects the level; every level has its own fp32 Kuu, L, Dinv and status word, `stride`
-// (matrices), `dstride` (Dinv) elements apart.  The levels are independent, so the batch costs one launch chain -- the
-// chain is latency-bound on the 32 x 32 diagonal factorisations -- instead of one chain and one host read-back per level.
+// (matrices), `dstride` (Dinv) elements apart.  The levels are independent, so the batch is ONE launch chain -- latency-bound
+// on the 32 x 32 diagonal factorisations for small M -- instead of one chain and one host read-back per level.
 __global__ void __launch_bounds__(NB * NB) k_chol_diag_batch(const float* __restrict__ A, float* __restrict__ L,
                                                              float* __restrict__ Dinv, int Mp, int kb, long long stride,
                                                              long long dstride, int* __restrict__ status) {

@@ -137,8 +137,9 @@ class _Call:
 
         The reference walks the levels one by one, each a try/except around an fp32 ``torch.linalg.cholesky``.  Here a
         failing level 0 is followed by ONE batched probe of the remaining levels (``gdrf_jitter_probe``: the levels are
-        independent and a factorisation is a latency-bound launch chain, so eight levels cost what one does) and the full
-        prologue at the first level that passes.  A model that keeps landing on level L > 0 (C1 at the reference's
+        independent and a factorisation is a latency-bound launch chain, so eight levels cost little more than one: 0.71 ms
+        against 0.63 ms for a full prologue at M = 625, 1.33 against 0.96 ms at M = 1024) and the full prologue at the first
+        level that passes.  A model that keeps landing on level L > 0 (C1 at the reference's
         defaults: L = 5 on every step) is met by speculation: the probe of levels 0 .. L-1 and the full prologue at L are
         queued back to back and read back together -- one host synchronisation per step; if the guess does not hold
         (a lower level passes now, or L fails) the general search runs.  The level returned is always the reference's."""

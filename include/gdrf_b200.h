@@ -139,8 +139,9 @@ int gdrf_prologue(const gdrf_shape* shape, const gdrf_inputs* in, double jitter,
  * torch.linalg.cholesky) answered for `count` <= GDRF_PROBE_MAX consecutive levels njitter_first, njitter_first + 1, ...
  * in ONE launch chain: dev_status[i] (DEVICE int[count]) = 0 when the reference's fp32 factorisation of
  * Kuu + (sum_{t <= njitter_first + i} jitter 10^t) I succeeds, 1 + the failing column otherwise.  The levels are
- * independent and the chain is latency-bound, so the batch costs what one level does.  Writes only its own scratch in
- * the workspace: a completed gdrf_prologue on the same workspace stays valid.                                    */
+ * independent and the chain is latency-bound, so the batch costs little more than one level (eight levels: 0.71 ms at
+ * m = 625, 1.33 ms at m = 1024).  Writes only its own scratch in the workspace: a completed gdrf_prologue on the same
+ * workspace stays valid.                                                                                          */
 #define GDRF_PROBE_MAX 8
 int gdrf_jitter_probe(const gdrf_shape* shape, const gdrf_inputs* in, double jitter, int njitter_first, int count,
                       void* workspace, size_t workspace_bytes, gdrf_stream_t stream, int* dev_status);
