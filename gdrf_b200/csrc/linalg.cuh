@@ -322,7 +322,7 @@ inline int tri_inverse(const double* L, const double* Dinv, double* X, double* T
 }
 
 // ---------------------------------------------------------------------------------------------
-// C = op(A) * op(B), square [Mp][Mp] fp64, 64 x 64 tile per CTA, 4 x 4 per thread.
+// C = op(A) * op(B), square [Mp][Mp] fp64, 128 x 128 tile per CTA, 8 x 8 per thread.
 // The Cholesky adjoint only multiplies triangular matrices: KSTART says where the contraction index can start for
 // a tile (0: 0, 1: the tile's first row, 2: its first column, 3: the larger of the two) and LOWER_ONLY skips the
 // tiles strictly above the diagonal (their values are discarded by the caller's tril).  The contraction range of a
@@ -332,47 +332,58 @@ inline int tri_inverse(const double* L, const double* Dinv, double* X, double* T
 template <bool TA, bool TB, int KSTART, bool LOWER_ONLY>
 __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
                                                double* __restrict__ C, int Mp) {
-  __shared__ double as[16][65], bs[16][65];
+  // 128 x 128 tile per CTA, 8 x 8 per thread (rows ty + 16 u, columns tx + 16 v: a warp reads 16 consecutive doubles of
+  // each operand row, conflict-free), k in steps of 8.  One shared-memory load per four multiply-adds: the 64 x 64 /
+  // 4 x 4 version (one per two) was bound by shared-memory bandwidth at ~5.7 TFLOP/s.
+  constexpr int BM = 128, BK = 8, LD = BM + 2;
+  __shared__ double as[BK][LD], bs[BK][LD];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BM;
   if (LOWER_ONLY && j0 > i0) return;
   const int kfirst = KSTART == 0 ? 0 : (KSTART == 1 ? i0 : (KSTART == 2 ? j0 : max(i0, j0)));
-  const int steps = (Mp - kfirst) / 16, per = (steps + gridDim.z - 1) / gridDim.z;
-  const int kbeg = kfirst + 16 * per * blockIdx.z, kend = min(Mp, kbeg + 16 * per);
+  const int steps = (Mp - kfirst) / BK, per = (steps + gridDim.z - 1) / gridDim.z;
+  const int kbeg = kfirst + BK * per * blockIdx.z, kend = min(Mp, kbeg + BK * per);
   if (kbeg >= kend) return;
-  double acc[4][4] = {};
-  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+  double acc[8][8] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * 64; t += 256) {
-      const int kk = t >> 6, e = t & 63;
-      as[kk][e] = TA ? A[(long long)(k0 + kk) * Mp + i0 + e] : A[(long long)(i0 + e) * Mp + k0 + kk];
-      bs[kk][e] = TB ? B[(long long)(j0 + e) * Mp + k0 + kk] : B[(long long)(k0 + kk) * Mp + j0 + e];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + 256 * q;
+      if (TA) { const int e = idx & (BM - 1), kk = idx >> 7; as[kk][e] = A[(long long)(k0 + kk) * Mp + i0 + e]; }
+      else    { const int kk = idx & (BK - 1), e = idx >> 3; as[kk][e] = A[(long long)(i0 + e) * Mp + k0 + kk]; }
+      if (TB) { const int kk = idx & (BK - 1), e = idx >> 3; bs[kk][e] = B[(long long)(j0 + e) * Mp + k0 + kk]; }
+      else    { const int e = idx & (BM - 1), kk = idx >> 7; bs[kk][e] = B[(long long)(k0 + kk) * Mp + j0 + e]; }
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      double a[4], b[4];
+    for (int kk = 0; kk < BK; ++kk) {
+      double a[8], b[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a[u] = as[kk][ty * 4 + u];
-        b[u] = bs[kk][tx * 4 + u];
+      for (int u = 0; u < 8; ++u) {
+        a[u] = as[kk][ty + 16 * u];
+        b[u] = bs[kk][tx + 16 * u];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+        for (int v = 0; v < 8; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < 8; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) atomicAdd(&C[(long long)(i0 + ty * 4 + u) * Mp + j0 + tx * 4 + v], acc[u][v]);
+    for (int v = 0; v < 8; ++v) atomicAdd(&C[(long long)(i0 + ty + 16 * u) * Mp + j0 + tx + 16 * v], acc[u][v]);
 }
 
 template <bool TA, bool TB, int KSTART = 0, bool LOWER_ONLY = false>
 inline void dgemm(const double* A, const double* B, double* C, int Mp, cudaStream_t st) {
   cudaMemsetAsync(C, 0, sizeof(double) * (size_t)Mp * Mp, st);
-  k_dgemm<TA, TB, KSTART, LOWER_ONLY><<<dim3(Mp / 64, Mp / 64, 4), 256, 0, st>>>(A, B, C, Mp);
+  // split the contraction so that the tiles (half of them skipped when only the lower part is wanted) fill the SMs
+  const int tiles = (Mp / 128) * (Mp / 128);
+  int z = (2 * 148 + tiles - 1) / tiles;
+  z = z < 1 ? 1 : (z > 16 ? 16 : z);
+  k_dgemm<TA, TB, KSTART, LOWER_ONLY><<<dim3(Mp / 128, Mp / 128, z), 256, 0, st>>>(A, B, C, Mp);
 }
 
 // mode 0: X <- -tril(X)      mode 1: X <- tril(X) with the diagonal halved  (the Phi of the Cholesky adjoint)
