@@ -151,6 +151,39 @@ def test_marginal_moments_vjp_matches_autograd_of_the_oracle():
                 mine, r64, r32 = mine.tril(), r64.tril(), r32.tril()
             rows[k] = (O.rel_err(mine, r64), O.rel_err(r32, r64), O.rel_err(mine, r32))
         assert_parity(rows, f"moments vjp {kw['kernel']}")
+    # more than 64 topics (two g_loc column blocks ride in G5), and a u_scale_tril outside the fp16 range: the VJP's own
+    # prologue reports status -1 and the backward runs on the bf16 planes -- finite, and close to the oracle's
+    inp = O.make_problem(N=600, D=2, K=70, V=8, grid=[6, 6], kernel="rbf", seed=23)
+    for scale, tol in ((1.0, None), (3.0e4, 5e-3)):
+        big = O.OracleInputs(**{**inp.__dict__, "u_scale_tril": inp.u_scale_tril * scale})
+        K, N = big.u_loc.shape[0], big.xs.shape[0]
+        g = torch.Generator().manual_seed(5)
+        a, b = torch.randn(K, N, generator=g), (1e-2 / scale ** 2) * torch.randn(K, N, generator=g)
+        i64 = big.to(torch.float64)
+        p64 = {k: getattr(i64, k).clone().requires_grad_(True) for k in names}
+        fl, fv, _ = O._one_conditional(i64, p64)
+        g64 = torch.autograd.grad((a.double() * fl).sum() + (b.double() * fv).sum(), [p64[k] for k in names])
+        i32 = big.to(torch.float32)
+        p32 = {k: getattr(i32, k).clone().requires_grad_(True) for k in names}
+        fl32, fv32, _ = O._one_conditional(i32, p32)
+        g32 = torch.autograd.grad((a * fl32).sum() + (b * fv32).sum(), [p32[k] for k in names])
+        leaves = {k: getattr(big, k).to(_dev()).clone().requires_grad_(True) for k in names}
+        flc, fvc = marginal_moments_diff(big.xs.to(_dev()), leaves["Z"], leaves["variance"], leaves["lengthscale"],
+                                         leaves["u_loc"], leaves["u_scale_tril"], kernel=big.kernel, jitter=big.jitter,
+                                         maxjitter=big.maxjitter)
+        ((a.to(_dev()) * flc).sum() + (b.to(_dev()) * fvc).sum()).backward()
+        rows = {}
+        for k, r64, r32 in zip(names, g64, g32):
+            mine = leaves[k].grad.cpu().double()
+            assert torch.isfinite(mine).all(), (scale, k)
+            if k == "u_scale_tril":
+                mine, r64, r32 = mine.tril(), r64.tril(), r32.tril()
+            rows[k] = (O.rel_err(mine, r64), O.rel_err(r32, r64), O.rel_err(mine, r32))
+        if tol is None:
+            assert_parity(rows, "moments vjp K = 70")
+        else:       # 16-bit backward operands of the out-of-range fallback (include/gdrf_b200.h: GDRF_FLAG_FWD_BF16)
+            print("moments vjp, bf16 fallback", {k: tuple(f"{x:.1e}" for x in v) for k, v in rows.items()})
+            assert all(v[0] < tol for v in rows.values()), rows
 
 
 def test_max_jitter_raises_like_the_reference():
