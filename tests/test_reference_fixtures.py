@@ -229,3 +229,32 @@ def test_random_inducing_init_on_a_non_unit_world_matches_the_reference_construc
         ref = torch.from_numpy(d["random_init/" + k])
         assert mine[k].shape == ref.shape, k
         assert torch.allclose(mine[k].detach(), ref, rtol=1e-4, atol=2e-5), (k, (mine[k].detach() - ref).abs().max().item())
+
+
+@pytest.mark.gpu
+def test_double_scaled_world_with_particles_equals_the_mean_of_single_particle_runs():
+    """reference_double_scale=True (the reference guide's second scale(), sparse_gdrf.py:380) with eps[P, K, N]
+    (Trace_ELBO(num_particles=P, vectorize_particles=True)): loss and every gradient equal the mean over P single-particle
+    evaluations, and the fp64 oracle's (guide at scale(scale(xs)), model at scale(xs)) mean loss."""
+    spec, u, d = load_ref_fixture("ref_world2d")
+    xs, ws = torch.from_numpy(d["xs"]).cuda(), torch.from_numpy(d["ws"]).cuda()
+    P = 3
+    eps = torch.randn(P, spec["K"], spec["N"], generator=torch.Generator().manual_seed(17))
+
+    def run(e):
+        m = _dropin(spec, d, "cuda:0")
+        _load_params(m, d)
+        loss = -m.elbo(xs, ws, eps=e.cuda())
+        loss.backward()
+        return loss.item(), {k: p.grad.detach().cpu().double() for k, p in m.named_parameters()}
+    singles = [run(eps[p]) for p in range(P)]
+    loss, g = run(eps)
+    assert abs(loss - sum(s[0] for s in singles) / P) <= 1e-6 * abs(loss)
+    for k in g:
+        mean = sum(s[1][k] for s in singles) / P
+        assert O.rel_err(g[k], mean) < 5e-5, (k, O.rel_err(g[k], mean))
+    o64 = 0.0
+    for p in range(P):
+        _, params = ref_constrained(spec, u, d, torch.float64)
+        o64 += O.elbo_terms(ref_oracle_inputs(spec, params, d, eps[p]), params)["loss"].item() / P
+    assert abs(loss - o64) <= TERM_TOL * abs(o64)
