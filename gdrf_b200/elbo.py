@@ -75,6 +75,44 @@ def effective_jitter(jitter: float, njitter: int) -> float:
     return float(sum(jitter * (10 ** i) for i in range(njitter + 1)))
 
 
+def jitter_search(full, probe, speculate, maxjitter: int, hint: int, fp32_mode: bool, probe_max: int) -> int:
+    """The level ``jittercholesky`` (gdrf/models/utils.py:27-40) stops at -- the first njitter < maxjitter whose
+    factorisation succeeds -- found with as few launch chains and host read-backs as possible.  Pure host logic over three
+    callables (``_Call.prologue`` binds them to the C ABI; tests/test_host.py drives them with tables):
+
+    * ``full(nj)`` runs the full prologue at level nj and returns its status (0: factorised; > 0: failed);
+    * ``probe(first, count)`` returns the fp32 pass / fail statuses of levels first .. first + count - 1 from ONE batched
+      launch chain (count <= probe_max; only used when ``fp32_mode``: the reference's fp32 arithmetic decides);
+    * ``speculate(hint)`` queues the probe of levels 0 .. hint - 1 next to the full prologue at ``hint`` and returns
+      (status of the full prologue, statuses of the lower levels) from one read-back.
+
+    ``hint`` is the level the previous evaluation of a model of this shape landed on (0: none).  Whatever the hint, the
+    level returned is the reference's; RuntimeError with the reference's message when every level fails."""
+    known = {}                               # level -> status already established (> 0: fails)
+    if fp32_mode and 0 < hint < maxjitter and hint <= probe_max:
+        st_full, lower = speculate(hint)
+        known = {lvl: v for lvl, v in enumerate(lower)}
+        if all(v > 0 for v in known.values()):
+            if st_full == 0:
+                return hint
+            known[hint] = 1
+    nj = 0
+    while nj < maxjitter:
+        if known.get(nj, 0) > 0:             # known to fail
+            nj += 1
+            continue
+        if fp32_mode and nj > 0 and nj not in known:
+            count = min(probe_max, maxjitter - nj)
+            for i, v in enumerate(probe(nj, count)):
+                known[nj + i] = v
+            continue
+        if full(nj) == 0:
+            return nj
+        known[nj] = 1
+        nj += 1
+    raise RuntimeError("reached max jitter, covariance is unstable")
+
+
 class _Call:
     """Validated shapes + ctypes structs for one evaluation."""
 
@@ -157,9 +195,11 @@ class _Call:
                 st = int(status[0].item())
             return st
 
-        known = {}                           # level -> fp32 status already probed
-        hint = _JITTER_HINTS.get(key, 0)
-        if fp32_mode and 0 < hint < maxjitter and hint <= _lib.PROBE_MAX:
+        def probe(first, count):
+            self._probe(jitter, first, count, status[1:])
+            return status[1:1 + count].tolist()
+
+        def speculate(hint):
             # the probe (its own scratch region of the workspace) runs on a side stream next to the full prologue: both
             # are latency-bound chains of small launches
             main = torch.cuda.current_stream(self.device)
@@ -169,31 +209,13 @@ class _Call:
             self._full_prologue(jitter, hint, status)
             main.wait_stream(side)
             st = status[:1 + hint].tolist()  # one read-back for the probe and the prologue
-            known = {lvl: st[1 + lvl] for lvl in range(hint)}
-            if all(v > 0 for v in known.values()):
-                if st[0] == -1:
-                    self.shape.flags |= _lib.FLAG_FWD_BF16
-                    st[0] = full(hint)
-                if st[0] == 0:
-                    return hint
-                known[hint] = 1
-        nj = 0
-        while nj < maxjitter:
-            if known.get(nj, 0) > 0:         # known to fail
-                nj += 1
-                continue
-            if fp32_mode and nj > 0 and nj not in known:
-                count = min(_lib.PROBE_MAX, maxjitter - nj)
-                self._probe(jitter, nj, count, status[1:])
-                for i, v in enumerate(status[1:1 + count].tolist()):
-                    known[nj + i] = v
-                continue
-            if full(nj) == 0:
-                _JITTER_HINTS[key] = nj
-                return nj
-            known[nj] = 1
-            nj += 1
-        raise RuntimeError("reached max jitter, covariance is unstable")
+            if st[0] == -1 and all(v > 0 for v in st[1:]):
+                st[0] = full(hint)           # the guess holds but the planes have to be repacked as bf16
+            return st[0], st[1:]
+
+        nj = jitter_search(full, probe, speculate, maxjitter, _JITTER_HINTS.get(key, 0), fp32_mode, _lib.PROBE_MAX)
+        _JITTER_HINTS[key] = nj
+        return nj
 
     def step(self, want_grad: bool, terms=None, grad=None, extra_flags: int = 0):
         lib = _lib.load()

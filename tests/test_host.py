@@ -362,3 +362,50 @@ def test_streaming_epoch_shards_one_multiset_across_ranks():
     for sub in range(2):
         assert np.array_equal(np.concatenate([parts[r][sub] for r in range(3)]), whole[sub])
         assert [len(parts[r][sub]) for r in range(3)] == [13, 12, 12]
+
+
+def test_jitter_search_returns_the_reference_level_whatever_the_hint():
+    """elbo.jitter_search -- the host logic behind _Call.prologue -- against jittercholesky's plain loop
+    (gdrf/models/utils.py:27-40) for random pass / fail tables, every hint, with and without the fp32 decision; and the
+    number of launch chains / read-backs it spends in the cases it is built for."""
+    import random
+    from gdrf_b200.elbo import jitter_search
+    rng = random.Random(7)
+    for trial in range(3000):
+        maxjitter = rng.choice([1, 2, 3, 6, 9, 15, 20])
+        first_ok = rng.randrange(0, maxjitter + 2)                  # levels below it fail the fp32 factorisation
+        fp32_ok = [lvl >= first_ok or rng.random() < 0.1 for lvl in range(maxjitter)]
+        full_ok = [ok and rng.random() < 0.9 for ok in fp32_ok]     # the fp64 values may fail where the fp32 mirror passes
+        hint, fp32_mode = rng.randrange(0, 12), rng.random() < 0.8
+        calls = {"full": 0, "probe": 0, "speculate": 0}
+
+        def full(nj):
+            assert 0 <= nj < maxjitter
+            calls["full"] += 1
+            return 0 if full_ok[nj] else nj + 3
+
+        def probe(first, count):
+            assert fp32_mode and 0 < first and first + count <= maxjitter and 1 <= count <= 8
+            calls["probe"] += 1
+            return [0 if fp32_ok[lvl] else 1 + lvl for lvl in range(first, first + count)]
+
+        def speculate(h):
+            assert fp32_mode and 0 < h < maxjitter and h <= 8
+            calls["speculate"] += 1
+            return (0 if full_ok[h] else 5), [0 if fp32_ok[lvl] else 2 for lvl in range(h)]
+
+        expected = next((lvl for lvl in range(maxjitter) if full_ok[lvl]), None)
+        if expected is None:
+            with pytest.raises(RuntimeError, match="reached max jitter, covariance is unstable"):
+                jitter_search(full, probe, speculate, maxjitter, hint, fp32_mode, 8)
+            continue
+        assert jitter_search(full, probe, speculate, maxjitter, hint, fp32_mode, 8) == expected, (trial, fp32_ok, full_ok, hint)
+        if not fp32_mode:
+            assert calls == {"full": expected + 1, "probe": 0, "speculate": 0}      # the reference's loop, level by level
+        elif 0 < hint == expected <= 8 and not any(fp32_ok[:hint]):
+            assert calls == {"full": 0, "probe": 0, "speculate": 1}                 # the guess holds: one read-back
+        elif hint == 0 and expected == 0:
+            assert calls == {"full": 1, "probe": 0, "speculate": 0}                 # the common case: level 0 passes
+        elif hint == 0 and full_ok[expected] and all(full_ok[lvl] == fp32_ok[lvl] for lvl in range(expected)):
+            # cold escalation to level L: level 0, ceil(L / 8) batched probes, the full prologue at L
+            assert calls["full"] == 2 and calls["probe"] == (expected + 7) // 8 and calls["speculate"] == 0, calls
